@@ -1,0 +1,104 @@
+"""Generate golden fixtures from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference through oracle/refstub.py, runs the reference CPU GaussianProcess /
+MultiOutputGP on small seeded problems and stores inputs + outputs in tests/golden/*.npz.
+The fixtures travel to the GPU box; the reference does not.  Fixture sizes are kept small
+(a few hundred KB in total).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import refstub  # noqa: E402
+
+warnings.simplefilter("ignore")
+mogp = refstub.import_reference()
+from mogp_emulator.Kernel import SquaredExponential, Matern52  # noqa: E402
+from mogp_emulator.linalg.cholesky import jit_cholesky  # noqa: E402
+
+
+def workload(n, d, n_out, m, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    Y = np.stack([np.sin(2.0 * X.sum(axis=1) + k) + 0.01 * rng.standard_normal(n) for k in range(n_out)])
+    Xs = rng.random((m, d))
+    return X, Y, Xs
+
+
+def prior_params(gp):
+    corr = []
+    for p in gp.priors.corr:
+        corr.append([getattr(p, "shape", np.nan), getattr(p, "scale", np.nan)])
+    nug = gp.priors.nugget
+    nug = [getattr(nug, "shape", np.nan), getattr(nug, "scale", np.nan)] if nug is not None else [np.nan, np.nan]
+    return np.array(corr, dtype=np.float64), np.array(nug, dtype=np.float64)
+
+
+def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with_deriv=True):
+    X, Y, Xs = workload(n, d, 1, m, seed)
+    y = Y[0]
+    if dup_rows:
+        X[1] = X[0]
+        y[1] = y[0]
+    kern = SquaredExponential() if kernel == "SquaredExponential" else Matern52()
+    gp = mogp.GaussianProcess(X, y, kernel=kern, nugget=nugget)
+    gp.fit(theta)
+    mean, var, _ = gp.predict(Xs)
+    mean_nn, var_nn, _ = gp.predict(Xs, include_nugget=False)
+    out = dict(X=X, y=y, Xs=Xs, theta=np.array(theta), kernel=kernel,
+               nugget_in=np.array(nugget if not isinstance(nugget, str) else np.nan),
+               nugget_type=gp.nugget_type, nugget_out=np.array(gp.nugget),
+               K=gp.get_K_matrix(), L=gp.Kinv.L, Kinv_t=gp.Kinv_t, logpost=np.array(gp.current_logpost),
+               mean=mean, var=var, var_no_nugget=var_nn)
+    corr, nug = prior_params(gp)
+    out["prior_corr"] = corr
+    out["prior_nugget"] = nug
+    if with_deriv:
+        out["deriv"] = gp.logpost_deriv(theta)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "logpost", gp.current_logpost, "nugget", gp.nugget)
+
+
+def multi_case(name, n, d, n_out, m, seed, kernel, nugget, theta_scale):
+    X, Y, Xs = workload(n, d, n_out, m, seed)
+    rng = np.random.default_rng(seed + 1000)
+    n_params = d + 1 + (1 if nugget == "fit" else 0)
+    thetas = theta_scale * rng.standard_normal((n_out, n_params))
+    if nugget == "fit":
+        thetas[:, -1] = -12.0 + rng.standard_normal(n_out)
+    gp = mogp.MultiOutputGP(X, Y, kernel=kernel, nugget=nugget)
+    gp.fit(thetas)
+    mean, var, _ = gp.predict(Xs, processes=1)
+    logposts = np.array([em.current_logpost for em in gp.emulators])
+    nuggets = np.array([em.nugget for em in gp.emulators])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X, Y=Y, Xs=Xs, thetas=thetas, kernel=kernel,
+                        nugget_type=gp.emulators[0].nugget_type,
+                        nugget_in=np.array(nugget if not isinstance(nugget, str) else np.nan),
+                        mean=mean, var=var, logposts=logposts, nuggets=nuggets)
+    print(name, "logposts", logposts)
+
+
+if __name__ == "__main__":
+    # C1-shaped (BASELINE.json configs[0]) but n=200 to keep the stored L small
+    single_case("sqexp_fixed_n200_d4", 200, 4, 64, 0, "SquaredExponential", 1e-6, [1.0, 1.0, 1.0, 1.0, 0.0])
+    # spans two 128-blocks with ragged edge, non-trivial theta
+    single_case("sqexp_fixed_n150_d3", 150, 3, 40, 5, "SquaredExponential", 1e-4, [0.3, -0.5, 1.2, 0.7])
+    single_case("mat52_adaptive_n160_d5", 160, 5, 33, 3, "Matern52", "adaptive", [1.0, 0.5, 0.0, -0.5, 1.0, 0.2])
+    # duplicated rows force the jitter path (expected nugget = 1e-6 * sigma^2)
+    single_case("mat52_adaptive_dup_n96_d2", 96, 2, 20, 7, "Matern52", "adaptive", [0.5, 0.5, 0.4], dup_rows=True)
+    single_case("sqexp_adaptive_dup_n140_d3", 140, 3, 20, 8, "SquaredExponential", "adaptive", [1.0, 1.0, 1.0, -0.3],
+                dup_rows=True)
+    single_case("sqexp_fit_n100_d2", 100, 2, 25, 11, "SquaredExponential", "fit", [0.8, 1.1, 0.1, -9.0])
+    single_case("mat52_fit_n130_d3", 130, 3, 25, 12, "Matern52", "fit", [0.2, 0.4, 0.6, 0.3, -7.0])
+    single_case("sqexp_fixed_n1_d2", 1, 2, 5, 13, "SquaredExponential", 1e-6, [0.0, 0.0, 0.0], with_deriv=False)
+    single_case("sqexp_fixed_n2_d1", 2, 1, 6, 14, "SquaredExponential", 0.0, [0.5, 0.1], with_deriv=False)
+    multi_case("multi_sqexp_fixed_e4_n120_d3", 120, 3, 4, 30, 20, "SquaredExponential", 1e-6, 0.5)
+    multi_case("multi_mat52_adaptive_e3_n90_d2", 90, 2, 3, 17, 21, "Matern52", "adaptive", 0.5)
