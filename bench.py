@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Benchmark of the GP fit+predict hot path (BASELINE.json metric: "GP fit+predict sec").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c5|...]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU)
+
+A step = MultiOutputGP fit(thetas) + predict(Xs, unc=True) of the whole job.  Default workload = BASELINE.json
+configs[2] (C3): 32 outputs x n=4096 x d=10 SqExp, nugget 1e-6, 10000 test points -- the configuration the
+headline target is quoted on.  With N ranks the 32 outputs are block-partitioned (strong scaling) and predict
+ends with the single NCCL all-gather.  One JSON line on rank 0.
+
+  value : seconds per step with the design matrix and targets already resident in HBM (an existing emulator
+          object; per step only thetas / test points go in and posteriors come out)
+  e2e   : seconds per step through the public API from host arrays: construct the emulator (H2D of X, Y),
+          fit, predict, posteriors back on the host
+  --impl reference : the reference's CPU algorithm (oracle port of mogp_emulator's numpy/scipy path) timed on
+          this box's host cores on a bounded sample (one output per step, scaled to the job)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (outputs, n, d, m, kernel, nugget, seed)      SURVEY.md section 8d
+    "c1": (1, 256, 4, 1000, "SquaredExponential", 1.0e-6, 0),
+    "c3": (32, 4096, 10, 10000, "SquaredExponential", 1.0e-6, 2),
+    "c4": (1, 16384, 20, 1000, "Matern52", "adaptive", 3),
+    "c5": (256, 8192, 15, 10000, "SquaredExponential", 1.0e-6, 4),
+    "tiny": (4, 512, 5, 700, "SquaredExponential", 1.0e-6, 9),
+}
+
+
+def make_workload(n, d, n_out, m, seed):
+    """X~U[0,1)^d, Y[k] = sin(2*sum(x)+k) + 0.01*N(0,1), Xs~U[0,1)^d."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    Y = np.stack([np.sin(2.0 * X.sum(axis=1) + k) + 0.01 * rng.standard_normal(n) for k in range(n_out)])
+    Xs = rng.random((m, d))
+    return X, Y, Xs
+
+
+def make_thetas(n_out, d):
+    """theta_corr = 1 + 0.01*k (a distinct kernel matrix per output, as after a MAP fit), theta_cov = 0."""
+    thetas = np.zeros((n_out, d + 1))
+    thetas[:, :d] = 1.0 + 0.01 * np.arange(n_out)[:, None]
+    return thetas
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_step(X, y, Xs, theta, kernel, nugget):
+    """One output of the job on the CPU with the reference's algorithm (oracle port)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gp_oracle as orc
+    t0 = time.perf_counter()
+    gp = orc.OracleGP(X, y, kernel=kernel, nugget=nugget, priors="weak", chunked=X.shape[0] > 8192).fit(theta)
+    mean, var = gp.predict(Xs)
+    return time.perf_counter() - t0, mean, var
+
+
+def run_reference(args, wl):
+    """--impl reference: the CPU path on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    E, n, d, m, kernel, nugget, seed = wl
+    X, Y, Xs = make_workload(n, d, min(E, args.warmup + args.steps + 1), m, seed)
+    thetas = make_thetas(E, d)
+    times = []
+    for s in range(args.warmup + args.steps):
+        k = s % Y.shape[0]
+        dt, _, _ = oracle_step(X, Y[k], Xs, thetas[k], kernel, nugget)
+        if s >= args.warmup:
+            times.append(dt)
+    per_output = float(np.mean(times))
+    value = per_output * E
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "gp_fit_predict_seconds", "value": value, "unit": "s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, wl, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "port",
+                         "sample": "each step = fit+predict of 1 of the %d outputs (n=%d, m=%d) with the oracle port of the "
+                                   "reference's numpy/scipy path on all host cores; value = mean step time x %d outputs "
+                                   "(outputs are independent; the reference's MultiOutputGP.fit is a serial loop)" % (E, n, m, E)},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, wl, gpus):
+    E, n, d, m, kernel, nugget, seed = wl
+    return {"workload": "%s: MultiOutputGP %d outputs x n=%d x d=%d %s, nugget=%s, fit(thetas)+predict(%d points, unc=True)"
+                        % (name, E, n, d, kernel, nugget, m),
+            "outputs": E, "n": n, "d": d, "m": m, "kernel": kernel, "nugget": nugget, "seed": seed,
+            "parallelism": "outputs block-partitioned over %d rank(s), one all-gather of posteriors" % gpus,
+            "l2_policy": "working set (%.1f GB of factors + workspace per step) exceeds the 126 MB L2; no flush needed"
+                         % (E * n * n * 8 / 1e9)}
+
+
+def run_b200(args, wl):
+    from mogp_emulator_b200 import MultiOutputGP_GPU, libmogp
+    from mogp_emulator_b200.rendezvous import init_comm, env_rank_world
+    from mogp_emulator_b200.sharding import shard_bounds
+
+    rank, world, local_rank = env_rank_world()
+    if not libmogp.gpu_usable():
+        raise RuntimeError("bench.py: libmogp_b200 not loaded or no sm_100 device: " + libmogp.last_error())
+    E, n, d, m, kernel, nugget, seed = wl
+    X, Y, Xs = make_workload(n, d, E, m, seed)
+    thetas = make_thetas(E, d)
+    comm = init_comm(local_rank)
+    device = local_rank
+
+    def sync_max(t):
+        return comm.allreduce_max(t) if comm is not None else t
+
+    def barrier():
+        if comm is not None:
+            comm.allreduce_max(0.0)
+
+    def step(gp):
+        gp.fit(thetas)
+        return gp.predict(Xs, unc=True)
+
+    gp = MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget, device=device, comm=comm)
+    lo, hi, _ = shard_bounds(E, rank, world)
+    for _ in range(args.warmup):
+        res = step(gp)
+    gp.timings(reset=True)
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step(gp)
+    elapsed = time.perf_counter() - t0     # every call synchronises its device before returning
+    barrier()
+    elapsed = sync_max(elapsed)
+    tm = gp.timings(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    per_step = elapsed / args.steps
+
+    # end to end from host arrays: construct (H2D of X and Y) + fit + predict (+ gather) + posteriors on the host
+    del gp
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gp2 = MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget, device=device, comm=comm)
+        res2 = step(gp2)
+        del gp2
+    e2e = sync_max((time.perf_counter() - t0) / e2e_steps)
+
+    if rank != 0:
+        return
+    e_loc = hi - lo
+    trsm_flops = float(e_loc) * n * n * m            # minimal count: one triangular solve per test point
+    n_trsm = max(tm["n_trsm"], 1.0)
+    trsm_ms = tm["trsm_ms"] / n_trsm
+    units_per_launch = tm["n_trsm"] and (e_loc * args.steps / tm["n_trsm"])
+    peak = libmogp.peak_dmma_tflops(device)
+    achieved = trsm_flops * args.steps / tm["n_trsm"] / (trsm_ms * 1e-3) * 1e-12 if tm["n_trsm"] else None
+    line = {
+        "metric": "gp_fit_predict_seconds", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, wl, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "s",
+                "h2d_bytes_per_step": int(8 * (X.size + Y[lo:hi].size + thetas[lo:hi].size + Xs.size)),
+                "d2h_bytes_per_step": int(8 * 2 * m * (E if world > 1 else e_loc) + 8 * 4 * e_loc)},
+        "gpu_launches": int(tm["n_launches"]),
+        "roofline": {"bound": "tensor", "kernel": "predict_trsm_kernel (V = L^-1 K*, DMMA)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": "DMMA issue peak measured in this run (mogp_peak_dmma); MEASURED_PEAKS.json has "
+                                    "no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 36.1 TFLOP/s",
+                     "flops_per_launch": trsm_flops * args.steps / tm["n_trsm"] if tm["n_trsm"] else None,
+                     "ms_per_launch": trsm_ms, "outputs_per_launch": units_per_launch},
+        "phases_ms_per_step": {"fit_all_outputs": tm["fit_ms"] / args.steps, "kstar_and_mean": tm["kstar_ms"] / args.steps,
+                               "predict_trsm": tm["trsm_ms"] / args.steps},
+        "fit_tflops": (e_loc * (n ** 3) / 3.0) / (tm["fit_ms"] / args.steps * 1e-3) * 1e-12 if tm["fit_ms"] else None,
+    }
+    if world == 1 and not args.no_cpu:
+        # bounded CPU sample on the same box: one output of the job with the oracle port of the reference
+        dt, cmean, cvar = oracle_step(X, Y[0], Xs, thetas[0], kernel, nugget)
+        line["cpu_baseline"] = {"value": dt * E, "unit": "s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "fit+predict of output 0 only (%.2f s on %d host cores), scaled x%d outputs"
+                                          % (dt, os.cpu_count(), E)}
+        gmean, gvar = res.mean[0], res.unc[0]
+        line["parity_vs_cpu_sample"] = {"mean_max_rel": float(np.max(np.abs(gmean - cmean)) / np.max(np.abs(cmean))),
+                                        "var_max_abs": float(np.max(np.abs(gvar - cvar)))}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

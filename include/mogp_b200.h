@@ -1,0 +1,118 @@
+/* libmogp_b200 -- C ABI of the B200-native GP fit+predict hot path.
+ *
+ * Drop-in boundary: these entry points are what the reference's Python front-ends
+ * (mogp_emulator/GaussianProcessGPU.py, MultiOutputGP_GPU.py, fitting.py) obtain today from the
+ * pybind11 module `libgpgpu` (mogp_gpu/src/bindings.cu).  Each function names the reference
+ * interface it replaces.  Plain pointers and sizes only; the caller allocates every output
+ * (the reference's Eigen::Ref convention, GaussianProcessGPU.py:476-490, 604-612); the library
+ * never keeps a caller pointer after the call returns.  All arrays are C-order float64.
+ *
+ * All functions return an int status (MOGP_OK == 0).  mogp_last_error() gives the message of the
+ * last failure on the calling thread.  A handle is not re-entrant.
+ */
+#ifndef MOGP_B200_H
+#define MOGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+enum {
+    MOGP_OK = 0,
+    MOGP_ERR_CUDA = 1,     /* CUDA runtime/driver failure (no device, launch error, ...)          */
+    MOGP_ERR_ARG = 2,      /* bad argument (reference: std::runtime_error, densegp_gpu.hpp:495)    */
+    MOGP_ERR_NOT_PD = 3,   /* factorisation failed (densegp_gpu.hpp:556-570, cholesky.py:219,281)  */
+    MOGP_ERR_NOT_FIT = 4,  /* predict/get on an output whose hyperparameters are not set           */
+    MOGP_ERR_NCCL = 5,
+    MOGP_ERR_NOMEM = 6
+};
+
+/* mogp_gpu/src/types.hpp:29-33 -- the numeric values are part of the reference's Python contract
+ * (MultiOutputGP_GPU.py:74-79). */
+enum { MOGP_NUG_ADAPTIVE = 0, MOGP_NUG_FIT = 1, MOGP_NUG_FIXED = 2 };
+enum { MOGP_KERNEL_SQEXP = 0, MOGP_KERNEL_MATERN52 = 1 };
+
+/* selectors for mogp_get */
+enum { MOGP_GET_K = 0, MOGP_GET_L = 1, MOGP_GET_ALPHA = 2, MOGP_GET_KINV = 3 };
+
+typedef struct mogp_handle mogp_handle; /* one emulator bank: E outputs over shared inputs, on one GPU */
+typedef struct mogp_comm mogp_comm;     /* one NCCL communicator rank                                  */
+
+/* replaces libgpgpu.have_compatible_device (mogp_gpu/src/util.cu, bindings.cu:600). */
+int mogp_device_count(int32_t* count);
+
+const char* mogp_last_error(void);
+
+/* replaces DenseGP_GPU(inputs, targets, testing_size, meanfunc, kernel, nugget_type, nugsize)
+ * (densegp_gpu.hpp:777-802) and MultiOutputGP_GPU(inputs, targets[], ...) (multioutputgp_gpu.hpp:
+ * 259-265).  X is (n, d); Y is (n_out, n); zero mean function.  The handle owns device copies.
+ * n_streams <= 0 picks a default (one GP per stream, up to 16 streams). */
+int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t n_out, int32_t kernel,
+                int32_t nugget_type, double nugget, int32_t device, int32_t n_streams, mogp_handle** out);
+int mogp_destroy(mogp_handle* h);
+
+/* replaces DenseGP_GPU::fit(theta) (densegp_gpu.hpp:493-612) / MultiOutputGP_GPU::fit(thetas),
+ * fit_emulator(idx, theta) (multioutputgp_gpu.hpp:150-181); semantics follow the CPU
+ * GaussianProcess.fit (GaussianProcess.py:629-685) and cholesky_factor / jit_cholesky
+ * (linalg/cholesky.py:168-281).
+ * thetas: (count, n_params) raw hyperparameters [theta_corr(d), theta_cov, (theta_nugget)] for
+ * outputs first..first+count-1.  Per output it reports
+ *   quad   = y^T K^-1 y,   logdet = log det(K + nugget I),   nugget = the nugget actually used,
+ *   status = MOGP_OK | MOGP_ERR_NOT_PD (that output is then marked not fit; others proceed).
+ * The data part of the reference's current_logpost is 0.5*(quad + logdet + n*log(2 pi)); priors are
+ * host-side scalars added by the caller.  Return value is MOGP_OK unless the call itself failed. */
+int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas, int32_t n_params,
+             double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out);
+
+/* marks outputs not fit (MultiOutputGP_GPU.reset_fit_status, GaussianProcessGPU theta=None). idx<0: all */
+int mogp_reset(mogp_handle* h, int32_t idx);
+int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out);
+
+/* replaces DenseGP_GPU::predict_batch / predict_variance_batch (densegp_gpu.hpp:300-408) and
+ * MultiOutputGP_GPU::predict_batch / predict_variance_batch (multioutputgp_gpu.hpp:183-228);
+ * values follow the CPU GaussianProcess.predict (GaussianProcess.py:889-920): variance clipped at 0.
+ * Xs: (m, d).  mean, var: (n_out, m) caller-allocated; var may be NULL when want_var == 0.
+ * status: (n_out) -- MOGP_ERR_NOT_FIT rows are filled with NaN (MultiOutputGP.py:476-546). */
+int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, int32_t include_nugget,
+                 double* mean, double* var, int32_t* status);
+
+/* Sharded multi-output predict: every rank predicts its own outputs, then ONE ncclAllGather of the
+ * packed per-rank [e_pad][2][m] block delivers all ranks' means and variances to every rank.
+ * mean_all, var_all: (world * e_pad, m); status_all: (world * e_pad) (MOGP_ERR_ARG marks padding rows). */
+int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, int64_t m, int32_t include_nugget,
+                           int32_t e_pad, double* mean_all, double* var_all, int32_t* status_all);
+
+/* replaces DenseGP_GPU::get_K / get_cholesky_lower / get_invQt / get_invQ (densegp_gpu.hpp:478,624-637).
+ * K, L, KINV: (n, n) row-major (L lower-triangular, upper zero); ALPHA: (n). */
+int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out);
+
+/* replaces DenseGP_GPU::logpost_deriv (densegp_gpu.hpp:663-770); formula of the CPU
+ * GaussianProcess.logpost_deriv (GaussianProcess.py:711-782) for zero mean, evaluated at the theta of
+ * the last mogp_fit of output idx:  grad[i] = 0.5*(tr(K^-1 dK_i) - alpha^T dK_i alpha), i over
+ * [corr(d), cov, (nugget)].  Prior terms are added by the caller. */
+int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params);
+
+/* accumulated device time per phase in ms since the last call with reset != 0:
+ * out[0..7] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches */
+int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset);
+
+/* NCCL plumbing (no reference equivalent: the reference is single-device, multioutputgp_gpu.hpp:183). */
+int mogp_comm_unique_id(char* out128);
+int mogp_comm_create(const char* uid128, int32_t rank, int32_t world, int32_t device, mogp_comm** out);
+int mogp_comm_destroy(mogp_comm* c);
+/* max-reduce of one double over ranks + barrier (bench timing). */
+int mogp_comm_allreduce_max(mogp_comm* c, double* value);
+
+/* measured FP64 tensor-pipe (DMMA) issue peak of `device` in TFLOP/s: the roofline denominator bench.py uses
+ * (MEASURED_PEAKS.json has no FP64 entry). */
+int mogp_peak_dmma(int32_t device, int32_t iters, double* tflops);
+
+int mogp_version(int32_t* major, int32_t* minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOGP_B200_H */

@@ -1,0 +1,257 @@
+"""``MultiOutputGP_GPU`` -- drop-in for the reference class of the same name
+(mogp_emulator/MultiOutputGP_GPU.py:27-382): E independent GPs over shared inputs.
+
+One libmogp_b200 handle holds this rank's outputs; ``fit`` runs one GP per CUDA stream, ``predict`` is one
+batched launch per phase.  With a communicator (``comm=``) the outputs are block-partitioned over the ranks
+(one process per GPU) and ``predict`` ends with a single NCCL all-gather of the packed means/variances, so
+every rank returns the full ``(n_emulators, n_predict)`` arrays.  Values follow the CPU ``MultiOutputGP``
+(MultiOutputGP.py:182-319, 331-459).
+"""
+import numpy as np
+
+from . import libmogp
+from .GaussianProcessGPU import PredictResult, GPUUnavailableError, _check_mean
+from .hyper import GPParams, GPPriors, make_priors
+from .kernels import interpret_kernel
+from .sharding import shard_bounds
+
+
+class MultiOutputGP_GPU(object):
+    def __init__(self, inputs, targets, mean=None, kernel="SquaredExponential", priors=None, nugget="adaptive",
+                 inputdict={}, use_patsy=True, batch_size=16000, device=0, comm=None, n_streams=0):
+        if not libmogp.HAVE_LIBMOGP:
+            raise RuntimeError("Cannot construct MultiOutputGP_GPU: the GPU library (libmogp_b200) could not be "
+                               "loaded: " + libmogp.last_error())
+        if not libmogp.gpu_usable():
+            raise RuntimeError("Cannot construct MultiOutputGP_GPU: a compatible GPU could not be found")
+        inputs = np.array(inputs, dtype=np.float64)
+        targets = np.array(targets, dtype=np.float64)
+        if inputs.ndim == 1:
+            inputs = np.reshape(inputs, (-1, 1))
+        if targets.ndim == 1:
+            targets = np.reshape(targets, (1, -1))
+        elif targets.ndim != 2:
+            raise ValueError("targets must be either a 1D or 2D array")
+        if inputs.ndim != 2:
+            raise ValueError("inputs must be either a 1D or 2D array")
+        if inputs.shape[0] != targets.shape[1]:
+            raise ValueError("the first dimension of inputs must be the same length as the second dimension of "
+                             "targets (or first if targets is 1D))")
+        if isinstance(nugget, str):
+            if nugget == "adaptive":
+                nugtype, nugsize = libmogp.nugget_type.adaptive, 0.0
+            elif nugget == "fit":
+                nugtype, nugsize = libmogp.nugget_type.fit, 0.0
+            else:
+                raise ValueError("nugget must be a string set to 'adaptive', 'fit', or a float")
+        elif isinstance(nugget, (float, int)) and not isinstance(nugget, bool):
+            if nugget < 0.0:
+                raise ValueError("nugget parameter must be non-negative")
+            nugtype, nugsize = libmogp.nugget_type.fixed, float(nugget)
+        else:
+            raise TypeError("nugget parameter must be a string or a non-negative float")
+        _check_mean(mean)
+        self._inputs = np.ascontiguousarray(inputs)
+        self._targets = np.ascontiguousarray(targets)
+        self._nugget_type = nugtype
+        self._nugget_size = nugsize
+        self.kernel_type, self.kernel = interpret_kernel(kernel)
+        self._comm = comm
+        E = self._targets.shape[0]
+        rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+        self._lo, self._hi, self._e_pad = shard_bounds(E, rank, world)
+        self._handle = None
+        if self._hi > self._lo:
+            self._handle = libmogp.Handle(self._inputs, self._targets[self._lo:self._hi], self.kernel_type, nugtype,
+                                          nugsize, device=device, n_streams=n_streams)
+        self._thetas = [GPParams(self.D, self.nugget_type, nugsize if nugtype == libmogp.nugget_type.fixed else None)
+                        for _ in range(E)]
+        self._logpost_data = [None] * E
+        self._fit = [False] * E
+        if isinstance(priors, (GPPriors, dict)) or priors is None:
+            priorslist = E * [priors]
+        else:
+            priorslist = list(priors)
+            assert len(priorslist) == E, "Bad length for list provided for priors to MultiOutputGP"
+        shared_default = None
+        self._priors = []
+        for p in priorslist:
+            if p is None:
+                if shared_default is None:
+                    shared_default = make_priors(None, self._inputs, self.D, self.nugget_type)
+                self._priors.append(shared_default)
+            else:
+                self._priors.append(make_priors(p, self._inputs, self.D, self.nugget_type))
+
+    # -- properties (MultiOutputGP_GPU.py:146-180) ------------------------------------------------------
+    @property
+    def inputs(self):
+        return self._inputs
+
+    @property
+    def targets(self):
+        return self._targets
+
+    @property
+    def D(self):
+        return self._inputs.shape[1]
+
+    @property
+    def n(self):
+        return self._inputs.shape[0]
+
+    @property
+    def nugget_type(self):
+        return self._nugget_type.name
+
+    @property
+    def nugget(self):
+        """Nugget of each emulator: the fixed value, or what the last fit used (0.0 before any fit)."""
+        if self._nugget_type == libmogp.nugget_type.fixed:
+            return self._nugget_size
+        return [0.0 if t.nugget is None else t.nugget for t in self._thetas]
+
+    @property
+    def n_emulators(self):
+        return self._targets.shape[0]
+
+    @property
+    def n_params(self):
+        return [t.n_data for t in self._thetas]
+
+    @property
+    def n_corr(self):
+        return [self.D] * self.n_emulators
+
+    @property
+    def priors(self):
+        return self._priors
+
+    @property
+    def thetas(self):
+        return self._thetas
+
+    @property
+    def local_range(self):
+        """[lo, hi) -- the outputs held by this rank."""
+        return self._lo, self._hi
+
+    def reset_fit_status(self):
+        if self._handle is not None:
+            self._handle.reset(-1)
+        for i in range(self.n_emulators):
+            self._fit[i] = False
+            self._thetas[i].unset_data()
+            self._logpost_data[i] = None
+
+    # -- fitting (MultiOutputGP_GPU.py:309-326; CPU semantics MultiOutputGP.py:331-360) -----------------
+    def _record(self, index, theta, quad, logdet, nug, status):
+        if status == libmogp.OK:
+            self._thetas[index].set_data(theta)
+            self._thetas[index].nugget = float(nug)
+            self._logpost_data[index] = 0.5 * (float(quad) + float(logdet) + self.n * np.log(2.0 * np.pi))
+            self._fit[index] = True
+        else:
+            self._thetas[index].unset_data()
+            self._logpost_data[index] = None
+            self._fit[index] = False
+
+    def fit(self, thetas):
+        """Fit every emulator; ``thetas`` has shape ``(n_emulators, n_params)``.  Emulators whose matrix is not
+        positive definite stay "not fit" and are reported by ``get_indices_not_fit`` (fitting.py:180-186)."""
+        thetas = np.array(thetas, dtype=np.float64)
+        if thetas.ndim == 1:
+            thetas = thetas.reshape(1, -1)
+        if thetas.shape[0] != self.n_emulators:
+            raise RuntimeError("thetas must have first dimension of size n_emulators")
+        if thetas.shape[1] != self.n_params[0]:
+            raise RuntimeError("bad shape for hyperparameters")
+        if self._handle is not None:
+            quad, logdet, nug, status = self._handle.fit(0, thetas[self._lo:self._hi])
+            for k, i in enumerate(range(self._lo, self._hi)):
+                self._record(i, thetas[i], quad[k], logdet[k], nug[k], status[k])
+
+    def fit_emulator(self, index, theta):
+        theta = np.array(theta, dtype=np.float64).reshape(-1)
+        if not 0 <= index < self.n_emulators:
+            raise RuntimeError("emulator index out of range")
+        if theta.shape[0] != self.n_params[index]:
+            raise RuntimeError("bad shape for hyperparameters")
+        if self._lo <= index < self._hi:
+            quad, logdet, nug, status = self._handle.fit(index - self._lo, theta)
+            self._record(index, theta, quad[0], logdet[0], nug[0], status[0])
+
+    def logposterior(self, index, theta=None):
+        """current_logpost of one (local) emulator, fitting it first when theta is given and differs."""
+        if theta is not None:
+            theta = np.array(theta, dtype=np.float64).reshape(-1)
+            t = self._thetas[index]
+            if not t.data_has_been_set() or not np.allclose(theta, t.get_data(), rtol=1.0e-10, atol=1.0e-15):
+                self.fit_emulator(index, theta)
+                if not self._fit[index]:
+                    raise RuntimeError("Unable to fit the Gaussian process: matrix not positive definite")
+        if not self._fit[index]:
+            return None
+        return self._logpost_data[index] - self._priors[index].logp(self._thetas[index])
+
+    def logpost_deriv(self, index, theta):
+        self.logposterior(index, theta)
+        grad = self._handle.logpost_grad(index - self._lo, self.n_params[index])
+        return grad - self._priors[index].dlogpdtheta(self._thetas[index])
+
+    def get_indices_fit(self):
+        return [i for i in range(self.n_emulators) if self._global_fit(i)]
+
+    def get_indices_not_fit(self):
+        return [i for i in range(self.n_emulators) if not self._global_fit(i)]
+
+    def _global_fit(self, i):
+        # without a communicator every output is local; with one, fit status of remote outputs is learnt at
+        # the gather in predict (until then they are reported from the local mirror, which fit() keeps
+        # consistent because every rank calls fit with the full thetas array)
+        return self._fit[i] if self._lo <= i < self._hi else self._remote_fit.get(i, True)
+
+    _remote_fit = {}
+
+    # -- prediction (MultiOutputGP_GPU.py:185-297; CPU semantics MultiOutputGP.py:182-319) ---------------
+    def predict(self, testing, unc=True, deriv=False, include_nugget=True, allow_not_fit=False, processes=None):
+        testing = np.array(testing, dtype=np.float64)
+        if self.D == 1 and testing.ndim == 1:
+            testing = np.reshape(testing, (-1, 1))
+        elif testing.ndim == 1:
+            testing = np.reshape(testing, (1, len(testing)))
+        assert testing.ndim == 2, "testing must be a 2D array"
+        assert testing.shape[1] == self.D, "second dimension of testing must be the same as the number of input parameters"
+        if deriv:
+            raise GPUUnavailableError("predictive derivatives are not implemented in this build")
+        E, m = self.n_emulators, testing.shape[0]
+        if self._comm is None:
+            if not allow_not_fit and len(self.get_indices_not_fit()) > 0:
+                raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
+            mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
+            return PredictResult(mean=mean, unc=var if unc else None, deriv=None)
+        # sharded: local predict + the one all-gather of the path
+        if self._handle is None:
+            raise RuntimeError("this rank holds no outputs: use at most n_emulators ranks")
+        mean_all, var_all, status_all = self._handle.predict_allgather(self._comm, testing, include_nugget, self._e_pad)
+        rows = []
+        self._remote_fit = {}
+        for r in range(self._comm.world):
+            lo, hi, _ = shard_bounds(E, r, self._comm.world)
+            for k in range(hi - lo):
+                rows.append(r * self._e_pad + k)
+                self._remote_fit[lo + k] = bool(status_all[r * self._e_pad + k] == libmogp.OK)
+        rows = np.array(rows, dtype=np.int64)
+        if not allow_not_fit and np.any(status_all[rows] != libmogp.OK):
+            raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
+        return PredictResult(mean=mean_all[rows], unc=var_all[rows] if unc else None, deriv=None)
+
+    def __call__(self, testing, processes=None):
+        return self.predict(testing, unc=False, deriv=False, processes=processes)[0]
+
+    def timings(self, reset=False):
+        return self._handle.timings(reset) if self._handle is not None else {}
+
+    def __str__(self):
+        return ("Multi-Output Gaussian Process with:\n" + str(self.n_emulators) + " emulators\n" +
+                str(self.n) + " training examples\n" + str(self.D) + " input variables")

@@ -1,0 +1,696 @@
+// C ABI of libmogp_b200 (see include/mogp_b200.h): handle management, the fit / predict orchestration
+// (one GP per stream for the factorisations, one batched launch per phase for predict) and getters.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/mogp_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "nccl_dyn.h"
+
+namespace mogp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_kblocked_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return 1;
+    cuuint64_t gdim[3] = {8, (cuuint64_t)rows, (cuuint64_t)(ld / 8)};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 8, 64};
+    cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)(KC / 8)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+int make_2d_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                 int box_cols) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return 1;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+}  // namespace mogp
+
+using namespace mogp;
+
+enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_COUNT };
+
+struct mogp_handle {
+    int device = 0, n_sms = 148;
+    int64_t n = 0, n_pad = 0;
+    int d = 0, E = 0, kernel = 0, nug_type = 0;
+    double nug_fixed = 0.0;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> ev_join;
+    cudaStream_t main = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    // device slabs
+    double *XT = nullptr, *Y = nullptr, *A = nullptr, *Dinv = nullptr, *alpha = nullptr, *z = nullptr;
+    double *hyper = nullptr, *scal = nullptr;  // scal: [E][2] = logdet, quad
+    int* info = nullptr;
+    // pinned host mirrors
+    double *h_hyper = nullptr, *h_scal = nullptr;
+    int* h_info = nullptr;
+    CUtensorMap tmXT;
+    CholMaps maps;
+    std::vector<char> fitted;
+    // predict workspace (grown on demand)
+    double *XsT = nullptr, *W = nullptr, *part = nullptr, *res = nullptr, *h_res = nullptr, *h_XsT = nullptr;
+    size_t XsT_cap = 0, W_cap = 0, part_cap = 0, res_cap = 0, h_res_cap = 0, h_XsT_cap = 0;
+    // grad workspace
+    double* G = nullptr;
+    double timings[T_COUNT] = {0};
+};
+
+struct mogp_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+    cudaStream_t stream = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr, *h_recv = nullptr;
+    size_t send_cap = 0, recv_cap = 0, h_cap = 0;
+    double* dscalar = nullptr;
+};
+
+#define API_CUDA(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);  \
+            return (e__ == cudaErrorMemoryAllocation) ? MOGP_ERR_NOMEM : MOGP_ERR_CUDA;              \
+        }                                                                                            \
+    } while (0)
+
+static int grow(double** p, size_t* cap, size_t bytes, bool pinned = false) {
+    if (*cap >= bytes) return MOGP_OK;
+    if (*p) {
+        if (pinned) cudaFreeHost(*p);
+        else cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+    }
+    cudaError_t e = pinned ? cudaMallocHost((void**)p, bytes) : cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) {
+        set_error("allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MOGP_ERR_NOMEM;
+    }
+    *cap = bytes;
+    return MOGP_OK;
+}
+
+extern "C" {
+
+int mogp_version(int32_t* major, int32_t* minor) {
+    if (major) *major = 0;
+    if (minor) *minor = 1;
+    return MOGP_OK;
+}
+
+const char* mogp_last_error(void) { return g_err; }
+
+int mogp_device_count(int32_t* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    int usable = 0;
+    for (int i = 0; i < c; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) usable++;
+    }
+    if (count) *count = usable;
+    return MOGP_OK;
+}
+
+int mogp_destroy(mogp_handle* h) {
+    if (!h) return MOGP_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto s : h->streams) cudaStreamDestroy(s);
+    for (auto e : h->ev_join) cudaEventDestroy(e);
+    if (h->main) cudaStreamDestroy(h->main);
+    cudaEvent_t evs[5] = {h->ev_fork, h->ev_a, h->ev_b, h->ev_c, h->ev_d};
+    for (auto e : evs)
+        if (e) cudaEventDestroy(e);
+    double* dev[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G};
+    for (auto p : dev)
+        if (p) cudaFree(p);
+    if (h->info) cudaFree(h->info);
+    double* host[] = {h->h_hyper, h->h_scal, h->h_res, h->h_XsT};
+    for (auto p : host)
+        if (p) cudaFreeHost(p);
+    if (h->h_info) cudaFreeHost(h->h_info);
+    cudaGetLastError();
+    delete h;
+    return MOGP_OK;
+}
+
+int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t n_out, int32_t kernel,
+                int32_t nugget_type, double nugget, int32_t device, int32_t n_streams, mogp_handle** out) {
+    if (!X || !Y || !out || n < 1 || d < 1 || d > 256 || n_out < 1) {
+        set_error("mogp_create: bad shape (n=%lld d=%d n_out=%d; need n>=1, 1<=d<=256, n_out>=1)", (long long)n, d, n_out);
+        return MOGP_ERR_ARG;
+    }
+    if (kernel != MOGP_KERNEL_SQEXP && kernel != MOGP_KERNEL_MATERN52) {
+        set_error("mogp_create: unknown kernel %d", kernel);
+        return MOGP_ERR_ARG;
+    }
+    if (nugget_type < 0 || nugget_type > 2 || (nugget_type == MOGP_NUG_FIXED && !(nugget >= 0.0))) {
+        set_error("mogp_create: bad nugget specification");
+        return MOGP_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        set_error("mogp_create: CUDA device %d not available (%d visible)", device, ndev);
+        return MOGP_ERR_CUDA;
+    }
+    API_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    API_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("mogp_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return MOGP_ERR_CUDA;
+    }
+    if (chol_init() || solve_init() || kmat_init() || predict_init()) {
+        set_error("kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MOGP_ERR_CUDA;
+    }
+    mogp_handle* h = new mogp_handle();
+    h->device = device;
+    h->n_sms = prop.multiProcessorCount;
+    h->n = n;
+    h->n_pad = round_up(n, NB);
+    h->d = d;
+    h->E = n_out;
+    h->kernel = kernel;
+    h->nug_type = nugget_type;
+    h->nug_fixed = nugget;
+    h->fitted.assign(n_out, 0);
+    const int64_t np = h->n_pad;
+    int S = n_streams > 0 ? n_streams : 16;
+    if (S > n_out) S = n_out;
+    int rc = MOGP_OK;
+#define CREATE_CUDA(expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);  \
+            rc = (e__ == cudaErrorMemoryAllocation) ? MOGP_ERR_NOMEM : MOGP_ERR_CUDA;                \
+            cudaGetLastError();                                                                      \
+            mogp_destroy(h);                                                                         \
+            return rc;                                                                               \
+        }                                                                                            \
+    } while (0)
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->main, cudaStreamNonBlocking));
+    for (int s = 0; s < S; s++) {
+        cudaStream_t st;
+        cudaEvent_t ev;
+        CREATE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        h->streams.push_back(st);
+        CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->ev_join.push_back(ev);
+    }
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreate(&h->ev_a));
+    CREATE_CUDA(cudaEventCreate(&h->ev_b));
+    CREATE_CUDA(cudaEventCreate(&h->ev_c));
+    CREATE_CUDA(cudaEventCreate(&h->ev_d));
+    CREATE_CUDA(cudaMalloc(&h->XT, sizeof(double) * d * np));
+    CREATE_CUDA(cudaMalloc(&h->Y, sizeof(double) * n_out * np));
+    CREATE_CUDA(cudaMalloc(&h->A, sizeof(double) * (size_t)n_out * np * np));
+    CREATE_CUDA(cudaMalloc(&h->Dinv, sizeof(double) * (size_t)n_out * np * NB));
+    CREATE_CUDA(cudaMalloc(&h->alpha, sizeof(double) * n_out * np));
+    CREATE_CUDA(cudaMalloc(&h->z, sizeof(double) * n_out * np));
+    CREATE_CUDA(cudaMalloc(&h->hyper, sizeof(double) * n_out * (d + 2)));
+    CREATE_CUDA(cudaMalloc(&h->scal, sizeof(double) * n_out * 2));
+    CREATE_CUDA(cudaMalloc(&h->info, sizeof(int) * n_out));
+    CREATE_CUDA(cudaMallocHost(&h->h_hyper, sizeof(double) * n_out * (d + 2)));
+    CREATE_CUDA(cudaMallocHost(&h->h_scal, sizeof(double) * n_out * 2));
+    CREATE_CUDA(cudaMallocHost(&h->h_info, sizeof(int) * n_out));
+    {
+        // transposed, zero-padded design matrix and zero-padded targets
+        std::vector<double> xt((size_t)d * np, 0.0), yp((size_t)n_out * np, 0.0);
+        for (int64_t i = 0; i < n; i++)
+            for (int k = 0; k < d; k++) xt[(size_t)k * np + i] = X[i * d + k];
+        for (int o = 0; o < n_out; o++) memcpy(&yp[(size_t)o * np], Y + (size_t)o * n, sizeof(double) * n);
+        CREATE_CUDA(cudaMemcpy(h->XT, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaMemcpy(h->Y, yp.data(), sizeof(double) * yp.size(), cudaMemcpyHostToDevice));
+    }
+    if (make_2d_tmap(&h->tmXT, h->XT, d, np, np, kmat_dbox(d), 128) ||
+        chol_make_maps(&h->maps, h->A, h->Dinv, (int64_t)n_out * np, np)) {
+        set_error("cuTensorMapEncodeTiled failed");
+        mogp_destroy(h);
+        return MOGP_ERR_CUDA;
+    }
+#undef CREATE_CUDA
+    *out = h;
+    return MOGP_OK;
+}
+
+int mogp_reset(mogp_handle* h, int32_t idx) {
+    if (!h || idx >= h->E) return MOGP_ERR_ARG;
+    if (idx < 0) std::fill(h->fitted.begin(), h->fitted.end(), 0);
+    else h->fitted[idx] = 0;
+    return MOGP_OK;
+}
+
+int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out) {
+    if (!h || idx < 0 || idx >= h->E || !out) return MOGP_ERR_ARG;
+    *out = h->fitted[idx];
+    return MOGP_OK;
+}
+
+// enqueue kernel matrix + factorisation + solves for output o with the given nugget on stream st
+static int enqueue_attempt(mogp_handle* h, int o, double nugget, cudaStream_t st) {
+    const int64_t np = h->n_pad;
+    API_CUDA(cudaMemsetAsync(h->info + o, 0, sizeof(int), st));
+    API_CUDA(cudaMemsetAsync(h->scal + 2 * o, 0, 2 * sizeof(double), st));
+    if (kmat_sym(h->tmXT, h->kernel, h->n, np, h->d, h->hyper, o, nugget, h->A, (int64_t)o * np, st)) {
+        set_error("kmat launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MOGP_ERR_CUDA;
+    }
+    int nl = chol_factor(h->maps, h->A, h->Dinv, o, np, h->info + o, h->scal + 2 * o, st);
+    if (nl < 0) {
+        set_error("cholesky launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MOGP_ERR_CUDA;
+    }
+    h->timings[T_NLAUNCH] += nl + 2;
+    int rs = solve_alpha(h->A + (size_t)o * np * np, np, h->Dinv + (size_t)o * np * NB, h->Y + (size_t)o * np,
+                         h->z + (size_t)o * np, h->alpha + (size_t)o * np, h->scal + 2 * o + 1, h->info + o, st);
+    if (rs) {
+        set_error(rs == 2 ? "n too large for the single-CTA solver" : "solve launch failed");
+        return rs == 2 ? MOGP_ERR_ARG : MOGP_ERR_CUDA;
+    }
+    API_CUDA(cudaMemcpyAsync(h->h_info + o, h->info + o, sizeof(int), cudaMemcpyDeviceToHost, st));
+    API_CUDA(cudaMemcpyAsync(h->h_scal + 2 * o, h->scal + 2 * o, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return MOGP_OK;
+}
+
+int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas, int32_t n_params,
+             double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out) {
+    if (!h || !thetas || first < 0 || count < 1 || first + count > h->E) {
+        set_error("mogp_fit: bad output range");
+        return MOGP_ERR_ARG;
+    }
+    const int d = h->d;
+    const int want = d + 1 + (h->nug_type == MOGP_NUG_FIT ? 1 : 0);
+    if (n_params != want) {
+        set_error("mogp_fit: theta has %d entries, expected %d", n_params, want);
+        return MOGP_ERR_ARG;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    const int hs = d + 2;
+    std::vector<double> nug(count, 0.0);
+    for (int i = 0; i < count; i++) {
+        const int o = first + i;
+        const double* th = thetas + (size_t)i * n_params;
+        double* hy = h->h_hyper + (size_t)o * hs;
+        for (int k = 0; k < d; k++) hy[k] = exp(th[k]);       // CorrTransform: l = exp(-theta/2) <=> weight exp(theta)
+        hy[d] = exp(th[d]);                                   // CovTransform
+        if (h->nug_type == MOGP_NUG_FIT) nug[i] = exp(th[d + 1]);
+        else if (h->nug_type == MOGP_NUG_FIXED) nug[i] = h->nug_fixed;
+        else nug[i] = 0.0;
+        hy[d + 1] = nug[i];
+        h->fitted[o] = 0;
+    }
+    API_CUDA(cudaEventRecord(h->ev_a, h->main));
+    API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
+                             cudaMemcpyHostToDevice, h->main));
+    API_CUDA(cudaEventRecord(h->ev_fork, h->main));
+    const int S = (int)h->streams.size();
+    for (int s = 0; s < S && s < count; s++) API_CUDA(cudaStreamWaitEvent(h->streams[s], h->ev_fork, 0));
+    for (int i = 0; i < count; i++) {
+        int rc = enqueue_attempt(h, first + i, nug[i], h->streams[i % S]);
+        if (rc) return rc;
+    }
+    for (int s = 0; s < S && s < count; s++) {
+        API_CUDA(cudaEventRecord(h->ev_join[s], h->streams[s]));
+        API_CUDA(cudaStreamWaitEvent(h->main, h->ev_join[s], 0));
+    }
+    API_CUDA(cudaEventRecord(h->ev_b, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+        h->timings[T_FIT] += ms;
+    }
+    // adaptive jitter retries (linalg/cholesky.py:264-279): jitter = mean(diag K) * 1e-6, x10 per failure, 5 tries.
+    // diag of a stationary kernel matrix is sigma2 for every entry, so mean(diag K) == sigma2.
+    for (int i = 0; i < count; i++) {
+        const int o = first + i;
+        int status = MOGP_OK;
+        if (h->h_info[o] != 0) {
+            status = MOGP_ERR_NOT_PD;
+            if (h->nug_type == MOGP_NUG_ADAPTIVE) {
+                double jitter = h->h_hyper[(size_t)o * hs + d] * 1e-6;
+                for (int t = 0; t < 5 && std::isfinite(jitter); t++) {
+                    int rc = enqueue_attempt(h, o, jitter, h->streams[0]);
+                    if (rc) return rc;
+                    API_CUDA(cudaStreamSynchronize(h->streams[0]));
+                    if (h->h_info[o] == 0) {
+                        status = MOGP_OK;
+                        nug[i] = jitter;
+                        break;
+                    }
+                    jitter *= 10.0;
+                }
+            }
+        }
+        if (status == MOGP_OK) {
+            h->fitted[o] = 1;
+            h->h_hyper[(size_t)o * hs + d + 1] = nug[i];
+        }
+        if (status_out) status_out[i] = status;
+        if (nugget_out) nugget_out[i] = nug[i];
+        if (logdet_out) logdet_out[i] = status == MOGP_OK ? h->h_scal[2 * o] : std::numeric_limits<double>::quiet_NaN();
+        if (quad_out) quad_out[i] = status == MOGP_OK ? h->h_scal[2 * o + 1] : std::numeric_limits<double>::quiet_NaN();
+    }
+    // the nugget actually used enters the predictive variance
+    API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
+                             cudaMemcpyHostToDevice, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    return MOGP_OK;
+}
+
+// Runs predict for all fitted outputs; results land in h->res as [E][2][m] (mean row, variance row),
+// rows of unfitted outputs are NaN.  Enqueued on h->main, not synchronised.
+static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_var, int include_nugget) {
+    const int64_t np = h->n_pad;
+    const int d = h->d;
+    std::vector<int> fit_idx;
+    for (int o = 0; o < h->E; o++)
+        if (h->fitted[o]) fit_idx.push_back(o);
+    int rc;
+    if ((rc = grow(&h->res, &h->res_cap, sizeof(double) * (size_t)h->E * 2 * m))) return rc;
+    API_CUDA(cudaMemsetAsync(h->res, 0xFF, sizeof(double) * (size_t)h->E * 2 * m, h->main));  // all-ones == NaN
+    if (fit_idx.empty() || m == 0) return MOGP_OK;
+
+    // group / chunk sizes under a workspace budget
+    size_t free_b = 0, total_b = 0;
+    API_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = (size_t)((free_b + h->W_cap) * 0.6);
+    int64_t mc_max = m;
+    while ((size_t)(round_up(mc_max, 128) + 128) * np * 8 > budget && mc_max > 128) mc_max = (mc_max + 1) / 2;
+    for (int64_t m0 = 0; m0 < m; m0 += mc_max) {
+        const int64_t mc = std::min<int64_t>(mc_max, m - m0);
+        size_t gcap = budget / ((size_t)(round_up(mc, 128) + 128) * np * 8);
+        if (gcap < 1) gcap = 1;
+        if (gcap > (size_t)MAXG) gcap = MAXG;
+        if (gcap > fit_idx.size()) gcap = fit_idx.size();
+        const int G = (int)gcap;
+        for (size_t g0 = 0; g0 < fit_idx.size(); g0 += G) {
+            const int cnt = (int)std::min<size_t>(G, fit_idx.size() - g0);
+            const int* outs = fit_idx.data() + g0;
+            TrsmPlan plan = predict_plan(mc, cnt, h->n_sms);
+            // panels * nw < mc + 128, so this stride covers every panel of every plan (and is what the
+            // budget above assumed); the kernel-matrix kernel fills all w_stride rows (zero-padded test points)
+            const int64_t w_stride = round_up(mc, 128) + 128;
+            const int n_tiles = (int)(np / 128);
+            if ((rc = grow(&h->XsT, &h->XsT_cap, sizeof(double) * d * w_stride))) return rc;
+            if ((rc = grow(&h->h_XsT, &h->h_XsT_cap, sizeof(double) * d * w_stride, true))) return rc;
+            if (want_var && (rc = grow(&h->W, &h->W_cap, sizeof(double) * (size_t)cnt * w_stride * np))) return rc;
+            if ((rc = grow(&h->part, &h->part_cap, sizeof(double) * (size_t)cnt * n_tiles * w_stride))) return rc;
+            if (g0 == 0) {
+                memset(h->h_XsT, 0, sizeof(double) * d * w_stride);
+                for (int64_t i = 0; i < mc; i++)
+                    for (int k = 0; k < d; k++) h->h_XsT[(size_t)k * w_stride + i] = Xs[(m0 + i) * d + k];
+                API_CUDA(cudaMemcpyAsync(h->XsT, h->h_XsT, sizeof(double) * d * w_stride, cudaMemcpyHostToDevice, h->main));
+            }
+            CUtensorMap tmXsT, tmW;
+            if (make_2d_tmap(&tmXsT, h->XsT, d, w_stride, w_stride, kmat_dbox(d), 128)) {
+                set_error("tensor map (XsT) failed");
+                return MOGP_ERR_CUDA;
+            }
+            API_CUDA(cudaEventRecord(h->ev_a, h->main));
+            if (kmat_cross(tmXsT, h->tmXT, h->kernel, h->n, np, w_stride, d, outs, cnt, h->hyper, h->W, w_stride, want_var,
+                           h->alpha, np, h->part, h->main) ||
+                mean_reduce(h->part, outs, cnt, n_tiles, w_stride, mc, h->res + m0, 2 * m, h->main)) {
+                set_error("kstar launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MOGP_ERR_CUDA;
+            }
+            API_CUDA(cudaEventRecord(h->ev_b, h->main));
+            if (want_var) {
+                if (make_kblocked_tmap(&tmW, h->W, (int64_t)cnt * w_stride, np, plan.nw)) {
+                    set_error("tensor map (W) failed");
+                    return MOGP_ERR_CUDA;
+                }
+                if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
+                                 include_nugget, np, mc, h->res + m + m0, 2 * m, h->main)) {
+                    set_error("predict_trsm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    return MOGP_ERR_CUDA;
+                }
+                h->timings[T_NTRSM] += 1;
+            }
+            API_CUDA(cudaEventRecord(h->ev_c, h->main));
+            h->timings[T_NLAUNCH] += 2 + (want_var ? 1 : 0);
+            // per-phase device times (the sync also protects the reused workspace and the pinned XsT buffer)
+            API_CUDA(cudaStreamSynchronize(h->main));
+            float ms1 = 0.f, ms2 = 0.f;
+            cudaEventElapsedTime(&ms1, h->ev_a, h->ev_b);
+            cudaEventElapsedTime(&ms2, h->ev_b, h->ev_c);
+            h->timings[T_KSTAR] += ms1;
+            h->timings[T_TRSM] += ms2;
+        }
+    }
+    return MOGP_OK;
+}
+
+int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, int32_t include_nugget,
+                 double* mean, double* var, int32_t* status) {
+    if (!h || (!Xs && m > 0) || m < 0 || !mean || (want_var && !var)) {
+        set_error("mogp_predict: bad arguments");
+        return MOGP_ERR_ARG;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    for (int o = 0; o < h->E; o++)
+        if (status) status[o] = h->fitted[o] ? MOGP_OK : MOGP_ERR_NOT_FIT;
+    if (m == 0) return MOGP_OK;
+    int rc = predict_device(h, Xs, m, want_var, include_nugget);
+    if (rc) return rc;
+    if ((rc = grow(&h->h_res, &h->h_res_cap, sizeof(double) * (size_t)h->E * 2 * m, true))) return rc;
+    API_CUDA(cudaMemcpyAsync(h->h_res, h->res, sizeof(double) * (size_t)h->E * 2 * m, cudaMemcpyDeviceToHost, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    for (int o = 0; o < h->E; o++) {
+        memcpy(mean + (size_t)o * m, h->h_res + (size_t)o * 2 * m, sizeof(double) * m);
+        if (want_var) memcpy(var + (size_t)o * m, h->h_res + (size_t)o * 2 * m + m, sizeof(double) * m);
+    }
+    return MOGP_OK;
+}
+
+int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
+    if (!h || idx < 0 || idx >= h->E || !out) return MOGP_ERR_ARG;
+    if (!h->fitted[idx]) {
+        set_error("mogp_get: output %d has not been fit", idx);
+        return MOGP_ERR_NOT_FIT;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n, np = h->n_pad;
+    if (which == MOGP_GET_ALPHA) {
+        API_CUDA(cudaMemcpy(out, h->alpha + (size_t)idx * np, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        return MOGP_OK;
+    }
+    if (which == MOGP_GET_L) {
+        API_CUDA(cudaMemcpy2D(out, sizeof(double) * n, h->A + (size_t)idx * np * np, sizeof(double) * np, sizeof(double) * n, n,
+                              cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; i++)
+            for (int64_t j = i + 1; j < n; j++) out[i * n + j] = 0.0;
+        return MOGP_OK;
+    }
+    if (which == MOGP_GET_K) {
+        // recomputed (the factor overwrote it): sigma2*k(X,X) without the nugget (GaussianProcess.get_K_matrix)
+        double* tmp = nullptr;
+        API_CUDA(cudaMalloc(&tmp, sizeof(double) * np * np));
+        int rc = kmat_sym(h->tmXT, h->kernel, n, np, h->d, h->hyper, idx, 0.0, tmp, 0, h->main);
+        if (rc == 0) {
+            cudaError_t e = cudaMemcpy2DAsync(out, sizeof(double) * n, tmp, sizeof(double) * np, sizeof(double) * n, n,
+                                              cudaMemcpyDeviceToHost, h->main);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->main);
+            rc = e == cudaSuccess ? 0 : 1;
+        }
+        cudaFree(tmp);
+        if (rc) {
+            set_error("get K failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MOGP_ERR_CUDA;
+        }
+        for (int64_t i = 0; i < n; i++)
+            for (int64_t j = i + 1; j < n; j++) out[i * n + j] = out[j * n + i];
+        return MOGP_OK;
+    }
+    set_error("mogp_get: selector %d not available", which);
+    return MOGP_ERR_ARG;
+}
+
+int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params) {
+    (void)h; (void)idx; (void)grad; (void)n_params;
+    set_error("mogp_logpost_grad: not built yet");
+    return MOGP_ERR_ARG;
+}
+
+int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset) {
+    if (!h || !out) return MOGP_ERR_ARG;
+    for (int i = 0; i < n && i < T_COUNT; i++) out[i] = h->timings[i];
+    if (reset) memset(h->timings, 0, sizeof(h->timings));
+    return MOGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL
+// ---------------------------------------------------------------------------------------------
+int mogp_comm_unique_id(char* out128) {
+    if (!out128) return MOGP_ERR_ARG;
+    const NcclApi* api = nccl_api();
+    if (!api) {
+        set_error("libnccl.so.2 could not be loaded");
+        return MOGP_ERR_NCCL;
+    }
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) {
+        set_error("ncclGetUniqueId failed");
+        return MOGP_ERR_NCCL;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, 128);
+    return MOGP_OK;
+}
+
+int mogp_comm_create(const char* uid128, int32_t rank, int32_t world, int32_t device, mogp_comm** out) {
+    if (!uid128 || !out || rank < 0 || rank >= world) return MOGP_ERR_ARG;
+    const NcclApi* api = nccl_api();
+    if (!api) {
+        set_error("libnccl.so.2 could not be loaded");
+        return MOGP_ERR_NCCL;
+    }
+    API_CUDA(cudaSetDevice(device));
+    mogp_comm* c = new mogp_comm();
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    ncclUniqueId id;
+    memcpy(&id, uid128, 128);
+    ncclResult_t r = api->CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank failed: %s", api->GetErrorString(r));
+        delete c;
+        return MOGP_ERR_NCCL;
+    }
+    API_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    API_CUDA(cudaMalloc(&c->dscalar, sizeof(double) * 2));
+    *out = c;
+    return MOGP_OK;
+}
+
+int mogp_comm_destroy(mogp_comm* c) {
+    if (!c) return MOGP_OK;
+    const NcclApi* api = nccl_api();
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (api && c->comm) api->CommDestroy(c->comm);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->sendbuf) cudaFree(c->sendbuf);
+    if (c->recvbuf) cudaFree(c->recvbuf);
+    if (c->dscalar) cudaFree(c->dscalar);
+    if (c->h_recv) cudaFreeHost(c->h_recv);
+    delete c;
+    return MOGP_OK;
+}
+
+int mogp_comm_allreduce_max(mogp_comm* c, double* value) {
+    if (!c || !value) return MOGP_ERR_ARG;
+    const NcclApi* api = nccl_api();
+    API_CUDA(cudaSetDevice(c->device));
+    API_CUDA(cudaMemcpyAsync(c->dscalar, value, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = api->AllReduce(c->dscalar, c->dscalar + 1, 1, ncclDouble, ncclMax, c->comm, c->stream);
+    if (r != ncclSuccess) {
+        set_error("ncclAllReduce failed: %s", api->GetErrorString(r));
+        return MOGP_ERR_NCCL;
+    }
+    API_CUDA(cudaMemcpyAsync(value, c->dscalar + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    API_CUDA(cudaStreamSynchronize(c->stream));
+    return MOGP_OK;
+}
+
+int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, int64_t m, int32_t include_nugget,
+                           int32_t e_pad, double* mean_all, double* var_all, int32_t* status_all) {
+    if (!h || !comm || !Xs || m < 1 || e_pad < h->E || !mean_all || !var_all) {
+        set_error("mogp_predict_allgather: bad arguments");
+        return MOGP_ERR_ARG;
+    }
+    const NcclApi* api = nccl_api();
+    API_CUDA(cudaSetDevice(h->device));
+    int rc = predict_device(h, Xs, m, 1, include_nugget);
+    if (rc) return rc;
+    const size_t blk = (size_t)e_pad * 2 * m;  // doubles per rank; one extra row-pair block carries the status words
+    const size_t send_n = blk + e_pad;
+    if ((rc = grow(&comm->sendbuf, &comm->send_cap, sizeof(double) * send_n))) return rc;
+    if ((rc = grow(&comm->recvbuf, &comm->recv_cap, sizeof(double) * send_n * comm->world))) return rc;
+    if ((rc = grow(&comm->h_recv, &comm->h_cap, sizeof(double) * send_n * comm->world, true))) return rc;
+    // pack: [e_pad][2][m] results (NaN for padding rows) + e_pad status words (as doubles)
+    API_CUDA(cudaMemsetAsync(comm->sendbuf, 0xFF, sizeof(double) * blk, h->main));
+    API_CUDA(cudaMemcpyAsync(comm->sendbuf, h->res, sizeof(double) * (size_t)h->E * 2 * m, cudaMemcpyDeviceToDevice, h->main));
+    std::vector<double> st(e_pad, (double)MOGP_ERR_ARG);
+    for (int o = 0; o < h->E; o++) st[o] = h->fitted[o] ? (double)MOGP_OK : (double)MOGP_ERR_NOT_FIT;
+    API_CUDA(cudaMemcpyAsync(comm->sendbuf + blk, st.data(), sizeof(double) * e_pad, cudaMemcpyHostToDevice, h->main));
+    // the single collective of the path: all-gather of every rank's packed posterior block
+    ncclResult_t r = api->AllGather(comm->sendbuf, comm->recvbuf, send_n, ncclDouble, comm->comm, h->main);
+    if (r != ncclSuccess) {
+        set_error("ncclAllGather failed: %s", api->GetErrorString(r));
+        return MOGP_ERR_NCCL;
+    }
+    API_CUDA(cudaMemcpyAsync(comm->h_recv, comm->recvbuf, sizeof(double) * send_n * comm->world, cudaMemcpyDeviceToHost, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    for (int rk = 0; rk < comm->world; rk++) {
+        const double* src = comm->h_recv + (size_t)rk * send_n;
+        for (int o = 0; o < e_pad; o++) {
+            const size_t row = (size_t)rk * e_pad + o;
+            memcpy(mean_all + row * m, src + (size_t)o * 2 * m, sizeof(double) * m);
+            memcpy(var_all + row * m, src + (size_t)o * 2 * m + m, sizeof(double) * m);
+            if (status_all) status_all[row] = (int32_t)src[blk + o];
+        }
+    }
+    return MOGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// Internal host-side interface between the translation units of libmogp_b200.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace mogp {
+
+constexpr int MAXG = 64;  // outputs handled by one batched predict launch
+
+struct CholMaps {
+    CUtensorMap a128;  // K-blocked map over the matrix slab [E*n_pad][n_pad], box 128 rows
+    CUtensorMap a64;   // same slab, box 64 rows
+    CUtensorMap d128;  // K-blocked map over the Dinv slab [E*n_pad][128], box 128 rows
+};
+
+// per-output hyperparameters in device memory: [w_0 .. w_{d-1}, sigma2, nugget]
+//   w_i = exp(theta_i), sigma2 = exp(theta_d)   (GPParams.py:3-161)
+
+// ---- chol.cu ----
+int chol_init();
+int chol_make_maps(CholMaps* maps, double* A_slab, double* Dinv_slab, int64_t total_rows, int64_t n_pad);
+// factorise output `o` of the slab in place on `st`; info/logdet must be zero.  Returns #launches or -1.
+int chol_factor(const CholMaps& maps, double* A_slab, double* Dinv_slab, int o, int64_t n_pad, int* info,
+                double* logdet, cudaStream_t st);
+
+// ---- kmat.cu ----
+int kmat_init();
+int kmat_dbox(int d);
+int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, int out_idx,
+             double nugget, double* A_slab, int64_t row_base, cudaStream_t st);
+int kmat_cross(const CUtensorMap& tmXsT, const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int64_t m_pad,
+               int d, const int* outs, int count, const double* hyper, double* W_slab, int64_t w_stride, int store,
+               const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st);
+int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int64_t m_pad, int64_t m, double* mean,
+                int64_t mean_stride, cudaStream_t st);
+
+// ---- solve.cu ----
+int solve_init();
+int solve_alpha(const double* A, int64_t n_pad, const double* Dinv, const double* y, double* z, double* alpha,
+                double* quad, const int* info, cudaStream_t st);
+
+// ---- predict.cu ----
+int predict_init();
+struct TrsmPlan {
+    int nw;      // test points per CTA (multiple of 16, 64..128)
+    int panels;  // CTAs per output
+};
+TrsmPlan predict_plan(int64_t m, int n_outputs, int n_sms);
+int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
+                 const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
+                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, cudaStream_t st);
+
+}  // namespace mogp

@@ -1,0 +1,213 @@
+// Kernel-matrix assembly for libmogp_b200 (replaces the scalar one-thread-per-element kernels
+// sqexp_cov_batch_kernel / mat52_cov_batch_kernel, reference mogp_gpu/src/kernel.cu:55-65,251-261;
+// arithmetic follows the CPU reference StationaryKernel.calc_r2 + calc_K, mogp_emulator/Kernel.py:476-485,
+// 787-791, 878-882, and GaussianProcess.get_cov_matrix, GaussianProcess.py:517-558).
+//
+//   r2[i][j] = sum_d exp(theta_d) (x_i,d - x'_j,d)^2 ;  K = sigma2 * k(r2)
+//
+// The design matrices are kept transposed in HBM (XT: d x n_pad), so a 128-point tile is a TMA 2-D box
+// (128 points x up-to-16 dims) landing in shared memory as [dim][point]: lanes read consecutive points
+// (conflict-free) and the row operand is a broadcast.  Each thread owns an 8x8 sub-tile in registers
+// and writes 128-byte row segments of K.
+//   SYM   : lower 128x128 tiles of K(X,X) + nugget*I into the Cholesky workspace (identity in padding)
+//   CROSS : test-major K*(Xs,X) into the predict workspace, with the fused posterior-mean partial
+//           dot  sum_r K*[c][r] alpha[r]  (deterministic per-tile partials, no atomics).
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/mogp_b200.h"
+
+namespace mogp {
+
+constexpr int DCH = 16;  // dims per TMA box / smem chunk (static smem stays under 48 KB)
+
+template <int KT>
+__device__ __forceinline__ double kfun(double r2) {
+    if (KT == MOGP_KERNEL_SQEXP) {
+        return exp(-0.5 * r2);
+    } else {
+        const double s = sqrt(5.0 * r2);
+        return (1.0 + s + (5.0 / 3.0) * r2) * exp(-s);
+    }
+}
+
+struct KmatParams {
+    int64_t n, n_pad;       // training points (real / padded)
+    int64_t rows_pad;       // CROSS: padded number of test points (m_pad)
+    int d, dbox;            // input dims, dims per TMA box
+    int hyper_stride;       // doubles per output in hyper (d + 2)
+    const double* hyper;    // [count][d+2]
+    double* out;            // SYM: matrix slab base; CROSS: workspace slab base
+    int64_t out_row_base;   // SYM: first row of this output inside the slab
+    int64_t out_stride;     // CROSS: rows per output in the workspace slab
+    const double* alpha;    // CROSS: [count][n_pad] or null
+    int64_t alpha_stride;
+    double* part;           // CROSS: [count][n_tiles][rows_pad] or null
+    int outs[MAXG];         // global output index handled by blockIdx.z (hyper/alpha rows)
+    int store;              // CROSS: write the matrix (0 when only the mean is wanted)
+    double nugget;          // SYM: value added on the diagonal
+};
+
+template <int KT, int CROSS>
+__global__ void __launch_bounds__(256, 1)
+kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC, const KmatParams p) {
+    __shared__ __align__(128) double Xr[DCH * 128];
+    __shared__ __align__(128) double Xc[DCH * 128];
+    __shared__ double w_s[256];  // up to 256 dims
+    __shared__ double al_s[128];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int I, J, o = 0;
+    if (CROSS) {
+        I = blockIdx.x;  // test tile
+        J = blockIdx.y;  // train tile
+        o = blockIdx.z;
+    } else {
+        const int id = blockIdx.x;
+        I = (int)((sqrtf(8.0f * (float)id + 1.0f) - 1.0f) * 0.5f);
+        while ((I + 1) * (I + 2) / 2 <= id) I++;
+        while (I * (I + 1) / 2 > id) I--;
+        J = id - I * (I + 1) / 2;
+    }
+    const double* hyp = p.hyper + (int64_t)p.outs[o] * p.hyper_stride;
+    for (int i = tid; i < 256; i += 256) w_s[i] = (i < p.d) ? hyp[i] : 0.0;
+    if (CROSS && tid < 128) al_s[tid] = p.alpha ? p.alpha[(int64_t)p.outs[o] * p.alpha_stride + (int64_t)J * 128 + tid] : 0.0;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    double r2[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) r2[a][b] = 0.0;
+
+    const int nchunk = (p.d + p.dbox - 1) / p.dbox;
+    uint32_t phase = 0;
+    for (int ch = 0; ch < nchunk; ch++) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar, 2u * 128u * (uint32_t)p.dbox * 8u);
+            tma_load_2d(Xr, &tmR, I * 128, ch * p.dbox, &bar);
+            tma_load_2d(Xc, &tmC, J * 128, ch * p.dbox, &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        const int dlim = min(p.dbox, p.d - ch * p.dbox);
+        for (int dd = 0; dd < dlim; dd++) {
+            const double wv = w_s[ch * p.dbox + dd];
+            double xr[8], xc[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) xr[a] = Xr[dd * 128 + ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 8; b++) xc[b] = Xc[dd * 128 + tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const double df = xr[a] - xc[b];
+                    r2[a][b] = fma(wv, df * df, r2[a][b]);
+                }
+        }
+        __syncthreads();  // single smem buffer: everyone done before the next box lands
+    }
+
+    const double sigma2 = hyp[p.d];
+    if (!CROSS) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int64_t row = (int64_t)I * 128 + ty + 16 * a;
+            double* orow = p.out + (p.out_row_base + row) * p.n_pad;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int64_t col = (int64_t)J * 128 + tx + 16 * b;
+                double v = sigma2 * kfun<KT>(r2[a][b]);
+                if (row == col) v += p.nugget;
+                if (row >= p.n || col >= p.n) v = (row == col) ? 1.0 : 0.0;
+                orow[col] = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int64_t row = (int64_t)I * 128 + ty + 16 * a;  // test point
+            double* orow = p.out + ((int64_t)o * p.out_stride + row) * p.n_pad;
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int64_t col = (int64_t)J * 128 + tx + 16 * b;  // training point
+                double v = sigma2 * kfun<KT>(r2[a][b]);
+                if (col >= p.n) v = 0.0;
+                if (p.store) orow[col] = v;
+                s = fma(v, al_s[tx + 16 * b], s);
+            }
+            if (p.part) {
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (tx == 0) p.part[((int64_t)o * gridDim.y + J) * p.rows_pad + row] = s;
+            }
+        }
+    }
+}
+
+struct OutList {
+    int outs[MAXG];
+};
+
+__global__ void mean_reduce_kernel(const double* __restrict__ part, int n_tiles, int64_t m_pad, int64_t m,
+                                   double* __restrict__ mean, int64_t mean_stride, const OutList ol) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y;
+    if (c >= m) return;
+    double s = 0.0;
+    for (int J = 0; J < n_tiles; J++) s += part[((int64_t)o * n_tiles + J) * m_pad + c];
+    mean[(int64_t)ol.outs[o] * mean_stride + c] = s;
+}
+
+int kmat_init() { return 0; }
+
+int kmat_dbox(int d) { return d < DCH ? d : DCH; }
+
+int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, int out_idx,
+             double nugget, double* A_slab, int64_t row_base, cudaStream_t st) {
+    KmatParams p{};
+    p.n = n; p.n_pad = n_pad; p.rows_pad = n_pad; p.d = d; p.dbox = kmat_dbox(d); p.hyper_stride = d + 2;
+    p.hyper = hyper; p.out = A_slab; p.out_row_base = row_base; p.outs[0] = out_idx; p.nugget = nugget;
+    const int T = (int)(n_pad / 128);
+    const int tiles = T * (T + 1) / 2;
+    if (kernel == MOGP_KERNEL_SQEXP)
+        kmat_kernel<MOGP_KERNEL_SQEXP, 0><<<tiles, 256, 0, st>>>(tmXT, tmXT, p);
+    else
+        kmat_kernel<MOGP_KERNEL_MATERN52, 0><<<tiles, 256, 0, st>>>(tmXT, tmXT, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int kmat_cross(const CUtensorMap& tmXsT, const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int64_t m_pad,
+               int d, const int* outs, int count, const double* hyper, double* W_slab, int64_t w_stride, int store,
+               const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st) {
+    KmatParams p{};
+    p.n = n; p.n_pad = n_pad; p.rows_pad = m_pad; p.d = d; p.dbox = kmat_dbox(d); p.hyper_stride = d + 2;
+    p.hyper = hyper; p.out = W_slab; p.out_stride = w_stride; p.alpha = alpha; p.alpha_stride = alpha_stride;
+    p.part = part; p.store = store;
+    for (int i = 0; i < count; i++) p.outs[i] = outs[i];
+    dim3 grid((unsigned)(m_pad / 128), (unsigned)(n_pad / 128), (unsigned)count);
+    if (kernel == MOGP_KERNEL_SQEXP)
+        kmat_kernel<MOGP_KERNEL_SQEXP, 1><<<grid, 256, 0, st>>>(tmXsT, tmXT, p);
+    else
+        kmat_kernel<MOGP_KERNEL_MATERN52, 1><<<grid, 256, 0, st>>>(tmXsT, tmXT, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int64_t m_pad, int64_t m, double* mean,
+                int64_t mean_stride, cudaStream_t st) {
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)count);
+    OutList ol{};
+    for (int i = 0; i < count; i++) ol.outs[i] = outs[i];
+    mean_reduce_kernel<<<grid, 256, 0, st>>>(part, n_tiles, m_pad, m, mean, mean_stride, ol);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace mogp

@@ -1,0 +1,252 @@
+"""ctypes binding of libmogp_b200.so -- the counterpart of the reference's ``LibGPGPU.py``
+(mogp_emulator/LibGPGPU.py:1-14), which imports the pybind11 module ``libgpgpu``.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``build.sh`` and contains sm_100a
+code only.  There is no CPU fallback: every entry point needs a B200.  ``gpu_usable()`` mirrors
+``LibGPGPU.gpu_usable`` (LibGPGPU.py:13).
+"""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmogp_b200.so")
+
+OK, ERR_CUDA, ERR_ARG, ERR_NOT_PD, ERR_NOT_FIT, ERR_NCCL, ERR_NOMEM = range(7)
+GET_K, GET_L, GET_ALPHA, GET_KINV = range(4)
+
+
+class nugget_type(enum.IntEnum):
+    """mogp_gpu/src/types.hpp:29 -- numeric values are part of the Python contract."""
+    adaptive = 0
+    fit = 1
+    fixed = 2
+
+
+class kernel_type(enum.IntEnum):
+    """mogp_gpu/src/types.hpp:32."""
+    SquaredExponential = 0
+    Matern52 = 1
+
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int_p = ctypes.POINTER(ctypes.c_int32)
+
+#: every symbol declared in include/mogp_b200.h with its ctypes signature
+SIGNATURES = {
+    "mogp_version": (ctypes.c_int, [_c_int_p, _c_int_p]),
+    "mogp_device_count": (ctypes.c_int, [_c_int_p]),
+    "mogp_last_error": (ctypes.c_char_p, []),
+    "mogp_create": (ctypes.c_int, [_c_double_p, ctypes.c_int64, ctypes.c_int32, _c_double_p, ctypes.c_int32,
+                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_int32, ctypes.c_int32,
+                                   ctypes.POINTER(ctypes.c_void_p)]),
+    "mogp_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mogp_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p, ctypes.c_int32,
+                                _c_double_p, _c_double_p, _c_double_p, _c_int_p]),
+    "mogp_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "mogp_is_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_int_p]),
+    "mogp_predict": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                    _c_double_p, _c_double_p, _c_int_p]),
+    "mogp_predict_allgather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_double_p, ctypes.c_int64,
+                                              ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, _c_int_p]),
+    "mogp_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p]),
+    "mogp_logpost_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int32]),
+    "mogp_timings": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int32]),
+    "mogp_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "mogp_comm_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "mogp_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mogp_comm_allreduce_max": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
+    "mogp_peak_dmma": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_double_p]),
+}
+
+_lib = None
+_load_error = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib, _load_error
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        _load_error = "libmogp_b200.so not found at %s (run `python -c 'import __graft_entry__ as g; g.build()'`)" % LIB_PATH
+        raise RuntimeError(_load_error)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+try:
+    load()
+    HAVE_LIBMOGP = True
+except (RuntimeError, OSError, AttributeError) as exc:  # pragma: no cover - depends on the build
+    HAVE_LIBMOGP = False
+    _load_error = str(exc)
+
+
+def device_count():
+    if not HAVE_LIBMOGP:
+        return 0
+    c = ctypes.c_int32(0)
+    _lib.mogp_device_count(ctypes.byref(c))
+    return int(c.value)
+
+
+def gpu_usable():
+    """True when the library is loaded and at least one sm_100 device is visible."""
+    return HAVE_LIBMOGP and device_count() > 0
+
+
+def last_error():
+    return _lib.mogp_last_error().decode("utf-8", "replace") if _lib is not None else (_load_error or "")
+
+
+def check(status, what=""):
+    """Map a status code to the exception type the reference's front-end raises
+    (std::runtime_error -> RuntimeError, densegp_gpu.hpp:495,556-570; ValueError for predict-before-fit,
+    GaussianProcessGPU.py:589)."""
+    if status == OK:
+        return
+    msg = "%s%s" % (what + ": " if what else "", last_error())
+    if status == ERR_NOT_FIT:
+        raise ValueError("hyperparameters have not been fit for this Gaussian Process")
+    if status == ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def as_f64(a):
+    """C-contiguous float64 view/copy (the reference's ndarray_coerce_type_and_flags,
+    GaussianProcessGPU.py:29-54)."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def dptr(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(_c_int_p)
+
+
+def peak_dmma_tflops(device=0, iters=20000):
+    """Measured DMMA (FP64 tensor pipe) issue peak of the device, TFLOP/s."""
+    v = ctypes.c_double(0.0)
+    check(_lib.mogp_peak_dmma(int(device), int(iters), ctypes.byref(v)), "mogp_peak_dmma")
+    return float(v.value)
+
+
+class Handle(object):
+    """Owner of one mogp_handle (a bank of E outputs over shared inputs on one GPU)."""
+
+    def __init__(self, inputs, targets, kernel, nug_type, nugget=0.0, device=0, n_streams=0):
+        if not HAVE_LIBMOGP:
+            raise RuntimeError("Cannot construct a GPU Gaussian process: " + (_load_error or "library not loaded"))
+        inputs = as_f64(inputs)
+        targets = as_f64(targets)
+        assert inputs.ndim == 2 and targets.ndim == 2 and targets.shape[1] == inputs.shape[0]
+        self.n, self.d = inputs.shape
+        self.n_out = targets.shape[0]
+        self._h = ctypes.c_void_p()
+        check(_lib.mogp_create(dptr(inputs), self.n, self.d, dptr(targets), self.n_out, int(kernel), int(nug_type),
+                               float(nugget), int(device), int(n_streams), ctypes.byref(self._h)), "mogp_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.mogp_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def fit(self, first, thetas):
+        thetas = as_f64(thetas)
+        if thetas.ndim == 1:
+            thetas = thetas.reshape(1, -1)
+        count, n_params = thetas.shape
+        quad = np.zeros(count)
+        logdet = np.zeros(count)
+        nug = np.zeros(count)
+        status = np.zeros(count, dtype=np.int32)
+        check(_lib.mogp_fit(self._h, int(first), int(count), dptr(thetas), int(n_params), dptr(quad), dptr(logdet),
+                            dptr(nug), iptr(status)), "mogp_fit")
+        return quad, logdet, nug, status
+
+    def reset(self, idx=-1):
+        check(_lib.mogp_reset(self._h, int(idx)))
+
+    def is_fit(self, idx):
+        out = ctypes.c_int32(0)
+        check(_lib.mogp_is_fit(self._h, int(idx), ctypes.byref(out)))
+        return bool(out.value)
+
+    def predict(self, testing, want_var=True, include_nugget=True):
+        testing = as_f64(testing)
+        m = testing.shape[0]
+        mean = np.empty((self.n_out, m))
+        var = np.empty((self.n_out, m)) if want_var else None
+        status = np.zeros(self.n_out, dtype=np.int32)
+        check(_lib.mogp_predict(self._h, dptr(testing), m, int(bool(want_var)), int(bool(include_nugget)), dptr(mean),
+                                dptr(var) if want_var else None, iptr(status)), "mogp_predict")
+        return mean, var, status
+
+    def predict_allgather(self, comm, testing, include_nugget, e_pad):
+        testing = as_f64(testing)
+        m = testing.shape[0]
+        rows = comm.world * e_pad
+        mean = np.empty((rows, m))
+        var = np.empty((rows, m))
+        status = np.zeros(rows, dtype=np.int32)
+        check(_lib.mogp_predict_allgather(self._h, comm._c, dptr(testing), m, int(bool(include_nugget)), int(e_pad),
+                                          dptr(mean), dptr(var), iptr(status)), "mogp_predict_allgather")
+        return mean, var, status
+
+    def get(self, idx, which):
+        shape = (self.n,) if which == GET_ALPHA else (self.n, self.n)
+        out = np.zeros(shape)
+        check(_lib.mogp_get(self._h, int(idx), int(which), dptr(out)), "mogp_get")
+        return out
+
+    def logpost_grad(self, idx, n_params):
+        out = np.zeros(n_params)
+        check(_lib.mogp_logpost_grad(self._h, int(idx), dptr(out), int(n_params)), "mogp_logpost_grad")
+        return out
+
+    def timings(self, reset=False):
+        out = np.zeros(9)
+        check(_lib.mogp_timings(self._h, dptr(out), 9, int(reset)))
+        keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms"]
+        return dict(zip(keys, out.tolist()))
+
+
+class Comm(object):
+    """One NCCL communicator rank (mogp_comm)."""
+
+    def __init__(self, uid, rank, world, device):
+        self.rank, self.world = int(rank), int(world)
+        self._c = ctypes.c_void_p()
+        check(_lib.mogp_comm_create(uid, self.rank, self.world, int(device), ctypes.byref(self._c)), "mogp_comm_create")
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        check(_lib.mogp_comm_unique_id(buf), "mogp_comm_unique_id")
+        return buf.raw
+
+    def allreduce_max(self, value):
+        v = ctypes.c_double(float(value))
+        check(_lib.mogp_comm_allreduce_max(self._c, ctypes.byref(v)), "mogp_comm_allreduce_max")
+        return float(v.value)
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c.value and _lib is not None:
+            _lib.mogp_comm_destroy(self._c)
+            self._c = ctypes.c_void_p()
+
+    __del__ = close

@@ -1,0 +1,178 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI via the
+drop-in Python classes, against (a) golden outputs of the unmodified reference (tests/golden/*.npz),
+(b) known answers from the reference's own tests, and (c) the CPU oracle on seeded inputs."""
+import glob
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import gp_oracle as orc
+from golden import known_answers as ka
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SINGLE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                if not os.path.basename(p).startswith("multi_"))
+MULTI = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "multi_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def mogp():
+    import mogp_emulator_b200 as m
+    assert m.gpu_usable(), "libmogp_b200.so not loaded or no B200 visible: the GPU tests must not fall back"
+    return m
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _logpost_rtol(K, nugget):
+    """current_logpost contains y^T K^-1 y, which two correct FP64 algorithms reproduce only to about
+    cond(K) * eps: 1e-9 for well-conditioned matrices, looser beyond."""
+    cond = np.linalg.cond(K + nugget * np.eye(K.shape[0]))
+    return max(1.0e-9, 4.0 * cond * np.finfo(np.float64).eps)
+
+
+def _nugget_arg(g):
+    t = str(g["nugget_type"])
+    return float(g["nugget_in"]) if t == "fixed" else t
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_single_output_matches_reference_golden(mogp, name):
+    g = _load(name)
+    gp = mogp.GaussianProcessGPU(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
+    gp.fit(g["theta"])
+    n = g["X"].shape[0]
+    # kernel matrix (no nugget), factor, alpha, log-posterior with the reference's default priors
+    assert_allclose(gp.get_K_matrix(), g["K"], rtol=1e-13, atol=1e-15)
+    nug = float(g["nugget_out"])
+    assert_allclose(gp.nugget, nug, rtol=1e-14, atol=0.0)
+    well_conditioned = "dup" not in name
+    if well_conditioned:
+        assert_allclose(gp.L, g["L"], rtol=1e-7, atol=1e-10)
+        assert_allclose(gp.Kinv_t, g["Kinv_t"], rtol=1e-6, atol=1e-6 * np.abs(g["Kinv_t"]).max())
+    assert_allclose(gp.current_logpost, np.asarray(g["logpost"]).reshape(-1)[0], rtol=_logpost_rtol(g["K"], nug))
+    mean, var, _ = gp.predict(g["Xs"])
+    scale = np.abs(g["mean"]).max()
+    assert_allclose(mean, g["mean"], rtol=1e-6, atol=1e-6 * scale)
+    assert_allclose(var, g["var"], rtol=1e-4, atol=1e-4 * max(nug, 1e-8))
+    _, var_nn, _ = gp.predict(g["Xs"], include_nugget=False)
+    assert_allclose(var_nn, g["var_no_nugget"], rtol=1e-4, atol=1e-4 * max(nug, 1e-8))
+    assert gp.predict(g["Xs"], unc=False).unc is None
+    assert_allclose(gp.predict(g["Xs"], unc=False).mean, mean, rtol=1e-12, atol=1e-12 * scale)
+    assert mean.shape == (g["Xs"].shape[0],) and var.shape == mean.shape and n == gp.n
+
+
+@pytest.mark.parametrize("name", MULTI)
+def test_multi_output_matches_reference_golden(mogp, name):
+    g = _load(name)
+    gp = mogp.MultiOutputGP_GPU(g["X"], g["Y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
+    assert gp.get_indices_fit() == []
+    gp.fit(g["thetas"])
+    assert gp.get_indices_not_fit() == []
+    mean, var, _ = gp.predict(g["Xs"])
+    assert mean.shape == g["mean"].shape
+    assert_allclose(mean, g["mean"], rtol=1e-6, atol=1e-6 * np.abs(g["mean"]).max())
+    assert_allclose(var, g["var"], rtol=1e-4, atol=1e-4 * max(float(np.max(g["nuggets"])), 1e-8))
+    for i in range(gp.n_emulators):
+        th = g["thetas"][i]
+        K = np.exp(th[gp.D]) * orc.kernel_f(g["X"], g["X"], th[:gp.D], str(g["kernel"]))
+        assert_allclose(gp.logposterior(i), g["logposts"][i], rtol=_logpost_rtol(K, float(g["nuggets"][i])))
+    nug = gp.nugget if isinstance(gp.nugget, list) else [gp.nugget] * gp.n_emulators
+    assert_allclose(nug, g["nuggets"], rtol=1e-14)
+
+
+def test_kernel_known_answers(mogp):
+    # scaled squared distances / closed forms pinned by the reference's tests (tests/golden/known_answers.py),
+    # exercised through get_K_matrix on the stacked point set [x1; x2]
+    for x1, x2, theta, want_r2 in ka.R2_CASES:
+        pts = np.vstack([x1, x2])
+        y = np.arange(pts.shape[0], dtype=np.float64)
+        n1 = x1.shape[0]
+        for kern, f in (("SquaredExponential", lambda r2: np.exp(-0.5 * r2)), ("Matern52", ka.matern52_closed_form)):
+            gp = mogp.GaussianProcessGPU(pts, y, kernel=kern, nugget=1.0)
+            gp.fit(np.append(theta, 0.0))
+            K = gp.get_K_matrix()
+            assert_allclose(K[:n1, n1:], f(want_r2), rtol=1e-14)
+            assert_allclose(np.diag(K), 1.0, rtol=0, atol=0)
+
+
+def test_cholesky_known_answers_through_gp(mogp):
+    # A 3-point GP whose kernel matrix is the reference's near-singular test matrix:
+    # K = [[1,1,c],[1,1,c],[c,c,1]] arises from points x0 == x1 and x2 with exp(-r2/2) = c
+    c = 0.0067379469990855
+    r = np.sqrt(-2.0 * np.log(c))
+    X = np.array([[0.0], [0.0], [r]])
+    y = np.array([1.0, 1.0, 2.0])
+    gp = mogp.GaussianProcessGPU(X, y, nugget=ka.CHOL_NEAR_SINGULAR_NUGGET)
+    gp.fit(np.zeros(2))
+    assert_allclose(gp.L, ka.CHOL_NEAR_SINGULAR_L, rtol=1e-9, atol=1e-14)
+    # adaptive: the plain factorisation must fail and the first jitter (1e-6 * mean diag) must succeed
+    gpa = mogp.GaussianProcessGPU(X, y, nugget="adaptive")
+    gpa.fit(np.zeros(2))
+    assert_allclose(gpa.nugget, 1.0e-6, rtol=1e-14)
+    assert_allclose(gpa.L, ka.CHOL_NEAR_SINGULAR_L, rtol=1e-9, atol=1e-14)
+    # fixed nugget 0 on the singular matrix: not positive definite -> RuntimeError, emulator left unfit
+    gp0 = mogp.GaussianProcessGPU(X, y, nugget=0.0)
+    with pytest.raises(RuntimeError):
+        gp0.fit(np.zeros(2))
+    assert not gp0.theta.data_has_been_set()
+    with pytest.raises(ValueError):
+        gp0.predict(np.array([[0.5]]))
+
+
+def test_variance_stability_case(mogp):
+    c = ka.VAR_STABILITY
+    gp = mogp.GaussianProcessGPU(c["x"], c["y"], nugget=c["nugget"])
+    gp.fit(c["theta"])
+    _, var, _ = gp.predict(c["testing"])
+    assert_allclose(np.zeros(101), var, atol=c["atol"])
+
+
+@pytest.mark.parametrize("kernel,nugget,n,d,m", [
+    ("SquaredExponential", 1e-6, 256, 4, 1000),      # BASELINE.json configs[0] (C1)
+    ("Matern52", "adaptive", 700, 20, 333),          # ragged n, d > one TMA box, ragged m
+    ("SquaredExponential", 1e-6, 1153, 10, 2500),    # 10 block rows, ragged
+])
+def test_seeded_parity_against_oracle(mogp, kernel, nugget, n, d, m):
+    X, Y, Xs = orc.make_workload(n, d, 1, m, seed=n)
+    theta = np.append(np.full(d, 1.0), 0.0)
+    ref = orc.OracleGP(X, Y[0], kernel=kernel, nugget=nugget).fit(theta)
+    rmean, rvar = ref.predict(Xs)
+    gp = mogp.GaussianProcessGPU(X, Y[0], kernel=kernel, nugget=nugget)
+    gp.fit(theta)
+    assert_allclose(gp.nugget, ref.nugget, rtol=1e-14)
+    assert_allclose(gp.current_logpost, ref.current_logpost, rtol=_logpost_rtol(ref.get_K_matrix(), ref.nugget))
+    assert_allclose(gp.L, ref.L, rtol=1e-7, atol=1e-10)
+    mean, var, _ = gp.predict(Xs)
+    assert_allclose(mean, rmean, rtol=1e-6, atol=1e-6 * np.abs(rmean).max())
+    assert_allclose(var, rvar, rtol=1e-4, atol=1e-4 * max(ref.nugget, 1e-8))
+
+
+def test_multi_output_not_fit_semantics(mogp):
+    X, Y, Xs = orc.make_workload(150, 3, 4, 50, seed=5)
+    gp = mogp.MultiOutputGP_GPU(X, Y, nugget=1e-6)
+    thetas = np.tile(np.array([1.0, 1.0, 1.0, 0.0]), (4, 1))
+    with pytest.raises(ValueError):
+        gp.predict(Xs)
+    gp.fit_emulator(1, thetas[1])
+    gp.fit_emulator(3, thetas[3])
+    assert gp.get_indices_fit() == [1, 3] and gp.get_indices_not_fit() == [0, 2]
+    with pytest.raises(ValueError):
+        gp.predict(Xs)
+    mean, var, _ = gp.predict(Xs, allow_not_fit=True)
+    assert np.all(np.isnan(mean[[0, 2]])) and np.all(np.isnan(var[[0, 2]]))
+    ref = orc.OracleGP(X, Y[1], nugget=1e-6).fit(thetas[1])
+    rmean, rvar = ref.predict(Xs)
+    assert_allclose(mean[1], rmean, rtol=1e-6, atol=1e-8)
+    assert_allclose(var[1], rvar, rtol=1e-4, atol=1e-10)
+    gp.reset_fit_status()
+    assert gp.get_indices_fit() == []
+    with pytest.raises(RuntimeError):
+        gp.fit(np.zeros((4, 7)))
