@@ -199,14 +199,14 @@ def run_b200(args, wl):
 
     # end to end from host arrays: construct (H2D of X and Y) + fit + predict (+ gather) + posteriors on the host
     del gp
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         gp2 = MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget, device=device, comm=comm)
         res2 = step(gp2)
         del gp2
-    e2e = sync_max((time.perf_counter() - t0) / e2e_steps)
+    e2e = sync_max((time.perf_counter() - t0) / max(e2e_steps, 1)) if e2e_steps else None
 
     if rank != 0:
         return
@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
