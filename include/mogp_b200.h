@@ -53,6 +53,8 @@ const char* mogp_last_error(void);
 int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t n_out, int32_t kernel,
                 int32_t nugget_type, double nugget, int32_t device, int32_t n_streams, mogp_handle** out);
 int mogp_destroy(mogp_handle* h);
+/* Handles return their device / pinned buffers to a process-wide cache for reuse; this releases the cache. */
+int mogp_trim(void);
 
 /* replaces DenseGP_GPU::fit(theta) (densegp_gpu.hpp:493-612) / MultiOutputGP_GPU::fit(thetas),
  * fit_emulator(idx, theta) (multioutputgp_gpu.hpp:150-181); semantics follow the CPU

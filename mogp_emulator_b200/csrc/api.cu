@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "nccl_dyn.h"
+#include "pool.h"
 
 namespace mogp {
 
@@ -120,18 +121,17 @@ struct mogp_comm {
         }                                                                                            \
     } while (0)
 
-static int grow(double** p, size_t* cap, size_t bytes, bool pinned = false) {
+static int grow(double** p, size_t* cap, size_t bytes, int device) {
+    // device == -1: pinned host
     if (*cap >= bytes) return MOGP_OK;
     if (*p) {
-        if (pinned) cudaFreeHost(*p);
-        else cudaFree(*p);
+        pool_free(*p);
         *p = nullptr;
         *cap = 0;
     }
-    cudaError_t e = pinned ? cudaMallocHost((void**)p, bytes) : cudaMalloc((void**)p, bytes);
-    if (e != cudaSuccess) {
-        set_error("allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-        cudaGetLastError();
+    *p = (double*)pool_alloc(bytes, device);
+    if (!*p) {
+        set_error("allocation of %zu bytes failed (device %d)", bytes, device);
         return MOGP_ERR_NOMEM;
     }
     *cap = bytes;
@@ -174,14 +174,9 @@ int mogp_destroy(mogp_handle* h) {
     cudaEvent_t evs[5] = {h->ev_fork, h->ev_a, h->ev_b, h->ev_c, h->ev_d};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
-    double* dev[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G};
-    for (auto p : dev)
-        if (p) cudaFree(p);
-    if (h->info) cudaFree(h->info);
-    double* host[] = {h->h_hyper, h->h_scal, h->h_res, h->h_XsT};
-    for (auto p : host)
-        if (p) cudaFreeHost(p);
-    if (h->h_info) cudaFreeHost(h->h_info);
+    void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
+                    h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info};
+    for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
     return MOGP_OK;
@@ -258,18 +253,28 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     CREATE_CUDA(cudaEventCreate(&h->ev_b));
     CREATE_CUDA(cudaEventCreate(&h->ev_c));
     CREATE_CUDA(cudaEventCreate(&h->ev_d));
-    CREATE_CUDA(cudaMalloc(&h->XT, sizeof(double) * d * np));
-    CREATE_CUDA(cudaMalloc(&h->Y, sizeof(double) * n_out * np));
-    CREATE_CUDA(cudaMalloc(&h->A, sizeof(double) * (size_t)n_out * np * np));
-    CREATE_CUDA(cudaMalloc(&h->Dinv, sizeof(double) * (size_t)n_out * np * NB));
-    CREATE_CUDA(cudaMalloc(&h->alpha, sizeof(double) * n_out * np));
-    CREATE_CUDA(cudaMalloc(&h->z, sizeof(double) * n_out * np));
-    CREATE_CUDA(cudaMalloc(&h->hyper, sizeof(double) * n_out * (d + 2)));
-    CREATE_CUDA(cudaMalloc(&h->scal, sizeof(double) * n_out * 2));
-    CREATE_CUDA(cudaMalloc(&h->info, sizeof(int) * n_out));
-    CREATE_CUDA(cudaMallocHost(&h->h_hyper, sizeof(double) * n_out * (d + 2)));
-    CREATE_CUDA(cudaMallocHost(&h->h_scal, sizeof(double) * n_out * 2));
-    CREATE_CUDA(cudaMallocHost(&h->h_info, sizeof(int) * n_out));
+#define CREATE_ALLOC(ptr, type, bytes, dev)                                                          \
+    do {                                                                                             \
+        ptr = (type*)pool_alloc((bytes), (dev));                                                     \
+        if (!ptr) {                                                                                  \
+            set_error("mogp_create: allocation of %zu bytes failed", (size_t)(bytes));               \
+            mogp_destroy(h);                                                                         \
+            return MOGP_ERR_NOMEM;                                                                   \
+        }                                                                                            \
+    } while (0)
+    CREATE_ALLOC(h->XT, double, sizeof(double) * d * np, device);
+    CREATE_ALLOC(h->Y, double, sizeof(double) * n_out * np, device);
+    CREATE_ALLOC(h->A, double, sizeof(double) * (size_t)n_out * np * np, device);
+    CREATE_ALLOC(h->Dinv, double, sizeof(double) * (size_t)n_out * np * NB, device);
+    CREATE_ALLOC(h->alpha, double, sizeof(double) * n_out * np, device);
+    CREATE_ALLOC(h->z, double, sizeof(double) * n_out * np, device);
+    CREATE_ALLOC(h->hyper, double, sizeof(double) * n_out * (d + 2), device);
+    CREATE_ALLOC(h->scal, double, sizeof(double) * n_out * 2, device);
+    CREATE_ALLOC(h->info, int, sizeof(int) * n_out, device);
+    CREATE_ALLOC(h->h_hyper, double, sizeof(double) * n_out * (d + 2), -1);
+    CREATE_ALLOC(h->h_scal, double, sizeof(double) * n_out * 2, -1);
+    CREATE_ALLOC(h->h_info, int, sizeof(int) * n_out, -1);
+#undef CREATE_ALLOC
     {
         // transposed, zero-padded design matrix and zero-padded targets
         std::vector<double> xt((size_t)d * np, 0.0), yp((size_t)n_out * np, 0.0);
@@ -424,14 +429,14 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
     for (int o = 0; o < h->E; o++)
         if (h->fitted[o]) fit_idx.push_back(o);
     int rc;
-    if ((rc = grow(&h->res, &h->res_cap, sizeof(double) * (size_t)h->E * 2 * m))) return rc;
+    if ((rc = grow(&h->res, &h->res_cap, sizeof(double) * (size_t)h->E * 2 * m, h->device))) return rc;
     API_CUDA(cudaMemsetAsync(h->res, 0xFF, sizeof(double) * (size_t)h->E * 2 * m, h->main));  // all-ones == NaN
     if (fit_idx.empty() || m == 0) return MOGP_OK;
 
     // group / chunk sizes under a workspace budget
     size_t free_b = 0, total_b = 0;
     API_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = (size_t)((free_b + h->W_cap) * 0.6);
+    const size_t budget = (size_t)((free_b + h->W_cap + pool_cached_bytes()) * 0.6);
     int64_t mc_max = m;
     while ((size_t)(round_up(mc_max, 128) + 128) * np * 8 > budget && mc_max > 128) mc_max = (mc_max + 1) / 2;
     for (int64_t m0 = 0; m0 < m; m0 += mc_max) {
@@ -449,10 +454,10 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
             // budget above assumed); the kernel-matrix kernel fills all w_stride rows (zero-padded test points)
             const int64_t w_stride = round_up(mc, 128) + 128;
             const int n_tiles = (int)(np / 128);
-            if ((rc = grow(&h->XsT, &h->XsT_cap, sizeof(double) * d * w_stride))) return rc;
-            if ((rc = grow(&h->h_XsT, &h->h_XsT_cap, sizeof(double) * d * w_stride, true))) return rc;
-            if (want_var && (rc = grow(&h->W, &h->W_cap, sizeof(double) * (size_t)cnt * w_stride * np))) return rc;
-            if ((rc = grow(&h->part, &h->part_cap, sizeof(double) * (size_t)cnt * n_tiles * w_stride))) return rc;
+            if ((rc = grow(&h->XsT, &h->XsT_cap, sizeof(double) * d * w_stride, h->device))) return rc;
+            if ((rc = grow(&h->h_XsT, &h->h_XsT_cap, sizeof(double) * d * w_stride, -1))) return rc;
+            if (want_var && (rc = grow(&h->W, &h->W_cap, sizeof(double) * (size_t)cnt * w_stride * np, h->device))) return rc;
+            if ((rc = grow(&h->part, &h->part_cap, sizeof(double) * (size_t)cnt * n_tiles * w_stride, h->device))) return rc;
             if (g0 == 0) {
                 memset(h->h_XsT, 0, sizeof(double) * d * w_stride);
                 for (int64_t i = 0; i < mc; i++)
@@ -510,7 +515,7 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
     if (m == 0) return MOGP_OK;
     int rc = predict_device(h, Xs, m, want_var, include_nugget);
     if (rc) return rc;
-    if ((rc = grow(&h->h_res, &h->h_res_cap, sizeof(double) * (size_t)h->E * 2 * m, true))) return rc;
+    if ((rc = grow(&h->h_res, &h->h_res_cap, sizeof(double) * (size_t)h->E * 2 * m, -1))) return rc;
     API_CUDA(cudaMemcpyAsync(h->h_res, h->res, sizeof(double) * (size_t)h->E * 2 * m, cudaMemcpyDeviceToHost, h->main));
     API_CUDA(cudaStreamSynchronize(h->main));
     for (int o = 0; o < h->E; o++) {
@@ -541,8 +546,11 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
     }
     if (which == MOGP_GET_K) {
         // recomputed (the factor overwrote it): sigma2*k(X,X) without the nugget (GaussianProcess.get_K_matrix)
-        double* tmp = nullptr;
-        API_CUDA(cudaMalloc(&tmp, sizeof(double) * np * np));
+        double* tmp = (double*)pool_alloc(sizeof(double) * np * np, h->device);
+        if (!tmp) {
+            set_error("get K: allocation failed");
+            return MOGP_ERR_NOMEM;
+        }
         int rc = kmat_sym(h->tmXT, h->kernel, n, np, h->d, h->hyper, idx, 0.0, tmp, 0, h->main);
         if (rc == 0) {
             cudaError_t e = cudaMemcpy2DAsync(out, sizeof(double) * n, tmp, sizeof(double) * np, sizeof(double) * n, n,
@@ -550,7 +558,7 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->main);
             rc = e == cudaSuccess ? 0 : 1;
         }
-        cudaFree(tmp);
+        pool_free(tmp);
         if (rc) {
             set_error("get K failed: %s", cudaGetErrorString(cudaGetLastError()));
             return MOGP_ERR_CUDA;
@@ -567,6 +575,11 @@ int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_param
     (void)h; (void)idx; (void)grad; (void)n_params;
     set_error("mogp_logpost_grad: not built yet");
     return MOGP_ERR_ARG;
+}
+
+int mogp_trim(void) {
+    pool_trim();
+    return MOGP_OK;
 }
 
 int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset) {
@@ -629,10 +642,10 @@ int mogp_comm_destroy(mogp_comm* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (api && c->comm) api->CommDestroy(c->comm);
     if (c->stream) cudaStreamDestroy(c->stream);
-    if (c->sendbuf) cudaFree(c->sendbuf);
-    if (c->recvbuf) cudaFree(c->recvbuf);
+    pool_free(c->sendbuf);
+    pool_free(c->recvbuf);
+    pool_free(c->h_recv);
     if (c->dscalar) cudaFree(c->dscalar);
-    if (c->h_recv) cudaFreeHost(c->h_recv);
     delete c;
     return MOGP_OK;
 }
@@ -664,9 +677,9 @@ int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, in
     if (rc) return rc;
     const size_t blk = (size_t)e_pad * 2 * m;  // doubles per rank; one extra row-pair block carries the status words
     const size_t send_n = blk + e_pad;
-    if ((rc = grow(&comm->sendbuf, &comm->send_cap, sizeof(double) * send_n))) return rc;
-    if ((rc = grow(&comm->recvbuf, &comm->recv_cap, sizeof(double) * send_n * comm->world))) return rc;
-    if ((rc = grow(&comm->h_recv, &comm->h_cap, sizeof(double) * send_n * comm->world, true))) return rc;
+    if ((rc = grow(&comm->sendbuf, &comm->send_cap, sizeof(double) * send_n, comm->device))) return rc;
+    if ((rc = grow(&comm->recvbuf, &comm->recv_cap, sizeof(double) * send_n * comm->world, comm->device))) return rc;
+    if ((rc = grow(&comm->h_recv, &comm->h_cap, sizeof(double) * send_n * comm->world, -1))) return rc;
     // pack: [e_pad][2][m] results (NaN for padding rows) + e_pad status words (as doubles)
     API_CUDA(cudaMemsetAsync(comm->sendbuf, 0xFF, sizeof(double) * blk, h->main));
     API_CUDA(cudaMemcpyAsync(comm->sendbuf, h->res, sizeof(double) * (size_t)h->E * 2 * m, cudaMemcpyDeviceToDevice, h->main));

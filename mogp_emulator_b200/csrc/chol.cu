@@ -217,8 +217,8 @@ chol_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  double* __restrict__ A, int64_t ld, int row_base, int kblk, const int* __restrict__ info) {
     // A: slab base; row_base: first slab row of this output's matrix (also its first Dinv slab row)
     using Cfg = TileCfg<WGM, WGN, NT, NS>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    extern __shared__ __align__(128) unsigned char tile_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tile_smem_raw) + 127) & ~uintptr_t(127));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + NS * Cfg::STAGE_BYTES);
     uint64_t* empty = full + NS;
 

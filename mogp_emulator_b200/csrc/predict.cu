@@ -55,8 +55,8 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
     using Cfg = PredCfg<NT>;
     constexpr int NS = Cfg::NS;
     constexpr int BN = Cfg::BN;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    extern __shared__ __align__(128) unsigned char pred_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pred_smem_raw) + 127) & ~uintptr_t(127));
     double* VS = reinterpret_cast<double*>(base + NS * Cfg::STAGE_BYTES);  // [128/8][BN][8]
     uint64_t* full = reinterpret_cast<uint64_t*>(base + NS * Cfg::STAGE_BYTES + Cfg::VS_BYTES);
     uint64_t* empty = full + NS;

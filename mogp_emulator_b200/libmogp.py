@@ -43,6 +43,7 @@ SIGNATURES = {
                                    ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_int32, ctypes.c_int32,
                                    ctypes.POINTER(ctypes.c_void_p)]),
     "mogp_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mogp_trim": (ctypes.c_int, []),
     "mogp_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p, ctypes.c_int32,
                                 _c_double_p, _c_double_p, _c_double_p, _c_int_p]),
     "mogp_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
@@ -134,6 +135,12 @@ def dptr(a):
 
 def iptr(a):
     return a.ctypes.data_as(_c_int_p)
+
+
+def trim():
+    """Release the library's cache of device / pinned buffers."""
+    if _lib is not None:
+        _lib.mogp_trim()
 
 
 def peak_dmma_tflops(device=0, iters=20000):

@@ -20,3 +20,42 @@ def gathered_rows(n_outputs, world):
         lo, hi, e_pad = shard_bounds(n_outputs, r, world)
         rows.extend(r * e_pad + k for k in range(hi - lo))
     return rows
+
+
+def pack_block(mean, var, fitted, e_pad):
+    """This rank's gather block, the layout libmogp_b200 sends through ncclAllGather
+    (csrc/api.cu: mogp_predict_allgather): ``[e_pad][2][m]`` results (NaN rows for padding / unfit outputs)
+    followed by ``e_pad`` status words (0 = ok, 4 = not fit, 2 = padding)."""
+    import numpy as np
+    e_loc, m = mean.shape
+    block = np.full(e_pad * 2 * m + e_pad, np.nan)
+    res = block[:e_pad * 2 * m].reshape(e_pad, 2, m)
+    status = block[e_pad * 2 * m:]
+    status[:] = 2.0
+    for k in range(e_loc):
+        if fitted[k]:
+            res[k, 0] = mean[k]
+            res[k, 1] = var[k]
+            status[k] = 0.0
+        else:
+            status[k] = 4.0
+    return block
+
+
+def unpack_gathered(gathered, n_outputs, world, m):
+    """(world, e_pad*2*m + e_pad) gathered blocks -> mean (E, m), var (E, m), status (E,) in output order."""
+    import numpy as np
+    e_pad = -(-int(n_outputs) // int(world))
+    gathered = np.asarray(gathered).reshape(world, e_pad * 2 * m + e_pad)
+    mean = np.empty((n_outputs, m))
+    var = np.empty((n_outputs, m))
+    status = np.empty(n_outputs, dtype=np.int32)
+    for r in range(world):
+        lo, hi, _ = shard_bounds(n_outputs, r, world)
+        res = gathered[r, :e_pad * 2 * m].reshape(e_pad, 2, m)
+        st = gathered[r, e_pad * 2 * m:]
+        for k in range(hi - lo):
+            mean[lo + k] = res[k, 0]
+            var[lo + k] = res[k, 1]
+            status[lo + k] = int(st[k])
+    return mean, var, status

@@ -1,0 +1,172 @@
+"""Host-side logic of the drop-in layer (no GPU): hyperparameter transforms and priors against the golden
+prior parameters produced by the unmodified reference, argument interpretation, PredictResult, sharding."""
+import glob
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import gp_oracle as orc
+from mogp_emulator_b200 import hyper, sharding
+from mogp_emulator_b200.GaussianProcessGPU import PredictResult, interpret_nugget
+from mogp_emulator_b200.kernels import interpret_kernel, SquaredExponential, Matern52
+from mogp_emulator_b200 import libmogp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SINGLE = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("multi_"))
+
+
+@pytest.mark.parametrize("path", SINGLE)
+def test_default_priors_match_reference(path):
+    g = np.load(path)
+    ntype = str(g["nugget_type"])
+    pri = hyper.GPPriors.default_priors(g["X"], g["X"].shape[1], ntype)
+    for p, (shape, scale) in zip(pri.corr, g["prior_corr"]):
+        if np.isnan(shape):
+            assert not isinstance(p, hyper.PriorDist)
+        else:
+            assert isinstance(p, hyper.InvGammaPrior)
+            assert_allclose([p.shape, p.scale], [shape, scale], rtol=1e-8)
+    if ntype == "fit":
+        assert_allclose([pri.nugget.shape, pri.nugget.scale], np.asarray(g["prior_nugget"]).reshape(-1), rtol=1e-8)
+    else:
+        assert pri.nugget is None
+
+
+@pytest.mark.parametrize("path", SINGLE)
+def test_prior_terms_reproduce_reference_logpost(path):
+    """data term (oracle) - logp(priors) == the reference's current_logpost; prior gradient matches the oracle's."""
+    g = np.load(path)
+    ntype = str(g["nugget_type"])
+    nug = float(g["nugget_in"]) if ntype == "fixed" else ntype
+    ref = orc.OracleGP(g["X"], g["y"], kernel=str(g["kernel"]), nugget=nug, priors="weak").fit(g["theta"])
+    D = g["X"].shape[1]
+    theta = hyper.GPParams(D, ntype, float(g["nugget_in"]) if ntype == "fixed" else None)
+    theta.set_data(g["theta"])
+    theta.nugget = ref.nugget
+    pri = hyper.GPPriors.default_priors(g["X"], D, ntype)
+    assert_allclose(ref.current_logpost - pri.logp(theta), np.asarray(g["logpost"]).reshape(-1)[0], rtol=1e-10)
+    want = orc.priors_dlogpdtheta(orc.default_priors(g["X"], ntype), g["theta"][:D], ref.nugget, theta.n_data)
+    assert_allclose(pri.dlogpdtheta(theta), want, rtol=1e-10, atol=1e-14)
+
+
+def test_gpparams_contract():
+    t = hyper.GPParams(3, "fit")
+    assert t.get_n_data() == 5 and t.get_n_mean() == 0 and not t.data_has_been_set()
+    assert_allclose(t.get_data(), np.zeros(5))
+    t.set_data([0.2, -0.4, 1.0, 0.5, -3.0])
+    assert t.data_has_been_set()
+    assert_allclose(t.corr, np.exp(-0.5 * np.array([0.2, -0.4, 1.0])))
+    assert_allclose(t.cov, np.exp(0.5))
+    assert_allclose(t.nugget, np.exp(-3.0))
+    t.unset_data()
+    assert not t.data_has_been_set() and t.nugget is None
+    assert_allclose(t.get_data(), np.zeros(5))
+    assert hyper.GPParams(2, "fixed", 1e-6).nugget == 1e-6
+    assert hyper.GPParams(2, "adaptive").get_n_data() == 3
+    with pytest.raises(AssertionError):
+        t.set_data([1.0, 2.0])
+
+
+def test_transforms_roundtrip_and_derivatives():
+    for tr, raw in ((hyper.CorrTransform, 0.7), (hyper.CovTransform, -1.3)):
+        s = float(tr.transform(raw))
+        assert_allclose(tr.inv_transform(s), raw)
+        h = 1e-6
+        fd = (float(tr.transform(raw + h)) - float(tr.transform(raw - h))) / (2 * h)
+        assert_allclose(tr.dscaled_draw(s), fd, rtol=1e-8)
+
+
+@pytest.mark.parametrize("cls,frozen", [
+    (hyper.InvGammaPrior, lambda a, b: __import__("scipy.stats").stats.invgamma(a, scale=b)),
+    (hyper.GammaPrior, lambda a, b: __import__("scipy.stats").stats.gamma(a, scale=b)),
+    (hyper.LogNormalPrior, lambda a, b: __import__("scipy.stats").stats.lognorm(a, scale=b)),
+])
+def test_prior_densities_match_scipy(cls, frozen):
+    p = cls(2.3, 0.7)
+    xs = np.array([0.05, 0.4, 1.7, 6.0])
+    assert_allclose([p.logp(x) for x in xs], frozen(2.3, 0.7).logpdf(xs), rtol=1e-12)
+    h = 1e-6
+    fd = [(p.logp(x + h) - p.logp(x - h)) / (2 * h) for x in xs]
+    assert_allclose([p.dlogpdx(x) for x in xs], fd, rtol=1e-6)
+    d = cls.default_prior(0.1, 3.0)
+    assert isinstance(d, cls)
+    assert_allclose([d._frozen().cdf(0.1), d._frozen().cdf(3.0)], [0.005, 0.995], atol=1e-8)
+
+
+def test_priors_sample_shapes_and_weak_defaults():
+    np.random.seed(3)
+    pri = hyper.GPPriors(n_corr=2, nugget_type="fit")
+    s = pri.sample()
+    assert s.shape == (4,) and np.all(np.abs(s) <= 2.5)
+    t = hyper.GPParams(2, "fit")
+    t.set_data(s)
+    assert pri.logp(t) == 0.0
+    assert_allclose(pri.dlogpdtheta(t), np.zeros(4))
+    with pytest.raises(TypeError):
+        hyper.make_priors(3.0, np.zeros((4, 2)), 2, "fixed")
+    assert isinstance(hyper.make_priors({"corr": [None, hyper.InvGammaPrior(2.0, 1.0)]}, np.zeros((4, 2)), 2, "fixed"),
+                      hyper.GPPriors)
+
+
+def test_interpret_nugget_and_kernel():
+    assert interpret_nugget("adaptive") == (libmogp.nugget_type.adaptive, 0.0)
+    assert interpret_nugget("fit") == (libmogp.nugget_type.fit, 0.0)
+    assert interpret_nugget(1) == (libmogp.nugget_type.fixed, 1.0)
+    assert interpret_nugget(1e-6) == (libmogp.nugget_type.fixed, 1e-6)
+    with pytest.raises(ValueError):
+        interpret_nugget("pivot")
+    with pytest.raises(ValueError):
+        interpret_nugget(-1.0)
+    with pytest.raises(TypeError):
+        interpret_nugget([1.0, 2.0])
+    assert interpret_kernel("Matern52")[0] == libmogp.kernel_type.Matern52
+    assert interpret_kernel(SquaredExponential())[0] == libmogp.kernel_type.SquaredExponential
+    assert isinstance(interpret_kernel(Matern52())[1], Matern52)
+    with pytest.raises(ValueError):
+        interpret_kernel("UniformSqExp")
+
+
+def test_predict_result_container():
+    pr = PredictResult(mean=np.arange(3.0), unc=np.ones(3), deriv=None)
+    mean, unc, deriv = pr
+    assert mean is pr.mean is pr["mean"] is pr[0]
+    assert unc is pr.unc is pr[1] and deriv is None and pr[2] is None
+    with pytest.raises(KeyError):
+        pr[3]
+    with pytest.raises(AttributeError):
+        pr.nope
+    assert len(pr) == 3 and "mean" in repr(pr)
+
+
+def test_shard_bounds_cover_outputs_exactly():
+    for E in (1, 3, 8, 32, 33, 256):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi, e_pad = sharding.shard_bounds(E, r, world)
+                assert 0 <= lo <= hi <= E and hi - lo <= e_pad == -(-E // world)
+                seen.extend(range(lo, hi))
+            assert seen == list(range(E))
+            rows = sharding.gathered_rows(E, world)
+            assert len(rows) == E and len(set(rows)) == E
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 2, 2)
+
+
+def test_pack_unpack_roundtrip():
+    rng = np.random.default_rng(0)
+    E, world, m = 5, 2, 7
+    mean, var = rng.random((E, m)), rng.random((E, m))
+    fitted = [True, False, True, True, True]
+    blocks = []
+    for r in range(world):
+        lo, hi, e_pad = sharding.shard_bounds(E, r, world)
+        blocks.append(sharding.pack_block(mean[lo:hi], var[lo:hi], fitted[lo:hi], e_pad))
+    gm, gv, st = sharding.unpack_gathered(np.stack(blocks), E, world, m)
+    assert list(st) == [0, 4, 0, 0, 0]
+    ok = np.array(fitted)
+    assert_allclose(gm[ok], mean[ok])
+    assert_allclose(gv[ok], var[ok])
+    assert np.all(np.isnan(gm[~ok])) and np.all(np.isnan(gv[~ok]))
