@@ -6,7 +6,7 @@ SRC=mogp_emulator_b200/csrc
 OUT=mogp_emulator_b200/libmogp_b200.so
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
      -Xptxas -v "$@" \
-     $SRC/api.cu $SRC/chol.cu $SRC/kmat.cu $SRC/solve.cu $SRC/predict.cu $SRC/peak.cu $SRC/pool.cu $SRC/nccl_dyn.cu \
+     $SRC/api.cu $SRC/chol.cu $SRC/kmat.cu $SRC/solve.cu $SRC/predict.cu $SRC/grad.cu $SRC/peak.cu $SRC/pool.cu $SRC/nccl_dyn.cu \
      -o $OUT -ldl 2> build.log || { cat build.log; exit 1; }
 grep -E "error|warning" build.log | grep -v "Wno" | head -20 || true
 echo "built $OUT"

@@ -116,11 +116,16 @@ class GaussianProcessGPU(object):
             self._logpost_data = None
 
     def _set_priors(self, newpriors=None):
-        self._priors = make_priors(newpriors, self._inputs, self.n_corr, self.nugget_type)
+        """Priors are host-side scalars that only enter logposterior / logpost_deriv; the default ones need a
+        root find per input dimension (Priors.py:698-760), so they are built on first use."""
+        self._priors_arg = newpriors
+        self._priors = None if newpriors is None else make_priors(newpriors, self._inputs, self.n_corr, self.nugget_type)
 
     # -- properties (GaussianProcessGPU.py:335-502) ---------------------------------------------------
     @property
     def priors(self):
+        if self._priors is None:
+            self._priors = make_priors(None, self._inputs, self.n_corr, self.nugget_type)
         return self._priors
 
     @property
@@ -201,7 +206,7 @@ class GaussianProcessGPU(object):
     def current_logpost(self):
         if not self._theta.data_has_been_set():
             return None
-        return self._logpost_data - self._priors.logp(self._theta)
+        return self._logpost_data - self.priors.logp(self._theta)
 
     def get_K_matrix(self):
         """sigma^2 * k(X, X) without the nugget (GaussianProcess.get_K_matrix, GaussianProcess.py:545-558)."""
@@ -247,7 +252,7 @@ class GaussianProcessGPU(object):
         if self._refit(theta):
             self.fit(theta)
         grad = self._handle.logpost_grad(0, self.n_params)
-        return grad - self._priors.dlogpdtheta(self._theta)
+        return grad - self.priors.dlogpdtheta(self._theta)
 
     def logpost_hessian(self, theta):
         raise GPUUnavailableError("The Hessian calculation is not currently implemented in the GPU version of MOGP.")

@@ -73,15 +73,10 @@ class MultiOutputGP_GPU(object):
         else:
             priorslist = list(priors)
             assert len(priorslist) == E, "Bad length for list provided for priors to MultiOutputGP"
-        shared_default = None
-        self._priors = []
-        for p in priorslist:
-            if p is None:
-                if shared_default is None:
-                    shared_default = make_priors(None, self._inputs, self.D, self.nugget_type)
-                self._priors.append(shared_default)
-            else:
-                self._priors.append(make_priors(p, self._inputs, self.D, self.nugget_type))
+        # priors only enter logposterior / logpost_deriv; default ones (a root find per input dimension,
+        # Priors.py:698-760) are built on first use and shared by all emulators that did not get their own
+        self._priors_args = priorslist
+        self._priors = None
 
     # -- properties (MultiOutputGP_GPU.py:146-180) ------------------------------------------------------
     @property
@@ -125,6 +120,17 @@ class MultiOutputGP_GPU(object):
 
     @property
     def priors(self):
+        if self._priors is None:
+            shared_default = None
+            built = []
+            for p in self._priors_args:
+                if p is None:
+                    if shared_default is None:
+                        shared_default = make_priors(None, self._inputs, self.D, self.nugget_type)
+                    built.append(shared_default)
+                else:
+                    built.append(make_priors(p, self._inputs, self.D, self.nugget_type))
+            self._priors = built
         return self._priors
 
     @property
@@ -192,12 +198,12 @@ class MultiOutputGP_GPU(object):
                     raise RuntimeError("Unable to fit the Gaussian process: matrix not positive definite")
         if not self._fit[index]:
             return None
-        return self._logpost_data[index] - self._priors[index].logp(self._thetas[index])
+        return self._logpost_data[index] - self.priors[index].logp(self._thetas[index])
 
     def logpost_deriv(self, index, theta):
         self.logposterior(index, theta)
         grad = self._handle.logpost_grad(index - self._lo, self.n_params[index])
-        return grad - self._priors[index].dlogpdtheta(self._thetas[index])
+        return grad - self.priors[index].dlogpdtheta(self._thetas[index])
 
     def get_indices_fit(self):
         return [i for i in range(self.n_emulators) if self._global_fit(i)]

@@ -100,6 +100,9 @@ struct mogp_handle {
     size_t XsT_cap = 0, W_cap = 0, part_cap = 0, res_cap = 0, h_res_cap = 0, h_XsT_cap = 0;
     // grad workspace
     double* G = nullptr;
+    size_t G_cap = 0;
+    double* h_grad = nullptr;
+    size_t h_grad_cap = 0;
     double timings[T_COUNT] = {0};
 };
 
@@ -175,7 +178,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info};
+                    h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -209,7 +212,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         set_error("mogp_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
         return MOGP_ERR_CUDA;
     }
-    if (chol_init() || solve_init() || kmat_init() || predict_init()) {
+    if (chol_init() || solve_init() || kmat_init() || predict_init() || grad_init()) {
         set_error("kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         return MOGP_ERR_CUDA;
     }
@@ -483,7 +486,7 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     return MOGP_ERR_CUDA;
                 }
                 if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
-                                 include_nugget, np, mc, h->res + m + m0, 2 * m, h->main)) {
+                                 include_nugget, np, mc, h->res + m + m0, 2 * m, 0, h->main)) {
                     set_error("predict_trsm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     return MOGP_ERR_CUDA;
                 }
@@ -572,9 +575,58 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
 }
 
 int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params) {
-    (void)h; (void)idx; (void)grad; (void)n_params;
-    set_error("mogp_logpost_grad: not built yet");
-    return MOGP_ERR_ARG;
+    if (!h || idx < 0 || idx >= h->E || !grad) return MOGP_ERR_ARG;
+    const int d = h->d;
+    const int want = d + 1 + (h->nug_type == MOGP_NUG_FIT ? 1 : 0);
+    if (n_params != want) {
+        set_error("mogp_logpost_grad: expected %d parameters, got %d", want, n_params);
+        return MOGP_ERR_ARG;
+    }
+    if (!h->fitted[idx]) {
+        set_error("mogp_logpost_grad: output %d has not been fit", idx);
+        return MOGP_ERR_NOT_FIT;
+    }
+    if (d > grad_max_dims()) {
+        set_error("mogp_logpost_grad: at most %d input dimensions are supported", grad_max_dims());
+        return MOGP_ERR_ARG;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t np = h->n_pad;
+    const int T = (int)(np / NB);
+    const size_t tiles = (size_t)T * (T + 1);
+    // workspace: Wt (np x np) | partial (tiles x (d+2)) | grad (d+2) | scratch variance (np)
+    const size_t off_part = (size_t)np * np, off_grad = off_part + tiles * (d + 2), off_var = off_grad + (d + 2);
+    int rc;
+    if ((rc = grow(&h->G, &h->G_cap, sizeof(double) * (off_var + np), h->device))) return rc;
+    if ((rc = grow(&h->h_grad, &h->h_grad_cap, sizeof(double) * (d + 2), -1))) return rc;
+    double* Wt = h->G;
+    CUtensorMap tmW, tmW128, tmW64;
+    TrsmPlan plan = predict_plan_square(np, h->n_sms);
+    if (make_kblocked_tmap(&tmW, Wt, np, np, plan.nw) || make_kblocked_tmap(&tmW128, Wt, np, np, 128) ||
+        make_kblocked_tmap(&tmW64, Wt, np, np, 64)) {
+        set_error("tensor map (grad workspace) failed");
+        return MOGP_ERR_CUDA;
+    }
+    API_CUDA(cudaEventRecord(h->ev_a, h->main));
+    const int outs[1] = {idx};
+    if (grad_set_identity(Wt, np, h->main) ||
+        predict_trsm(plan, outs, 1, h->maps.a128, h->maps.d128, tmW, Wt, np, h->hyper, d, 0, np, np, h->G + off_var, 0, 1,
+                     h->main) ||
+        grad_reduce_tiles(tmW128, tmW64, h->kernel, h->XT, h->n, np, d, h->alpha + (size_t)idx * np,
+                          h->hyper + (size_t)idx * (d + 2), h->nug_type == MOGP_NUG_FIT, h->G + off_part, h->G + off_grad,
+                          h->main)) {
+        set_error("gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MOGP_ERR_CUDA;
+    }
+    API_CUDA(cudaEventRecord(h->ev_b, h->main));
+    API_CUDA(cudaMemcpyAsync(h->h_grad, h->G + off_grad, sizeof(double) * (d + 2), cudaMemcpyDeviceToHost, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    h->timings[T_GRAD] += ms;
+    h->timings[T_NLAUNCH] += 4;
+    for (int i = 0; i < n_params; i++) grad[i] = h->h_grad[i];
+    return MOGP_OK;
 }
 
 int mogp_trim(void) {

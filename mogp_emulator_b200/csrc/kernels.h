@@ -49,6 +49,15 @@ struct TrsmPlan {
 TrsmPlan predict_plan(int64_t m, int n_outputs, int n_sms);
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
-                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, cudaStream_t st);
+                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, cudaStream_t st);
+TrsmPlan predict_plan_square(int64_t n_pad, int n_sms);
+
+// ---- grad.cu ----
+int grad_init();
+int grad_max_dims();
+int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st);
+int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int kernel, const double* XT, int64_t n,
+                      int64_t n_pad, int d, const double* alpha, const double* hyper, int fit_nugget, double* partial,
+                      double* grad, cudaStream_t st);
 
 }  // namespace mogp

@@ -44,6 +44,7 @@ struct PredParams {
     int hyper_stride;       // d + 2
     int d;
     int include_nugget;
+    int tri_rhs;            // right-hand side is the identity: panel c0 starts its walk at block row c0/128
     double* var;            // result rows: var of output o at var + o*var_stride
     int64_t var_stride;
 };
@@ -72,6 +73,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
     const int wrow = (int)(o_local * p.w_stride) + c0;          // row of the panel inside the W slab
     const int lrow = (int)(o * p.n_pad);                        // first row of this output's L / Dinv
     const int T = p.T;
+    const int i0 = p.tri_rhs ? (c0 / NB) : 0;   // V rows above block row i0 are exactly zero
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) {
@@ -94,15 +96,16 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
             prefetch_tmap(&tmD);
             prefetch_tmap(&tmW);
             PipeState<NS> ps;
-            for (int i = 0; i < T; i++) {
+            for (int i = i0; i < T; i++) {
+                const int step = i - i0;
                 // right-hand side tile K*_i -> VS (needs the previous step's diagonal product done with VS)
-                if (i > 0) mbar_wait(vs_free, (uint32_t)((i - 1) & 1));
+                if (step > 0) mbar_wait(vs_free, (uint32_t)((step - 1) & 1));
                 mbar_arrive_expect_tx(ks_full, Cfg::VS_BYTES);
                 for (int ch = 0; ch < NCH; ch++)
                     tma_load_3d(VS + ch * (KC / 8) * BN * 8, &tmW, 0, wrow, i * (NB / 8) + ch * (KC / 8), ks_full);
                 // sum_{j<i} L_ij V_j
-                for (int j = 0; j < i; j++) {
-                    if (j == i - 1) mbar_wait(step_done, (uint32_t)((i - 1) & 1));  // V_{i-1} is in HBM/L2
+                for (int j = i0; j < i; j++) {
+                    if (j == i - 1) mbar_wait(step_done, (uint32_t)((step - 1) & 1));  // V_{i-1} is in HBM/L2
                     for (int ch = 0; ch < NCH; ch++) {
                         mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
                         unsigned char* st = base + ps.stage * Cfg::STAGE_BYTES;
@@ -136,7 +139,8 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
     for (int nt = 0; nt < NT; nt++) colsum[nt][0] = colsum[nt][1] = 0.0;
 
     PipeState<NS> ps;
-    for (int i = 0; i < T; i++) {
+    for (int i = i0; i < T; i++) {
+        const int step = i - i0;
         double acc[2][NT][4];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
@@ -145,7 +149,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
 #pragma unroll
                 for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.0;
 
-        for (int c = 0; c < i * NCH; c++) {
+        for (int c = 0; c < step * NCH; c++) {
             mbar_wait(&full[ps.stage], ps.phase);
             const double* As = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES);
             const double* Bs = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES + Cfg::A_BYTES);
@@ -156,7 +160,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
         }
 
         // rhs = K*_i - acc, in place in VS (element (k = L row r, n = test point c) at VS[r/8][c][r%8])
-        mbar_wait(ks_full, (uint32_t)(i & 1));
+        mbar_wait(ks_full, (uint32_t)(step & 1));
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
 #pragma unroll
@@ -193,7 +197,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
                     const double v = acc[mt][nt][e];
                     colsum[nt][e & 1] = fma(v, v, colsum[nt][e & 1]);
                 }
-        if (i + 1 < T) {
+        if (i + 1 < T || p.tri_rhs) {   // the last block row is only needed when V itself is the result
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
@@ -207,10 +211,12 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
                     }
                 }
             // generic-proxy global writes -> L2 -> visible to the TMA (async proxy) loads of the next steps
-            __threadfence();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(step_done);
+            if (i + 1 < T) {
+                __threadfence();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(step_done);
+            }
         }
     }
 
@@ -274,15 +280,35 @@ TrsmPlan predict_plan(int64_t m, int n_outputs, int n_sms) {
     return best;
 }
 
+// identity right-hand side (n_pad columns): widths that divide 128 so a panel never straddles a block row
+TrsmPlan predict_plan_square(int64_t n_pad, int n_sms) {
+    TrsmPlan best{128, (int)(n_pad / 128)};
+    double best_cost = 1e300;
+    const int widths[3] = {32, 64, 128};
+    for (int bn : widths) {
+        const int64_t panels = n_pad / bn;
+        const int64_t waves = (panels + n_sms - 1) / n_sms;
+        const double cost = (double)waves * bn;
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best.nw = bn;
+            best.panels = (int)panels;
+        }
+    }
+    return best;
+}
+
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
-                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, cudaStream_t st) {
+                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, cudaStream_t st) {
     PredParams p{};
     p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m; p.T = (int)(n_pad / NB);
     for (int i = 0; i < count; i++) p.outs[i] = outs[i];
     p.hyper = hyper; p.hyper_stride = d + 2; p.d = d; p.include_nugget = include_nugget; p.var = var;
     p.var_stride = var_stride;
+    p.tri_rhs = tri_rhs;
     switch (plan.nw / 16) {
+        case 2: return launch_pred<2>(plan, count, tmL, tmD, tmW, p, st);
         case 4: return launch_pred<4>(plan, count, tmL, tmD, tmW, p, st);
         case 5: return launch_pred<5>(plan, count, tmL, tmD, tmW, p, st);
         case 6: return launch_pred<6>(plan, count, tmL, tmD, tmW, p, st);

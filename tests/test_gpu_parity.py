@@ -176,3 +176,64 @@ def test_multi_output_not_fit_semantics(mogp):
     assert gp.get_indices_fit() == []
     with pytest.raises(RuntimeError):
         gp.fit(np.zeros((4, 7)))
+
+
+@pytest.mark.parametrize("name", [s for s in SINGLE if "n1_" not in s and "n2_" not in s])
+def test_logpost_deriv_matches_reference_golden(mogp, name):
+    g = _load(name)
+    gp = mogp.GaussianProcessGPU(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
+    got = gp.logpost_deriv(g["theta"])
+    want = np.asarray(g["deriv"]).reshape(-1)
+    assert got.shape == want.shape == (gp.n_params,)
+    cond = np.linalg.cond(g["K"] + float(g["nugget_out"]) * np.eye(g["K"].shape[0]))
+    tol = max(1e-6, 20.0 * cond * np.finfo(np.float64).eps)
+    assert_allclose(got, want, rtol=tol, atol=tol * np.abs(want).max())
+
+
+@pytest.mark.parametrize("kernel,nugget,n,d", [("SquaredExponential", 1e-4, 300, 3), ("Matern52", "fit", 260, 12)])
+def test_logpost_deriv_against_oracle_and_finite_differences(mogp, kernel, nugget, n, d):
+    X, Y, _ = orc.make_workload(n, d, 1, 5, seed=77)
+    n_params = d + 1 + (1 if nugget == "fit" else 0)
+    theta = np.linspace(-0.4, 0.6, n_params)
+    if nugget == "fit":
+        theta[-1] = -6.0
+    ref = orc.OracleGP(X, Y[0], kernel=kernel, nugget=nugget)
+    gp = mogp.GaussianProcessGPU(X, Y[0], kernel=kernel, nugget=nugget)
+    want = ref.logpost_deriv(theta)
+    got = gp.logpost_deriv(theta)
+    assert_allclose(got, want, rtol=1e-6, atol=1e-6 * np.abs(want).max())
+    # central finite differences of the GPU log-posterior itself
+    h = 1e-5
+    for i in (0, d, n_params - 1):
+        e = np.zeros(n_params)
+        e[i] = h
+        fd = (gp.logposterior(theta + e) - gp.logposterior(theta - e)) / (2 * h)
+        assert_allclose(got[i], fd, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+
+
+def test_fit_GP_MAP_matches_cpu_optimiser(mogp):
+    """Same optimiser (L-BFGS-B from the same start) over the GPU objective and over the oracle's: the two
+    searches must land on the same optimum (reference flow: fitting.py:219-266)."""
+    from scipy.optimize import minimize
+    X, Y, Xs = orc.make_workload(120, 2, 1, 30, seed=4)
+    theta0 = np.zeros(3)
+    ref = orc.OracleGP(X, Y[0], nugget=1e-5)
+    res = minimize(ref.logposterior, theta0, method="L-BFGS-B", jac=ref.logpost_deriv)
+    gp = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-5)
+    gp = mogp.fit_GP_MAP(gp, n_tries=1, theta0=theta0)
+    assert gp.theta.data_has_been_set()
+    assert_allclose(gp.current_logpost, res["fun"], rtol=1e-6)
+    assert_allclose(gp.theta.get_data(), res["x"], rtol=1e-3, atol=1e-3)
+    ref.fit(gp.theta.get_data())
+    rmean, rvar = ref.predict(Xs)
+    mean, var, _ = gp.predict(Xs)
+    assert_allclose(mean, rmean, rtol=1e-6, atol=1e-8)
+    assert_allclose(var, rvar, rtol=1e-4, atol=1e-9)
+    # multi-output entry point, two outputs, one restart each from a given start
+    X, Y, Xs = orc.make_workload(80, 2, 2, 10, seed=6)
+    mo = mogp.fit_GP_MAP(X, Y, nugget=1e-5, n_tries=1, theta0=np.zeros(3))
+    assert mo.get_indices_not_fit() == []
+    for i in range(2):
+        r = orc.OracleGP(X, Y[i], nugget=1e-5)
+        rr = minimize(r.logposterior, np.zeros(3), method="L-BFGS-B", jac=r.logpost_deriv)
+        assert_allclose(mo.logposterior(i), rr["fun"], rtol=1e-6)
