@@ -3,10 +3,14 @@
 // for y^T alpha (:604-611); CPU semantics: ChoInv.solve = cho_solve((L, True), y), linalg/cholesky.py:22-42,
 // used at GaussianProcess.py:666-672.
 //
-// Blocked substitution over 128-row blocks: the off-diagonal part is a streaming GEMV over L (row-major,
-// 16-byte vector loads), the diagonal block is applied through its precomputed inverse (Dinv, produced by
-// the Cholesky panel kernel), so there is no scalar dependency chain.  One CTA per right-hand side:
-// independent outputs run concurrently on their own streams.
+// Blocked substitution over 128-row blocks, one thread-block CLUSTER per right-hand side.  The off-diagonal
+// part of every step is a streaming GEMV over a block row (forward) / block column (backward) of L whose
+// 128-wide column (row) blocks are dealt round-robin to the CTAs of the cluster, so the cluster pulls L through
+// C SMs' worth of L2->SM bandwidth instead of one.  Each CTA keeps only its own blocks of the solution vector
+// in shared memory (those are the only ones its share of the GEMV touches).  Per step the C partial sums land
+// in the owner CTA's shared memory through DSMEM (st.shared::cluster), one barrier.cluster publishes them, and
+// the owner applies the precomputed inverse of the diagonal block (Dinv, from the Cholesky panel kernel) -- no
+// scalar dependency chain.  Partials are summed in rank order: results are deterministic.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,50 +22,91 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(512, 1)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the shared memory of CTA `rank` of this cluster at the address `local` has in this CTA
+__device__ __forceinline__ void dsmem_store(double* local, uint32_t rank, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+constexpr int SOLVE_THREADS = 512;
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_alpha_kernel(const double* __restrict__ A, int64_t ld, int T, const double* __restrict__ Dinv,
                    const double* __restrict__ y, double* __restrict__ z_out, double* __restrict__ alpha_out,
                    double* __restrict__ quad, const int* __restrict__ info) {
-    extern __shared__ __align__(16) double sv[];  // v[n_pad] | acc[128] | red[4*128]
+    extern __shared__ __align__(16) double sv[];
+    // every CTA of the cluster takes the same branch: no barrier is left dangling
     if (*info != 0) return;
-    const int n_pad = T * NB;
-    double* v = sv;
-    double* acc = sv + n_pad;
-    double* red = acc + NB;
+    const int C = (int)cluster_nctarank(), me = (int)cluster_ctarank();
+    const int nown = (T + C - 1) / C;        // blocks of the vector kept by one CTA (block j lives in CTA j % C, slot j / C)
+    double* v = sv;                          // [nown][128]
+    double* slots = v + (size_t)nown * NB;   // [C][128] partial sums received from the cluster
+    double* acc = slots + (size_t)C * NB;    // [128]
+    double* red = acc + NB;                  // [4][128]
+    double* qs = red + 4 * NB;               // [C] per-CTA sums of z^2 (CTA 0's copy is the one used)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < n_pad; i += 512) v[i] = y[i];
+    for (int s = 0; s < nown; s++) {
+        const int j = s * C + me;
+        for (int r = tid; r < NB; r += SOLVE_THREADS) v[s * NB + r] = (j < T) ? y[(int64_t)j * NB + r] : 0.0;
+    }
     __syncthreads();
+    cluster_sync_all();   // all CTAs are running before the first remote store
 
-    // ---- forward substitution ----
+    // ---- forward substitution:  z_i = Dinv_i (y_i - sum_{j<i} L_ij z_j) ----
     for (int i = 0; i < T; i++) {
-        const int c_end = i * NB;
+        const int owner = i % C;
         {
             double s[8];
 #pragma unroll
             for (int rr = 0; rr < 8; rr++) s[rr] = 0.0;
             const double* rowp = A + (int64_t)(i * NB + warp * 8) * ld;
-            for (int c = lane * 2; c < c_end; c += 64) {
-                const double2 vv = *reinterpret_cast<const double2*>(v + c);
+            for (int j = me, sl = 0; j < i; j += C, sl++) {
 #pragma unroll
-                for (int rr = 0; rr < 8; rr++) {
-                    const double2 l = *reinterpret_cast<const double2*>(rowp + (int64_t)rr * ld + c);
-                    s[rr] = fma(l.x, vv.x, s[rr]);
-                    s[rr] = fma(l.y, vv.y, s[rr]);
+                for (int half = 0; half < 2; half++) {
+                    const int cl = half * 64 + lane * 2;
+                    const double2 vv = *reinterpret_cast<const double2*>(v + sl * NB + cl);
+                    const double* p = rowp + (int64_t)j * NB + cl;
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) {
+                        const double2 l = *reinterpret_cast<const double2*>(p + (int64_t)rr * ld);
+                        s[rr] = fma(l.x, vv.x, s[rr]);
+                        s[rr] = fma(l.y, vv.y, s[rr]);
+                    }
                 }
             }
 #pragma unroll
             for (int rr = 0; rr < 8; rr++) {
                 const double t = warp_sum(s[rr]);
-                if (lane == 0) acc[warp * 8 + rr] = v[c_end + warp * 8 + rr] - t;
+                if (lane == 0) dsmem_store(slots + me * NB + warp * 8 + rr, (uint32_t)owner, t);
             }
         }
-        __syncthreads();
-        {
+        cluster_sync_all();
+        if (me == owner) {   // CTA-uniform
+            const int sl = i / C;
+            if (tid < NB) {
+                double t = 0.0;
+                for (int c = 0; c < C; c++) t += slots[c * NB + tid];
+                acc[tid] = v[sl * NB + tid] - t;
+            }
+            __syncthreads();
             const double* Db = Dinv + (int64_t)i * NB * NB;
             const double2 a0 = *reinterpret_cast<const double2*>(acc + lane * 4);
             const double2 a1 = *reinterpret_cast<const double2*>(acc + lane * 4 + 2);
-            double res[8];
 #pragma unroll
             for (int rr = 0; rr < 8; rr++) {
                 const double* dr = Db + (int64_t)(warp * 8 + rr) * NB + lane * 4;
@@ -71,81 +116,140 @@ solve_alpha_kernel(const double* __restrict__ A, int64_t ld, int T, const double
                 t = fma(d0.y, a0.y, t);
                 t = fma(d1.x, a1.x, t);
                 t = fma(d1.y, a1.y, t);
-                res[rr] = warp_sum(t);
+                t = warp_sum(t);
+                if (lane == 0) {
+                    v[sl * NB + warp * 8 + rr] = t;
+                    z_out[(int64_t)i * NB + warp * 8 + rr] = t;
+                }
             }
-            __syncthreads();  // all reads of acc done before v (and later acc) change
-            if (lane == 0) {
-#pragma unroll
-                for (int rr = 0; rr < 8; rr++) v[c_end + warp * 8 + rr] = res[rr];
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
+
+    // ---- quad = z^T z: per-CTA sums over own blocks, combined in rank order by CTA 0 ----
     {
         double q = 0.0;
-        for (int i = tid; i < n_pad; i += 512) {
-            q = fma(v[i], v[i], q);
-            z_out[i] = v[i];
-        }
+        for (int idx = tid; idx < nown * NB; idx += SOLVE_THREADS) q = fma(v[idx], v[idx], q);   // slots past T hold zeros
         q = warp_sum(q);
         if (lane == 0) red[warp] = q;
         __syncthreads();
         if (tid == 0) {
             double t = 0.0;
-            for (int w = 0; w < 16; w++) t += red[w];
+            for (int w = 0; w < SOLVE_THREADS / 32; w++) t += red[w];
+            dsmem_store(qs + me, 0u, t);
+        }
+        cluster_sync_all();
+        if (me == 0 && tid == 0) {
+            double t = 0.0;
+            for (int c = 0; c < C; c++) t += qs[c];
             *quad = t;
         }
-        __syncthreads();
     }
 
-    // ---- backward substitution ----
+    // ---- backward substitution:  alpha_i = Dinv_i^T (z_i - sum_{j>i} L_ji^T alpha_j) ----
     const int c = tid & 127, q4 = tid >> 7;
     for (int i = T - 1; i >= 0; i--) {
+        const int owner = i % C;
         {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             const double* colp = A + (int64_t)i * NB + c;
-            int r = (i + 1) * NB + q4;
-            for (; r + 12 < n_pad; r += 16) {
-                s0 = fma(colp[(int64_t)r * ld], v[r], s0);
-                s1 = fma(colp[(int64_t)(r + 4) * ld], v[r + 4], s1);
-                s2 = fma(colp[(int64_t)(r + 8) * ld], v[r + 8], s2);
-                s3 = fma(colp[(int64_t)(r + 12) * ld], v[r + 12], s3);
+            // own row blocks j > i, j = me (mod C)
+            int j = i + 1 + ((me - (i + 1)) % C + C) % C;
+            for (; j < T; j += C) {
+                const double* vb = v + (j / C) * NB;
+                const double* lp = colp + (int64_t)j * NB * ld;
+#pragma unroll
+                for (int r = q4; r < NB; r += 16) {
+                    s0 = fma(lp[(int64_t)r * ld], vb[r], s0);
+                    s1 = fma(lp[(int64_t)(r + 4) * ld], vb[r + 4], s1);
+                    s2 = fma(lp[(int64_t)(r + 8) * ld], vb[r + 8], s2);
+                    s3 = fma(lp[(int64_t)(r + 12) * ld], vb[r + 12], s3);
+                }
             }
-            for (; r < n_pad; r += 4) s0 = fma(colp[(int64_t)r * ld], v[r], s0);
             red[q4 * NB + c] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
-        if (tid < NB) acc[tid] = v[i * NB + tid] - ((red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]));
-        __syncthreads();
-        {
-            const double* Db = Dinv + (int64_t)i * NB * NB;
-            double s = 0.0;
-            for (int r = q4; r < NB; r += 4)
-                if (r >= c) s = fma(Db[r * NB + c], acc[r], s);
-            red[q4 * NB + c] = s;
+        if (tid < NB)
+            dsmem_store(slots + me * NB + tid, (uint32_t)owner,
+                        (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]));
+        cluster_sync_all();
+        if (me == owner) {
+            const int sl = i / C;
+            if (tid < NB) {
+                double t = 0.0;
+                for (int cc = 0; cc < C; cc++) t += slots[cc * NB + tid];
+                acc[tid] = v[sl * NB + tid] - t;
+            }
+            __syncthreads();
+            {
+                const double* Db = Dinv + (int64_t)i * NB * NB;
+                double s = 0.0;
+                for (int r = q4; r < NB; r += 4)
+                    if (r >= c) s = fma(Db[r * NB + c], acc[r], s);
+                red[q4 * NB + c] = s;
+            }
+            __syncthreads();
+            if (tid < NB) {
+                const double a = (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]);
+                v[sl * NB + tid] = a;
+                alpha_out[(int64_t)i * NB + tid] = a;
+            }
         }
-        __syncthreads();
-        if (tid < NB) v[i * NB + tid] = (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]);
-        __syncthreads();
+        __syncthreads();   // red is rewritten by the next step
     }
-    for (int i = tid; i < n_pad; i += 512) alpha_out[i] = v[i];
 }
+
+static int g_max_cluster = 0;
 
 int solve_init() {
     static bool done = false;
     if (done) return 0;
     if (cudaFuncSetAttribute(solve_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return 1;
+    // clusters of 16 CTAs need the non-portable opt-in; fall back to the portable 8
+    g_max_cluster = 8;
+    if (cudaFuncSetAttribute(solve_alpha_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16);
+        cfg.blockDim = dim3(SOLVE_THREADS);
+        cfg.dynamicSmemBytes = 64 * 1024;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 16;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, solve_alpha_kernel, &cfg) == cudaSuccess && ncl >= 1) g_max_cluster = 16;
+    }
+    cudaGetLastError();
     done = true;
     return 0;
 }
 
 int solve_alpha(const double* A, int64_t n_pad, const double* Dinv, const double* y, double* z, double* alpha,
                 double* quad, const int* info, cudaStream_t st) {
-    const size_t smem = (size_t)(n_pad + NB + 4 * NB) * sizeof(double);
-    if (smem > 200 * 1024) return 2;  // n_pad > ~24k: needs the multi-CTA solver
-    solve_alpha_kernel<<<1, 512, smem, st>>>(A, n_pad, (int)(n_pad / NB), Dinv, y, z, alpha, quad, info);
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    const int T = (int)(n_pad / NB);
+    int C = 1;
+    while (C * 2 <= g_max_cluster && C * 4 <= T) C *= 2;   // at least two blocks of the vector per CTA
+    const int nown = (T + C - 1) / C;
+    const size_t smem = (size_t)(nown * NB + C * NB + NB + 4 * NB + 16) * sizeof(double);
+    if (smem > 200 * 1024) return 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C);
+    cfg.blockDim = dim3(SOLVE_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_alpha_kernel, A, n_pad, T, Dinv, y, z, alpha, quad, info);
+    return e == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace mogp
