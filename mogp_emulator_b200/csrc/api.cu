@@ -97,7 +97,8 @@ struct mogp_handle {
     std::vector<char> fitted;
     // predict workspace (grown on demand)
     double *XsT = nullptr, *W = nullptr, *part = nullptr, *res = nullptr, *h_res = nullptr, *h_XsT = nullptr;
-    size_t XsT_cap = 0, W_cap = 0, part_cap = 0, res_cap = 0, h_res_cap = 0, h_XsT_cap = 0;
+    double *sync = nullptr, *normacc = nullptr;   // TRSM ticket/flag words (used as int) and running column norms
+    size_t XsT_cap = 0, W_cap = 0, part_cap = 0, res_cap = 0, h_res_cap = 0, h_XsT_cap = 0, sync_cap = 0, normacc_cap = 0;
     // grad workspace
     double* G = nullptr;
     size_t G_cap = 0;
@@ -178,7 +179,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
+                    h->sync, h->normacc, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -452,7 +453,7 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
         for (size_t g0 = 0; g0 < fit_idx.size(); g0 += G) {
             const int cnt = (int)std::min<size_t>(G, fit_idx.size() - g0);
             const int* outs = fit_idx.data() + g0;
-            TrsmPlan plan = predict_plan(mc, cnt, h->n_sms);
+            TrsmPlan plan = predict_plan(mc, cnt, (int)np, h->n_sms);
             // panels * nw < mc + 128, so this stride covers every panel of every plan (and is what the
             // budget above assumed); the kernel-matrix kernel fills all w_stride rows (zero-padded test points)
             const int64_t w_stride = round_up(mc, 128) + 128;
@@ -485,8 +486,11 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     set_error("tensor map (W) failed");
                     return MOGP_ERR_CUDA;
                 }
+                if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, cnt, n_tiles), h->device))) return rc;
+                if ((rc = grow(&h->normacc, &h->normacc_cap, sizeof(double) * (size_t)cnt * w_stride, h->device))) return rc;
                 if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
-                                 include_nugget, np, mc, h->res + m + m0, 2 * m, 0, h->main)) {
+                                 include_nugget, np, mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms,
+                                 h->main)) {
                     set_error("predict_trsm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     return MOGP_ERR_CUDA;
                 }
@@ -609,9 +613,10 @@ int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_param
     }
     API_CUDA(cudaEventRecord(h->ev_a, h->main));
     const int outs[1] = {idx};
+    if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, 1, T), h->device))) return rc;
     if (grad_set_identity(Wt, np, h->main) ||
         predict_trsm(plan, outs, 1, h->maps.a128, h->maps.d128, tmW, Wt, np, h->hyper, d, 0, np, np, h->G + off_var, 0, 1,
-                     h->main) ||
+                     (int*)h->sync, nullptr, h->n_sms, h->main) ||
         grad_reduce_tiles(tmW128, tmW64, h->kernel, h->XT, h->n, np, d, h->alpha + (size_t)idx * np,
                           h->hyper + (size_t)idx * (d + 2), h->nug_type == MOGP_NUG_FIT, h->G + off_part, h->G + off_grad,
                           h->main)) {

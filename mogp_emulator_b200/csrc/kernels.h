@@ -43,14 +43,17 @@ int solve_alpha(const double* A, int64_t n_pad, const double* Dinv, const double
 // ---- predict.cu ----
 int predict_init();
 struct TrsmPlan {
-    int nw;      // test points per CTA (multiple of 16, 64..128)
-    int panels;  // CTAs per output
+    int nw;      // test points per tile (32 or 64)
+    int panels;  // panels per output
 };
-TrsmPlan predict_plan(int64_t m, int n_outputs, int n_sms);
+TrsmPlan predict_plan(int64_t m, int n_outputs, int n_pad, int n_sms);
+TrsmPlan predict_plan_square(int64_t n_pad, int n_sms);
+// bytes of the ticket/flag workspace one launch needs (zeroed by predict_trsm itself)
+size_t predict_sync_bytes(const TrsmPlan& plan, int count, int T);
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
-                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, cudaStream_t st);
-TrsmPlan predict_plan_square(int64_t n_pad, int n_sms);
+                 int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, int* sync, double* normacc,
+                 int n_sms, cudaStream_t st);
 
 // ---- grad.cu ----
 int grad_init();
