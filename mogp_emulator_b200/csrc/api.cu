@@ -98,6 +98,8 @@ struct mogp_handle {
     // predict workspace (grown on demand)
     double *XsT = nullptr, *W = nullptr, *part = nullptr, *res = nullptr, *h_res = nullptr, *h_XsT = nullptr;
     double *sync = nullptr, *normacc = nullptr;   // TRSM ticket/flag words (used as int) and running column norms
+    double* csync = nullptr;                       // Cholesky ticket/progress words (used as int)
+    size_t csync_cap = 0;
     size_t XsT_cap = 0, W_cap = 0, part_cap = 0, res_cap = 0, h_res_cap = 0, h_XsT_cap = 0, sync_cap = 0, normacc_cap = 0;
     // grad workspace
     double* G = nullptr;
@@ -179,7 +181,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->sync, h->normacc, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
+                    h->sync, h->normacc, h->csync, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -312,29 +314,55 @@ int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out) {
     return MOGP_OK;
 }
 
-// enqueue kernel matrix + factorisation + solves for output o with the given nugget on stream st
-static int enqueue_attempt(mogp_handle* h, int o, double nugget, cudaStream_t st) {
+// enqueue kernel matrix + factorisation + solves for the outputs outs[0..count) on h->main (batched launches), with
+// the nugget currently stored in h->hyper[o][d+1]; info / (logdet, quad) land in the pinned mirrors.
+static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
     const int64_t np = h->n_pad;
-    API_CUDA(cudaMemsetAsync(h->info + o, 0, sizeof(int), st));
-    API_CUDA(cudaMemsetAsync(h->scal + 2 * o, 0, 2 * sizeof(double), st));
-    if (kmat_sym(h->tmXT, h->kernel, h->n, np, h->d, h->hyper, o, nugget, h->A, (int64_t)o * np, st)) {
-        set_error("kmat launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return MOGP_ERR_CUDA;
+    const int T = (int)(np / NB);
+    for (int g0 = 0; g0 < count; g0 += MAXG) {
+        const int cnt = std::min(MAXG, count - g0);
+        const int* og = outs + g0;
+        for (int i = 0; i < cnt; i++) {
+            API_CUDA(cudaMemsetAsync(h->info + og[i], 0, sizeof(int), h->main));
+            API_CUDA(cudaMemsetAsync(h->scal + 2 * og[i], 0, 2 * sizeof(double), h->main));
+        }
+        API_CUDA(cudaEventRecord(h->ev_a, h->main));
+        if (kmat_sym(h->tmXT, h->kernel, h->n, np, h->d, h->hyper, og, cnt, 1, h->A, np, h->main)) {
+            set_error("kmat launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MOGP_ERR_CUDA;
+        }
+        API_CUDA(cudaEventRecord(h->ev_b, h->main));
+        int rc;
+        if ((rc = grow(&h->csync, &h->csync_cap, chol_sync_bytes(cnt, T), h->device))) return rc;
+        int nl = chol_factor_batch(h->maps, h->A, h->Dinv, og, cnt, np, h->info, h->scal, (int*)h->csync, h->n_sms, h->main);
+        if (nl < 0) {
+            set_error("cholesky launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MOGP_ERR_CUDA;
+        }
+        API_CUDA(cudaEventRecord(h->ev_c, h->main));
+        int rs = solve_alpha(h->A, np, h->Dinv, h->Y, h->z, h->alpha, h->scal, h->info, og, cnt, h->main);
+        if (rs) {
+            set_error(rs == 2 ? "n too large for the cluster solver" : "solve launch failed");
+            return rs == 2 ? MOGP_ERR_ARG : MOGP_ERR_CUDA;
+        }
+        API_CUDA(cudaEventRecord(h->ev_d, h->main));
+        h->timings[T_NLAUNCH] += nl + 2;
+        for (int i = 0; i < cnt; i++) {
+            API_CUDA(cudaMemcpyAsync(h->h_info + og[i], h->info + og[i], sizeof(int), cudaMemcpyDeviceToHost, h->main));
+            API_CUDA(cudaMemcpyAsync(h->h_scal + 2 * og[i], h->scal + 2 * og[i], 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                                     h->main));
+        }
+        API_CUDA(cudaStreamSynchronize(h->main));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+        h->timings[T_KMAT] += ms;
+        cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+        h->timings[T_CHOL] += ms;
+        cudaEventElapsedTime(&ms, h->ev_c, h->ev_d);
+        h->timings[T_SOLVE] += ms;
+        cudaEventElapsedTime(&ms, h->ev_a, h->ev_d);
+        h->timings[T_FIT] += ms;
     }
-    int nl = chol_factor(h->maps, h->A, h->Dinv, o, np, h->info + o, h->scal + 2 * o, st);
-    if (nl < 0) {
-        set_error("cholesky launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return MOGP_ERR_CUDA;
-    }
-    h->timings[T_NLAUNCH] += nl + 2;
-    int rs = solve_alpha(h->A + (size_t)o * np * np, np, h->Dinv + (size_t)o * np * NB, h->Y + (size_t)o * np,
-                         h->z + (size_t)o * np, h->alpha + (size_t)o * np, h->scal + 2 * o + 1, h->info + o, st);
-    if (rs) {
-        set_error(rs == 2 ? "n too large for the single-CTA solver" : "solve launch failed");
-        return rs == 2 ? MOGP_ERR_ARG : MOGP_ERR_CUDA;
-    }
-    API_CUDA(cudaMemcpyAsync(h->h_info + o, h->info + o, sizeof(int), cudaMemcpyDeviceToHost, st));
-    API_CUDA(cudaMemcpyAsync(h->h_scal + 2 * o, h->scal + 2 * o, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     return MOGP_OK;
 }
 
@@ -353,6 +381,7 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
     API_CUDA(cudaSetDevice(h->device));
     const int hs = d + 2;
     std::vector<double> nug(count, 0.0);
+    std::vector<int> todo(count);
     for (int i = 0; i < count; i++) {
         const int o = first + i;
         const double* th = thetas + (size_t)i * n_params;
@@ -364,60 +393,54 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
         else nug[i] = 0.0;
         hy[d + 1] = nug[i];
         h->fitted[o] = 0;
+        todo[i] = o;
     }
-    API_CUDA(cudaEventRecord(h->ev_a, h->main));
     API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
                              cudaMemcpyHostToDevice, h->main));
-    API_CUDA(cudaEventRecord(h->ev_fork, h->main));
-    const int S = (int)h->streams.size();
-    for (int s = 0; s < S && s < count; s++) API_CUDA(cudaStreamWaitEvent(h->streams[s], h->ev_fork, 0));
-    for (int i = 0; i < count; i++) {
-        int rc = enqueue_attempt(h, first + i, nug[i], h->streams[i % S]);
-        if (rc) return rc;
-    }
-    for (int s = 0; s < S && s < count; s++) {
-        API_CUDA(cudaEventRecord(h->ev_join[s], h->streams[s]));
-        API_CUDA(cudaStreamWaitEvent(h->main, h->ev_join[s], 0));
-    }
-    API_CUDA(cudaEventRecord(h->ev_b, h->main));
-    API_CUDA(cudaStreamSynchronize(h->main));
-    {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
-        h->timings[T_FIT] += ms;
-    }
+    int rc = enqueue_attempt(h, todo.data(), count);
+    if (rc) return rc;
     // adaptive jitter retries (linalg/cholesky.py:264-279): jitter = mean(diag K) * 1e-6, x10 per failure, 5 tries.
     // diag of a stationary kernel matrix is sigma2 for every entry, so mean(diag K) == sigma2.
-    for (int i = 0; i < count; i++) {
-        const int o = first + i;
-        int status = MOGP_OK;
-        if (h->h_info[o] != 0) {
-            status = MOGP_ERR_NOT_PD;
-            if (h->nug_type == MOGP_NUG_ADAPTIVE) {
-                double jitter = h->h_hyper[(size_t)o * hs + d] * 1e-6;
-                for (int t = 0; t < 5 && std::isfinite(jitter); t++) {
-                    int rc = enqueue_attempt(h, o, jitter, h->streams[0]);
-                    if (rc) return rc;
-                    API_CUDA(cudaStreamSynchronize(h->streams[0]));
-                    if (h->h_info[o] == 0) {
-                        status = MOGP_OK;
-                        nug[i] = jitter;
-                        break;
-                    }
-                    jitter *= 10.0;
-                }
+    std::vector<int> status(count, MOGP_OK);
+    std::vector<int> failed;
+    for (int i = 0; i < count; i++)
+        if (h->h_info[first + i] != 0) {
+            status[i] = MOGP_ERR_NOT_PD;
+            if (h->nug_type == MOGP_NUG_ADAPTIVE) failed.push_back(first + i);
+        }
+    double scale = 1e-6;
+    for (int t = 0; t < 5 && !failed.empty(); t++, scale *= 10.0) {
+        std::vector<int> run;
+        for (int o : failed) {
+            const double jitter = h->h_hyper[(size_t)o * hs + d] * scale;
+            if (!std::isfinite(jitter)) continue;
+            h->h_hyper[(size_t)o * hs + d + 1] = jitter;
+            run.push_back(o);
+        }
+        if (run.empty()) break;
+        API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
+                                 cudaMemcpyHostToDevice, h->main));
+        rc = enqueue_attempt(h, run.data(), (int)run.size());
+        if (rc) return rc;
+        failed.clear();
+        for (int o : run) {
+            if (h->h_info[o] == 0) {
+                status[o - first] = MOGP_OK;
+                nug[o - first] = h->h_hyper[(size_t)o * hs + d + 1];
+            } else {
+                failed.push_back(o);
             }
         }
-        if (status == MOGP_OK) {
-            h->fitted[o] = 1;
-            h->h_hyper[(size_t)o * hs + d + 1] = nug[i];
-        }
-        if (status_out) status_out[i] = status;
-        if (nugget_out) nugget_out[i] = nug[i];
-        if (logdet_out) logdet_out[i] = status == MOGP_OK ? h->h_scal[2 * o] : std::numeric_limits<double>::quiet_NaN();
-        if (quad_out) quad_out[i] = status == MOGP_OK ? h->h_scal[2 * o + 1] : std::numeric_limits<double>::quiet_NaN();
     }
-    // the nugget actually used enters the predictive variance
+    for (int i = 0; i < count; i++) {
+        const int o = first + i;
+        if (status[i] == MOGP_OK) h->fitted[o] = 1;
+        h->h_hyper[(size_t)o * hs + d + 1] = nug[i];   // the nugget actually used enters the predictive variance
+        if (status_out) status_out[i] = status[i];
+        if (nugget_out) nugget_out[i] = nug[i];
+        if (logdet_out) logdet_out[i] = status[i] == MOGP_OK ? h->h_scal[2 * o] : std::numeric_limits<double>::quiet_NaN();
+        if (quad_out) quad_out[i] = status[i] == MOGP_OK ? h->h_scal[2 * o + 1] : std::numeric_limits<double>::quiet_NaN();
+    }
     API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
                              cudaMemcpyHostToDevice, h->main));
     API_CUDA(cudaStreamSynchronize(h->main));
@@ -558,7 +581,8 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
             set_error("get K: allocation failed");
             return MOGP_ERR_NOMEM;
         }
-        int rc = kmat_sym(h->tmXT, h->kernel, n, np, h->d, h->hyper, idx, 0.0, tmp, 0, h->main);
+        const int one[1] = {idx};
+        int rc = kmat_sym(h->tmXT, h->kernel, n, np, h->d, h->hyper, one, 1, 0, tmp, 0, h->main);
         if (rc == 0) {
             cudaError_t e = cudaMemcpy2DAsync(out, sizeof(double) * n, tmp, sizeof(double) * np, sizeof(double) * n, n,
                                               cudaMemcpyDeviceToHost, h->main);

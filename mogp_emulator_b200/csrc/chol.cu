@@ -1,24 +1,33 @@
-// Blocked right-looking FP64 Cholesky for libmogp_b200 (replaces cusolverDnDpotrf, reference
+// Blocked FP64 Cholesky for libmogp_b200 (replaces cusolverDnDpotrf, reference
 // mogp_gpu/src/densegp_gpu.hpp:451-475; semantics of LAPACK dpotrf as used by the CPU reference,
 // mogp_emulator/linalg/cholesky.py:225-281).
 //
-// Storage: row-major lower triangle of an (n_pad x n_pad) matrix, ld = n_pad, n_pad % 128 == 0
-// (padding rows/cols carry an identity block).  Per 128-wide block column k:
-//   potf2_inv_kernel : warp-cooperative factorisation of the 128x128 diagonal block in shared memory
-//                      + its triangular inverse (kept in Dinv for the panel solve, the fit solves and
-//                      the predict TRSM) + running log-determinant + LAPACK-style info.
-//   tile kernel TRSM : L_ik = A_ik * inv(L_kk)^T  as a DMMA GEMM (64x128 tiles)
-//   tile kernel SYRK : A_ij -= L_ik * L_jk^T      as a DMMA GEMM (128x64 tiles, lower tiles only)
-// The two GEMM kernels are one template: TMA (cp.async.bulk.tensor.3d) producer warp -> mbarrier
-// full/empty ring of K-blocked stages -> 4 consumer warps issuing mma.sync.m16n8k8.f64 (setmaxnreg moves the producer warpgroup's
-// registers to them), two CTAs per SM.
+// Storage: row-major lower triangle of an (n_pad x n_pad) matrix per output, ld = n_pad, n_pad % 128 == 0
+// (padding rows/cols carry an identity block).  The factorisation of ALL outputs of a call is ONE persistent
+// dataflow kernel (one CTA per SM) that draws tiles from a global ticket counter in block-column-major order:
+//
+//   ROW  tile (i, p, j), i > j : the 64 rows p of block row i, block column j (left-looking)
+//            L_ij = (A_ij - sum_{k<j} L_ik L_jk^T) inv(L_jj)^T
+//   DIAG tile (j, p, j)        : R_jj = A_jj - sum_{k<j} L_jk L_jk^T   (64 rows p of the diagonal block)
+//   D    tile (j)              : L_jj = chol(R_jj), its triangular inverse (Dinv, used by every later solve),
+//                                log-determinant, LAPACK-style info
+//
+// Both products of a ROW tile are FP64 tensor-pipe GEMMs (mma.sync.m16n8k8.f64) in TN form, computed transposed
+// (block-column rows x panel rows) so the 64-row panel is the N side: the L_jk / inv(L_jj) tiles (A operand) and
+// the panel's own solved tiles L_(i,p),k (B operand) stream through a TMA -> mbarrier ring, A_ij lands in a
+// resident staging buffer that becomes the B operand of the diagonal product -- the same tile body as the
+// predict TRSM (predict.cu): a Cholesky panel row IS a forward substitution against the rows above it.
+// Every dependency of a tile has a smaller ticket, hence is held by a running CTA: progress counters in global
+// memory (red.release / ld.acquire + proxy fences for the TMA readers) order the tiles, nothing deadlocks, and
+// there is no per-step launch, tail or wave quantisation; outputs interleave in the ticket order, so many small
+// factorisations fill the machine as well as one large one.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace mogp {
 
 // ------------------------------------------------------------------------------------------
-// diagonal block: factor + invert
+// diagonal block: factor + invert, cooperatively by NTHR threads of one CTA (device function)
 // ------------------------------------------------------------------------------------------
 constexpr int PS = NB + 1;  // shared-memory row stride (doubles): odd => conflict-free column walks
 constexpr int SB = 16;      // sub-block width inside the diagonal block
@@ -33,22 +42,17 @@ struct Potf2Smem {
     int fail;
 };
 
-__global__ void __launch_bounds__(512, 1)
-potf2_inv_kernel(double* __restrict__ A, int64_t ld, int kblk, double* __restrict__ Dinv, int* __restrict__ info,
-                 double* __restrict__ logdet) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(smem_raw);
-    if (*info != 0) return;
-    const int tid = threadIdx.x;
-    const int64_t k0 = (int64_t)kblk * NB;
-    double* Ablk = A + k0 * ld + k0;
-
-    for (int idx = tid; idx < NB * NB; idx += 512) {
-        const int r = idx >> 7, c = idx & 127;
-        sm.S[r * PS + c] = (c <= r) ? Ablk[(int64_t)r * ld + c] : 0.0;
-    }
+// On entry sm.S holds the lower triangle of the block (upper part zero).  On success (returns 0) sm.S holds
+// inv(L) (lower), Lout (global, row stride ld) has received L with a zero upper part, and *logdet_add is
+// 2*sum(log L_ii) on thread 0.  On failure returns the 1-based index of the failing pivot (LAPACK info).
+// BAR_ALL / BAR_ROW: named barrier ids for all NTHR threads / the first 128 threads.
+template <int NTHR, int BAR_ALL, int BAR_ROW>
+__device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* __restrict__ Lout, int64_t ld,
+                                               double* logdet_add) {
+    constexpr int NG = NTHR / NB;   // thread groups of 128
+    static_assert(NTHR % NB == 0 && NG >= 1 && SB % NG == 0, "thread count");
     if (tid == 0) sm.fail = 0;
-    __syncthreads();
+    named_bar_sync(BAR_ALL, NTHR);
 
     // ---- factorisation: 8 sub-blocks of 16 columns -------------------------------------------
     for (int s = 0; s < NB / SB; s++) {
@@ -71,12 +75,12 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int kblk, double* __restric
                     sm.ri = ri;
                     sm.rd[r] = ri;
                 }
-                named_bar_sync(1, NB);
+                named_bar_sync(BAR_ROW, NB);
                 if (sm.fail) break;
                 const double ri = sm.ri;
                 if (r > j0 + j) a[j] *= ri;  // LAPACK scales the column by the reciprocal pivot
                 if (r >= j0 + j && r < j0 + SB) sm.Lr[(r - j0) * (SB + 1) + j] = a[j];
-                named_bar_sync(1, NB);
+                named_bar_sync(BAR_ROW, NB);
                 if (r > j0 + j) {
 #pragma unroll
                     for (int c = j + 1; c < SB; c++) {
@@ -94,7 +98,7 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int kblk, double* __restric
                 for (int jj = 0; jj < SB; jj++) sm.S[r * PS + j0 + jj] = (j0 + jj <= r) ? a[jj] : 0.0;
             }
         }
-        __syncthreads();
+        named_bar_sync(BAR_ALL, NTHR);
         if (sm.fail) break;
         // trailing update inside the diagonal block: S[r][c] -= sum_kk S[r][j0+kk] * S[c][j0+kk]
         {
@@ -103,7 +107,7 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int kblk, double* __restric
                 double a[SB];
 #pragma unroll
                 for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
-                for (int c = j0 + SB + q; c <= r; c += 4) {
+                for (int c = j0 + SB + q; c <= r; c += NG) {
                     double dot = 0.0;
 #pragma unroll
                     for (int kk = 0; kk < SB; kk++) dot = fma(a[kk], sm.S[c * PS + j0 + kk], dot);
@@ -111,25 +115,22 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int kblk, double* __restric
                 }
             }
         }
-        __syncthreads();
+        named_bar_sync(BAR_ALL, NTHR);
     }
-    if (sm.fail) {
-        if (tid == 0) *info = (int)k0 + sm.fail;
-        return;
-    }
+    if (sm.fail) return sm.fail;
 
     // ---- write L_kk back (upper part of the block zeroed) and accumulate log det -------------
-    for (int idx = tid; idx < NB * NB; idx += 512) {
+    for (int idx = tid; idx < NB * NB; idx += NTHR) {
         const int r = idx >> 7, c = idx & 127;
-        Ablk[(int64_t)r * ld + c] = sm.S[r * PS + c];
+        Lout[(int64_t)r * ld + c] = sm.S[r * PS + c];
     }
     {
         double v = (tid < NB) ? log(sm.S[tid * PS + tid]) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) sm.red[tid >> 5] = v;
-        __syncthreads();
-        if (tid == 0) *logdet += 2.0 * (sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3]);
+        if (tid < NB && (tid & 31) == 0) sm.red[tid >> 5] = v;
+        named_bar_sync(BAR_ALL, NTHR);
+        if (tid == 0) *logdet_add = 2.0 * ((sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]));
     }
 
     // ---- in-place inverse of the lower-triangular block --------------------------------------
@@ -148,195 +149,397 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int kblk, double* __restric
                 x[i] = (i == c) ? rdi : ((i > c) ? -sacc * rdi : 0.0);
             }
         }
-        __syncthreads();
+        named_bar_sync(BAR_ALL, NTHR);
         if (tid < NB) {
             double* Lb = sm.S + (b * SB) * PS + b * SB;
 #pragma unroll
             for (int i = 0; i < SB; i++)
                 if (i >= c) Lb[i * PS + c] = x[i];
         }
-        __syncthreads();
+        named_bar_sync(BAR_ALL, NTHR);
     }
     // (ii) block columns right to left:  Inv21 = -Inv22 * L21 * Inv11
+    constexpr int CW = SB / NG;   // columns of the 16-wide block column handled per thread
     for (int J = NB / SB - 2; J >= 0; J--) {
         const int R0 = SB * (J + 1), C0 = SB * J;
         const int r = tid & 127, cq = tid >> 7;
         if (r >= R0) {
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+            double x[CW];
+#pragma unroll
+            for (int cc = 0; cc < CW; cc++) x[cc] = 0.0;
             for (int q = R0; q <= r; q++) {
                 const double a = sm.S[r * PS + q];
-                const double* bq = sm.S + q * PS + C0 + 4 * cq;
-                x0 = fma(a, bq[0], x0);
-                x1 = fma(a, bq[1], x1);
-                x2 = fma(a, bq[2], x2);
-                x3 = fma(a, bq[3], x3);
+                const double* bq = sm.S + q * PS + C0 + CW * cq;
+#pragma unroll
+                for (int cc = 0; cc < CW; cc++) x[cc] = fma(a, bq[cc], x[cc]);
             }
-            double* xr = sm.X + r * (SB + 1) + 4 * cq;
-            xr[0] = x0; xr[1] = x1; xr[2] = x2; xr[3] = x3;
+            double* xr = sm.X + r * (SB + 1) + CW * cq;
+#pragma unroll
+            for (int cc = 0; cc < CW; cc++) xr[cc] = x[cc];
         }
-        __syncthreads();
+        named_bar_sync(BAR_ALL, NTHR);
         if (r >= R0) {
             const double* xr = sm.X + r * (SB + 1);
 #pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const int c = 4 * cq + cc;
+            for (int cc = 0; cc < CW; cc++) {
+                const int c = CW * cq + cc;
                 double y = 0.0;
                 for (int kk = c; kk < SB; kk++) y = fma(xr[kk], sm.S[(C0 + kk) * PS + C0 + c], y);
                 sm.S[r * PS + C0 + c] = -y;
             }
         }
-        __syncthreads();
+        named_bar_sync(BAR_ALL, NTHR);
     }
-    double* Dblk = Dinv + k0 * NB;
-    for (int idx = tid; idx < NB * NB; idx += 512) {
-        const int r = idx >> 7, c = idx & 127;
-        Dblk[idx] = (c <= r) ? sm.S[r * PS + c] : 0.0;
-    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
-// DMMA tile kernel (TRSM panel solve and SYRK trailing update)
+// the dataflow kernel
 // ------------------------------------------------------------------------------------------
-enum { OP_SYRK = 0, OP_TRSM = 1 };
-
-template <int WGM, int WGN, int NT, int NS>
-struct TileCfg {
-    static constexpr int BM = 32 * WGM;
-    static constexpr int BN = 8 * NT * WGN;
-    static constexpr int NCW = WGM * WGN;
-    static constexpr int THREADS = (NCW + 4) * 32;  // consumer warpgroup + producer warpgroup (one active lane)
-    static constexpr int A_BYTES = BM * KC * 8;
+struct CholCfg {
+    static constexpr int BN = 64;                  // panel rows per tile (the N side of the transposed products)
+    static constexpr int NT = BN / 16;
+    static constexpr int NCW = 8;                  // DMMA consumer warps
+    static constexpr int THREADS = (NCW + 4) * 32; // + producer warpgroup (one active lane)
+    static constexpr int NS = 4;
+    static constexpr int A_BYTES = NB * KC * 8;
     static constexpr int B_BYTES = BN * KC * 8;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 2 * NS * 8 + 128;
+    static constexpr int VS_BYTES = NB * BN * 8;
+    static constexpr int BAR_BYTES = (2 * NS + 2 + 4 + 1) * 8 + 16;
+    static constexpr int SMEM_BYTES = NS * STAGE_BYTES + VS_BYTES + BAR_BYTES + 128;
+};
+static_assert(sizeof(Potf2Smem) <= CholCfg::NS * CholCfg::STAGE_BYTES + CholCfg::VS_BYTES,
+              "the diagonal-block factorisation borrows the ring + staging buffer");
+
+constexpr int CH_HDR = 32;   // ints in front of the per-output progress blocks (word 0 = ticket counter)
+
+struct CholParams {
+    double* A;          // matrix slab [E*n_pad][n_pad]
+    double* Dinv;       // [E*n_pad][128]
+    int64_t n_pad;
+    int T;              // n_pad / 128
+    int count;          // outputs factorised by this launch
+    int outs[MAXG];     // their slab indices
+    int* info;          // [E]   LAPACK info per output (0 = ok); must be zero on entry
+    double* scal;       // [E][2] scal[2*o] receives log det
+    int* sync;          // [CH_HDR + count*(2T+8)]: ticket, then per output prog[T][2] and dprog (zeroed per launch)
 };
 
-template <int OP, int WGM, int WGN, int NT, int NS>
-__global__ void __launch_bounds__(TileCfg<WGM, WGN, NT, NS>::THREADS, 2)
-chol_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 double* __restrict__ A, int64_t ld, int row_base, int kblk, const int* __restrict__ info) {
-    // A: slab base; row_base: first slab row of this output's matrix (also its first Dinv slab row)
-    using Cfg = TileCfg<WGM, WGN, NT, NS>;
-    extern __shared__ __align__(128) unsigned char tile_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tile_smem_raw) + 127) & ~uintptr_t(127));
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + NS * Cfg::STAGE_BYTES);
-    uint64_t* empty = full + NS;
+enum { TK_DIAG = 0, TK_D = 1, TK_ROW = 2 };
 
-    if (*info != 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+struct TileId {
+    int kind, lo, i, p, j;
+};
 
-    // tile coordinates
-    int arow, brow, a_kout0, b_kout0;
-    if (OP == OP_SYRK) {
-        const int id = blockIdx.x;
-        int I = (int)((sqrtf(4.0f * (float)id + 1.0f) - 1.0f) * 0.5f);
-        while ((I + 1) * (I + 2) <= id) I++;
-        while (I * (I + 1) > id) I--;
-        const int J2 = id - I * (I + 1);
-        arow = row_base + (kblk + 1 + I) * NB;
-        brow = row_base + (kblk + 1) * NB + J2 * Cfg::BN;
-        a_kout0 = b_kout0 = kblk * (NB / 8);
+// ticket -> tile.  Column j holds count*(2T+1-2j) tickets: [2*count DIAG][count D][count*2*(T-1-j) ROW, i ascending]
+__device__ __forceinline__ TileId decode_ticket(int t, int T, int count) {
+    TileId id;
+    const int x = t / count;
+    int j = (int)((double)(T + 1) - sqrt((double)(T + 1) * (double)(T + 1) - (double)x));
+    if (j < 0) j = 0;
+    if (j > T - 1) j = T - 1;
+    while (j > 0 && j * (2 * T + 2 - j) > x) j--;
+    while (j < T - 1 && (j + 1) * (2 * T + 2 - (j + 1)) <= x) j++;
+    int u = t - count * j * (2 * T + 2 - j);
+    id.j = j;
+    if (u < 2 * count) {
+        id.kind = TK_DIAG; id.lo = u >> 1; id.p = u & 1; id.i = j;
+    } else if (u < 3 * count) {
+        id.kind = TK_D; id.lo = u - 2 * count; id.p = 0; id.i = j;
     } else {
-        arow = row_base + (kblk + 1) * NB + blockIdx.x * Cfg::BM;
-        brow = row_base + kblk * NB;  // rows of the Dinv slab
-        a_kout0 = kblk * (NB / 8);
-        b_kout0 = 0;
+        u -= 3 * count;
+        const int per = 2 * (T - 1 - j);
+        id.kind = TK_ROW; id.lo = u / per;
+        const int w = u - id.lo * per;
+        id.i = j + 1 + (w >> 1); id.p = w & 1;
     }
+    return id;
+}
+
+__global__ void __launch_bounds__(CholCfg::THREADS, 1)
+chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ CUtensorMap tmD, const CholParams p) {
+    using Cfg = CholCfg;
+    constexpr int NS = Cfg::NS, BN = Cfg::BN, NT = Cfg::NT;
+    extern __shared__ __align__(128) unsigned char chol_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(chol_smem_raw) + 127) & ~uintptr_t(127));
+    double* VS = reinterpret_cast<double*>(base + NS * Cfg::STAGE_BYTES);  // [128/8][BN][8]
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + NS * Cfg::STAGE_BYTES + Cfg::VS_BYTES);
+    uint64_t* empty = full + NS;
+    uint64_t* ks_full = empty + NS;
+    uint64_t* vs_free = ks_full + 1;
+    uint64_t* tq_full = vs_free + 1;   // [2]
+    uint64_t* tq_empty = tq_full + 2;  // [2]
+    uint64_t* d_done = tq_empty + 2;   // consumers are done with the borrowed smem of a D tile
+    int* tq = reinterpret_cast<int*>(d_done + 1);  // [2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T;
+    const int total = p.count * T * (T + 2);
+    const int blk = 2 * T + 8;   // ints per output in the progress area
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], Cfg::NCW);
         }
+        mbar_init(ks_full, 1);
+        mbar_init(vs_free, Cfg::NCW);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tq_full[s], 1);
+            mbar_init(&tq_empty[s], Cfg::NCW);
+        }
+        mbar_init(d_done, Cfg::NCW);
         fence_mbar_init();
     }
     __syncthreads();
 
-    constexpr int NCHUNK = NB / KC;
+    constexpr int NCH = NB / KC;  // chunks per 128-wide K block
+    constexpr int SKIP = 1 << 30;
     if (warp >= Cfg::NCW) {
-        // ---- TMA producer warpgroup (hands its registers to the consumers) ----
-        reg_dealloc<24>();
+        // =========================== ticket + TMA producer ===========================
+        reg_dealloc<40>();
         if (warp == Cfg::NCW && lane == 0) {
-            prefetch_tmap(&tmA);
-            prefetch_tmap(&tmB);
+            prefetch_tmap(&tmL);
+            prefetch_tmap(&tmW);
+            prefetch_tmap(&tmD);
             PipeState<NS> ps;
-            for (int c = 0; c < NCHUNK; c++) {
-                mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
-                unsigned char* st = base + ps.stage * Cfg::STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[ps.stage], Cfg::STAGE_BYTES);
-                tma_load_3d(st, &tmA, 0, arow, a_kout0 + c * (KC / 8), &full[ps.stage]);
-                tma_load_3d(st + Cfg::A_BYTES, &tmB, 0, brow, b_kout0 + c * (KC / 8), &full[ps.stage]);
-                ps.advance();
+            int seq = 0, dseq = 0;
+            for (int nq = 0;; nq++) {
+                const int slot = nq & 1;
+                mbar_wait(&tq_empty[slot], (uint32_t)(((nq >> 1) & 1) ^ 1));
+                const int t = atomicAdd(p.sync, 1);
+                if (t >= total) {
+                    tq[slot] = -1;
+                    mbar_arrive(&tq_full[slot]);
+                    break;
+                }
+                const TileId id = decode_ticket(t, T, p.count);
+                const int o = p.outs[id.lo];
+                int* prog = p.sync + CH_HDR + id.lo * blk;   // prog[i*2 + p]
+                int* dprog = prog + 2 * T;
+                const int j = id.j;
+                if (id.kind == TK_D) {
+                    // both halves of R_jj are in place; consumers factor it with plain (L2) loads
+                    wait_counter(prog + 2 * j, Cfg::NCW * (j + 1));
+                    wait_counter(prog + 2 * j + 1, Cfg::NCW * (j + 1));
+                    const bool skip = ld_acquire_gpu(p.info + o) != 0;
+                    tq[slot] = t | (skip ? SKIP : 0);
+                    mbar_arrive(&tq_full[slot]);
+                    // the D tile borrows the ring and the staging buffer: nothing may be in flight into them
+                    mbar_wait(d_done, (uint32_t)(dseq & 1));
+                    dseq++;
+                    continue;
+                }
+                const bool skip = ld_acquire_gpu(p.info + o) != 0;   // a failed output only bumps its counters
+                tq[slot] = t | (skip ? SKIP : 0);
+                mbar_arrive(&tq_full[slot]);
+                if (skip) continue;
+                const int rb = (int)(o * p.n_pad);
+                const int wrow = rb + id.i * NB + id.p * BN;   // the tile's 64 rows
+                const int lrow = rb + j * NB;                  // block row j (L_jk tiles, Dinv_jj)
+                int* prog_own = prog + 2 * id.i + id.p;
+                bool vs_loaded = false;
+                int issued = 0;
+                auto load_vs = [&]() {
+                    if (seq > 0) mbar_wait(vs_free, (uint32_t)((seq - 1) & 1));
+                    mbar_arrive_expect_tx(ks_full, Cfg::VS_BYTES);
+                    for (int ch = 0; ch < NCH; ch++)
+                        tma_load_3d(VS + ch * (KC / 8) * BN * 8, &tmW, 0, wrow, j * (NB / 8) + ch * (KC / 8), ks_full);
+                    vs_loaded = true;
+                };
+                // operands of block k: L_jk (both row halves of block row j) and the tile's own L_(i,p),k
+                bool all_ready = (j == 0) || (ld_acquire_gpu(prog_own) >= Cfg::NCW * j &&
+                                              ld_acquire_gpu(prog + 2 * j) >= Cfg::NCW * j &&
+                                              ld_acquire_gpu(prog + 2 * j + 1) >= Cfg::NCW * j);
+                if (all_ready) fence_proxy_async();
+                for (int k = 0; k < j; k++) {
+                    if (!all_ready) {
+                        wait_counter(prog_own, Cfg::NCW * (k + 1));
+                        wait_counter(prog + 2 * j, Cfg::NCW * (k + 1));
+                        wait_counter(prog + 2 * j + 1, Cfg::NCW * (k + 1));
+                        fence_proxy_async();
+                    }
+                    for (int ch = 0; ch < NCH; ch++) {
+                        if (!vs_loaded && issued == NS - 1) load_vs();
+                        mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
+                        unsigned char* st = base + ps.stage * Cfg::STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[ps.stage], Cfg::STAGE_BYTES);
+                        const int kout = k * (NB / 8) + ch * (KC / 8);
+                        tma_load_3d(st, &tmL, 0, lrow, kout, &full[ps.stage]);
+                        tma_load_3d(st + Cfg::A_BYTES, &tmW, 0, wrow, kout, &full[ps.stage]);
+                        ps.advance();
+                        issued++;
+                    }
+                }
+                if (!vs_loaded) load_vs();
+                if (id.kind == TK_ROW) {
+                    // inv(L_jj): published by the D tile of column j
+                    wait_counter(dprog, Cfg::NCW * (j + 1));
+                    fence_proxy_async();
+                    for (int ch = 0; ch < NCH; ch++) {
+                        mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
+                        unsigned char* st = base + ps.stage * Cfg::STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[ps.stage], Cfg::A_BYTES);
+                        tma_load_3d(st, &tmD, 0, lrow, ch * (KC / 8), &full[ps.stage]);
+                        ps.advance();
+                    }
+                }
+                seq++;
             }
         }
         return;
     }
 
-    // ---- DMMA consumers ----
+    // =========================== DMMA consumers ===========================
     reg_alloc<232>();
-    const int wm = warp / WGN, wn = warp % WGN;
-    const int g = lane >> 2, t = lane & 3;
-    double acc[2][NT][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++)
-#pragma unroll
-            for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.0;
+    const int ctid = threadIdx.x;   // 0..255
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int arow0 = wm * 32, bcol0 = wn * 8 * NT;
 
     PipeState<NS> ps;
-    for (int c = 0; c < NCHUNK; c++) {
-        mbar_wait(&full[ps.stage], ps.phase);
-        const double* As = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES);
-        const double* Bs = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES + Cfg::A_BYTES);
-        mma_stage<2, NT, KC>(acc, As, Cfg::BM, wm * 32, Bs, Cfg::BN, wn * 8 * NT, g, t);
+    int seq = 0;
+    for (int nq = 0;; nq++) {
+        const int slot = nq & 1;
+        mbar_wait(&tq_full[slot], (uint32_t)((nq >> 1) & 1));
+        const int tword = tq[slot];
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[ps.stage]);
-        ps.advance();
-    }
+        if (lane == 0) mbar_arrive(&tq_empty[slot]);
+        if (tword < 0) break;
+        const bool skip = (tword & SKIP) != 0;
+        const TileId id = decode_ticket(tword & (SKIP - 1), T, p.count);
+        const int o = p.outs[id.lo];
+        int* prog = p.sync + CH_HDR + id.lo * blk;
+        int* dprog = prog + 2 * T;
+        const int j = id.j;
+        const int64_t rb = (int64_t)o * p.n_pad;
 
-    // ---- epilogue ----
-    const int64_t crow0 = arow + wm * 32 + g;
-    const int64_t ccol0 = (OP == OP_SYRK ? brow - row_base : kblk * NB) + wn * 8 * NT + 2 * t;
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            double* rowp = A + (crow0 + mt * 16 + h * 8) * ld + ccol0;
-            if (OP == OP_SYRK) {
-                double2 v[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; nt++) v[nt] = *reinterpret_cast<const double2*>(rowp + nt * 8);
-#pragma unroll
-                for (int nt = 0; nt < NT; nt++) {
-                    v[nt].x -= acc[mt][nt][2 * h];
-                    v[nt].y -= acc[mt][nt][2 * h + 1];
-                    *reinterpret_cast<double2*>(rowp + nt * 8) = v[nt];
+        if (id.kind == TK_D) {
+            if (!skip) {
+                Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(base);
+                double* Ablk = p.A + (rb + (int64_t)j * NB) * p.n_pad + (int64_t)j * NB;
+                for (int idx = ctid; idx < NB * NB; idx += Cfg::NCW * 32) {
+                    const int r = idx >> 7, c = idx & 127;
+                    sm.S[r * PS + c] = (c <= r) ? __ldcg(Ablk + (int64_t)r * p.n_pad + c) : 0.0;
                 }
-            } else {
-#pragma unroll
-                for (int nt = 0; nt < NT; nt++)
-                    *reinterpret_cast<double2*>(rowp + nt * 8) = make_double2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+                double ld_add = 0.0;
+                const int fail = potf2_inv_block<Cfg::NCW * 32, 2, 3>(sm, ctid, Ablk, p.n_pad, &ld_add);
+                if (fail) {
+                    if (ctid == 0) p.info[o] = j * NB + fail;
+                } else {
+                    double* Dblk = p.Dinv + (rb + (int64_t)j * NB) * NB;
+                    for (int idx = ctid; idx < NB * NB; idx += Cfg::NCW * 32) {
+                        const int r = idx >> 7, c = idx & 127;
+                        Dblk[idx] = (c <= r) ? sm.S[r * PS + c] : 0.0;
+                    }
+                    // the D tiles of one output run strictly in order: plain read-modify-write is race-free
+                    if (ctid == 0) p.scal[2 * o] = (j > 0 ? __ldcg(p.scal + 2 * o) : 0.0) + ld_add;
+                }
             }
+            __threadfence();
+            fence_proxy_async();
+            named_bar_sync(1, Cfg::NCW * 32);   // everyone is done with the borrowed shared memory
+            if (lane == 0) {
+                red_release_gpu_add(dprog, 1);
+                mbar_arrive(d_done);
+            }
+            continue;
         }
+        if (skip) {
+            __syncwarp();
+            if (lane == 0) red_release_gpu_add(prog + 2 * id.i + id.p, 1);
+            continue;
+        }
+
+        const int64_t wrow = rb + (int64_t)id.i * NB + id.p * BN;
+        double acc[2][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[mt][nt][e] = 0.0;
+
+        // acc[c][r] = sum_{k<j} L_jk[c,:] . L_(i,p),k[r,:]      (c: column inside block j, r: panel row)
+        for (int c = 0; c < j * NCH; c++) {
+            mbar_wait(&full[ps.stage], ps.phase);
+            const double* As = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES);
+            const double* Bs = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+            mma_stage<2, NT, KC>(acc, As, NB, arow0, Bs, BN, bcol0, g, t4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[ps.stage]);
+            ps.advance();
+        }
+
+        // R = A_tile - acc, in place in VS (element (k = column c of block j, n = panel row r) at VS[c/8][r][c%8])
+        mbar_wait(ks_full, (uint32_t)(seq & 1));
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int r = arow0 + mt * 16 + g + ((e >> 1) << 3);
+                    const int c = bcol0 + nt * 8 + 2 * t4 + (e & 1);
+                    double* qv = VS + ((size_t)((r >> 3) * BN + c) * 8 + (r & 7));
+                    *qv = *qv - acc[mt][nt][e];
+                    acc[mt][nt][e] = 0.0;
+                }
+        named_bar_sync(1, Cfg::NCW * 32);
+
+        if (id.kind == TK_DIAG) {
+            // write R back in place: 64 B segments (8 columns of one row) per thread
+            for (int idx = ctid; idx < (NB / 8) * BN; idx += Cfg::NCW * 32) {
+                const int k8 = idx / BN, r = idx - k8 * BN;
+                const double2* src = reinterpret_cast<const double2*>(VS + (size_t)idx * 8);
+                double2* dst = reinterpret_cast<double2*>(p.A + (wrow + r) * p.n_pad + (int64_t)j * NB + k8 * 8);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(vs_free);
+            seq++;
+        } else {
+            // L_ij^T = inv(L_jj) * R^T
+            for (int ch = 0; ch < NCH; ch++) {
+                mbar_wait(&full[ps.stage], ps.phase);
+                const double* As = reinterpret_cast<const double*>(base + ps.stage * Cfg::STAGE_BYTES);
+                mma_stage<2, NT, KC>(acc, As, NB, arow0, VS + ch * (KC / 8) * BN * 8, BN, bcol0, g, t4);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                ps.advance();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(vs_free);
+            seq++;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e1 = 0; e1 < 2; e1++) {
+                    const int c = bcol0 + nt * 8 + 2 * t4 + e1;   // panel row
+                    double* wr = p.A + (wrow + c) * p.n_pad + (int64_t)j * NB + arow0 + g;
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        wr[mt * 16] = acc[mt][nt][e1];
+                        wr[mt * 16 + 8] = acc[mt][nt][2 + e1];
+                    }
+                }
+        }
+        // publish: generic-proxy global writes -> gpu scope -> async-proxy (TMA) readers of other CTAs
+        __threadfence();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add(prog + 2 * id.i + id.p, 1);
     }
 }
-
-using SyrkCfg = TileCfg<4, 1, 8, 4>;  // 128 x 64 tiles
-using TrsmCfg = TileCfg<2, 2, 8, 4>;  // 64 x 128 tiles
 
 int chol_init() {
     static bool done = false;
     if (done) return 0;
-    cudaError_t e;
-    e = cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Potf2Smem));
-    if (e != cudaSuccess) return 1;
-    e = cudaFuncSetAttribute(chol_tile_kernel<OP_SYRK, 4, 1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SyrkCfg::SMEM_BYTES);
-    if (e != cudaSuccess) return 1;
-    e = cudaFuncSetAttribute(chol_tile_kernel<OP_TRSM, 2, 2, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TrsmCfg::SMEM_BYTES);
-    if (e != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CholCfg::SMEM_BYTES) !=
+        cudaSuccess)
+        return 1;
     done = true;
     return 0;
 }
@@ -348,29 +551,23 @@ int chol_make_maps(CholMaps* maps, double* A_slab, double* Dinv_slab, int64_t to
     return 0;
 }
 
-// Enqueue the whole factorisation of output `o` of the slab on `st`.  info/logdet must have been zeroed.
-// Returns the number of kernels launched (negative on launch error).
-int chol_factor(const CholMaps& maps, double* A_slab, double* Dinv_slab, int o, int64_t n_pad, int* info,
-                double* logdet, cudaStream_t st) {
-    const int T = (int)(n_pad / NB);
-    const int row_base = (int)(o * n_pad);
-    double* A = A_slab + (int64_t)row_base * n_pad;
-    double* Dinv = Dinv_slab + (int64_t)row_base * NB;
-    int launches = 0;
-    for (int k = 0; k < T; k++) {
-        potf2_inv_kernel<<<1, 512, sizeof(Potf2Smem), st>>>(A, n_pad, k, Dinv, info, logdet);
-        launches++;
-        const int Tt = T - k - 1;
-        if (Tt > 0) {
-            chol_tile_kernel<OP_TRSM, 2, 2, 8, 4>
-                <<<Tt * (NB / TrsmCfg::BM), TrsmCfg::THREADS, TrsmCfg::SMEM_BYTES, st>>>(maps.a64, maps.d128, A_slab, n_pad, row_base, k, info);
-            chol_tile_kernel<OP_SYRK, 4, 1, 8, 4>
-                <<<Tt * (Tt + 1), SyrkCfg::THREADS, SyrkCfg::SMEM_BYTES, st>>>(maps.a128, maps.a64, A_slab, n_pad, row_base, k, info);
-            launches += 2;
-        }
-    }
+size_t chol_sync_bytes(int count, int T) { return sizeof(int) * ((size_t)CH_HDR + (size_t)count * (2 * T + 8)); }
+
+// Enqueue the factorisation of `count` outputs (slab indices outs[]) on `st` as one launch.  info[o] and
+// scal[2*o] of those outputs must have been zeroed.  Returns the number of kernels launched (negative on error).
+int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, const int* outs, int count,
+                      int64_t n_pad, int* info, double* scal, int* sync, int n_sms, cudaStream_t st) {
+    if (count < 1 || count > MAXG) return -1;
+    CholParams p{};
+    p.A = A_slab; p.Dinv = Dinv_slab; p.n_pad = n_pad; p.T = (int)(n_pad / NB); p.count = count;
+    for (int i = 0; i < count; i++) p.outs[i] = outs[i];
+    p.info = info; p.scal = scal; p.sync = sync;
+    if (cudaMemsetAsync(sync, 0, chol_sync_bytes(count, p.T), st) != cudaSuccess) return -1;
+    const int64_t tiles = (int64_t)count * p.T * (p.T + 2);
+    const unsigned grid = (unsigned)(tiles < n_sms ? tiles : n_sms);
+    chol_dataflow_kernel<<<grid, CholCfg::THREADS, CholCfg::SMEM_BYTES, st>>>(maps.a128, maps.a64, maps.d128, p);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return launches;
+    return 1;
 }
 
 }  // namespace mogp

@@ -95,6 +95,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- cross-CTA dataflow helpers (ticket counters / ready flags in global memory) ----
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until *p >= target.  A producer thread that then issues TMA loads of the published data must follow up
+// with fence_proxy_async() (the data was written through the generic proxy).
+__device__ __forceinline__ void wait_counter(const int* p, int target) {
+    if (ld_acquire_gpu(p) >= target) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_gpu(p) < target) {
+        __nanosleep(100);
+        if (globaltimer_ns() - t0 > 20000000000ull) __trap();   // 20 s: never in a correct run
+    }
+}
+
 // D(16x8) += A(16x8, row) * B(8x8, col), FP64 tensor pipe (SASS: DMMA.16x8x8)
 __device__ __forceinline__ void dmma_16x8x8(double (&c)[4], double a0, double a1, double a2, double a3, double b0,
                                             double b1) {

@@ -20,15 +20,17 @@ struct CholMaps {
 // ---- chol.cu ----
 int chol_init();
 int chol_make_maps(CholMaps* maps, double* A_slab, double* Dinv_slab, int64_t total_rows, int64_t n_pad);
-// factorise output `o` of the slab in place on `st`; info/logdet must be zero.  Returns #launches or -1.
-int chol_factor(const CholMaps& maps, double* A_slab, double* Dinv_slab, int o, int64_t n_pad, int* info,
-                double* logdet, cudaStream_t st);
+size_t chol_sync_bytes(int count, int T);
+// factorise `count` outputs (slab indices outs[]) in place as one dataflow launch on `st`; info[o] / scal[2*o]
+// must be zero.  Returns #launches or -1.
+int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, const int* outs, int count,
+                      int64_t n_pad, int* info, double* scal, int* sync, int n_sms, cudaStream_t st);
 
 // ---- kmat.cu ----
 int kmat_init();
 int kmat_dbox(int d);
-int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, int out_idx,
-             double nugget, double* A_slab, int64_t row_base, cudaStream_t st);
+int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, const int* outs,
+             int count, int add_nugget, double* A_slab, int64_t slab_rows_per_output, cudaStream_t st);
 int kmat_cross(const CUtensorMap& tmXsT, const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int64_t m_pad,
                int d, const int* outs, int count, const double* hyper, double* W_slab, int64_t w_stride, int store,
                const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st);
@@ -37,8 +39,8 @@ int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int
 
 // ---- solve.cu ----
 int solve_init();
-int solve_alpha(const double* A, int64_t n_pad, const double* Dinv, const double* y, double* z, double* alpha,
-                double* quad, const int* info, cudaStream_t st);
+int solve_alpha(const double* A_slab, int64_t n_pad, const double* Dinv_slab, const double* Y, double* z, double* alpha,
+                double* scal, const int* info, const int* outs, int count, cudaStream_t st);
 
 // ---- predict.cu ----
 int predict_init();

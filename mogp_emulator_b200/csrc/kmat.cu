@@ -37,14 +37,13 @@ struct KmatParams {
     int hyper_stride;       // doubles per output in hyper (d + 2)
     const double* hyper;    // [count][d+2]
     double* out;            // SYM: matrix slab base; CROSS: workspace slab base
-    int64_t out_row_base;   // SYM: first row of this output inside the slab
     int64_t out_stride;     // CROSS: rows per output in the workspace slab
     const double* alpha;    // CROSS: [count][n_pad] or null
     int64_t alpha_stride;
     double* part;           // CROSS: [count][n_tiles][rows_pad] or null
     int outs[MAXG];         // global output index handled by blockIdx.z (hyper/alpha rows)
     int store;              // CROSS: write the matrix (0 when only the mean is wanted)
-    double nugget;          // SYM: value added on the diagonal
+    int add_nugget;         // SYM: add hyper[d+1] (the nugget) on the diagonal
 };
 
 template <int KT, int CROSS>
@@ -64,6 +63,7 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
         o = blockIdx.z;
     } else {
         const int id = blockIdx.x;
+        o = blockIdx.y;
         I = (int)((sqrtf(8.0f * (float)id + 1.0f) - 1.0f) * 0.5f);
         while ((I + 1) * (I + 2) / 2 <= id) I++;
         while (I * (I + 1) / 2 > id) I--;
@@ -115,15 +115,17 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
 
     const double sigma2 = hyp[p.d];
     if (!CROSS) {
+        const double nugget = p.add_nugget ? hyp[p.d + 1] : 0.0;
+        const int64_t row_base = (int64_t)p.outs[o] * p.out_stride;
 #pragma unroll
         for (int a = 0; a < 8; a++) {
             const int64_t row = (int64_t)I * 128 + ty + 16 * a;
-            double* orow = p.out + (p.out_row_base + row) * p.n_pad;
+            double* orow = p.out + (row_base + row) * p.n_pad;
 #pragma unroll
             for (int b = 0; b < 8; b++) {
                 const int64_t col = (int64_t)J * 128 + tx + 16 * b;
                 double v = sigma2 * kfun<KT>(r2[a][b]);
-                if (row == col) v += p.nugget;
+                if (row == col) v += nugget;
                 if (row >= p.n || col >= p.n) v = (row == col) ? 1.0 : 0.0;
                 orow[col] = v;
             }
@@ -171,17 +173,22 @@ int kmat_init() { return 0; }
 
 int kmat_dbox(int d) { return d < DCH ? d : DCH; }
 
-int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, int out_idx,
-             double nugget, double* A_slab, int64_t row_base, cudaStream_t st) {
+// K + nugget*I (lower 128x128 tiles) of `count` outputs in one launch.  Output k uses hyper row outs[k] and is
+// written at slab rows slab_idx[k]*n_pad.. of A_slab (slab_idx == nullptr: same as outs).
+int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, const int* outs,
+             int count, int add_nugget, double* A_slab, int64_t slab_rows_per_output, cudaStream_t st) {
+    if (count < 1 || count > MAXG) return 1;
     KmatParams p{};
     p.n = n; p.n_pad = n_pad; p.rows_pad = n_pad; p.d = d; p.dbox = kmat_dbox(d); p.hyper_stride = d + 2;
-    p.hyper = hyper; p.out = A_slab; p.out_row_base = row_base; p.outs[0] = out_idx; p.nugget = nugget;
+    p.hyper = hyper; p.out = A_slab; p.out_stride = slab_rows_per_output; p.add_nugget = add_nugget;
+    for (int i = 0; i < count; i++) p.outs[i] = outs[i];
     const int T = (int)(n_pad / 128);
     const int tiles = T * (T + 1) / 2;
+    dim3 grid((unsigned)tiles, (unsigned)count);
     if (kernel == MOGP_KERNEL_SQEXP)
-        kmat_kernel<MOGP_KERNEL_SQEXP, 0><<<tiles, 256, 0, st>>>(tmXT, tmXT, p);
+        kmat_kernel<MOGP_KERNEL_SQEXP, 0><<<grid, 256, 0, st>>>(tmXT, tmXT, p);
     else
-        kmat_kernel<MOGP_KERNEL_MATERN52, 0><<<tiles, 256, 0, st>>>(tmXT, tmXT, p);
+        kmat_kernel<MOGP_KERNEL_MATERN52, 0><<<grid, 256, 0, st>>>(tmXT, tmXT, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

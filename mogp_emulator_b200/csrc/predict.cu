@@ -56,20 +56,6 @@ struct PredParams {
     double* normacc;        // [count][w_stride] running ||V_c||^2 over the block rows done so far
 };
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 // Dataflow (tile-ticket) blocked forward substitution.
 //
 // Unit of work = tile (block row i, panel of BN test points, output):   V_i = inv(L_ii) (K*_i - sum_{j<i} L_ij V_j).

@@ -44,14 +44,34 @@ __device__ __forceinline__ void dsmem_store(double* local, uint32_t rank, double
 
 constexpr int SOLVE_THREADS = 512;
 
+struct SolveParams {
+    const double* A;      // matrix slab [E*n_pad][n_pad] holding the factors
+    const double* Dinv;   // [E*n_pad][128]
+    const double* Y;      // [E][n_pad]
+    double* z;            // [E][n_pad]
+    double* alpha;        // [E][n_pad]
+    double* scal;         // [E][2]: scal[2*o+1] receives y^T K^-1 y
+    const int* info;      // [E]
+    int64_t n_pad;
+    int T;
+    int outs[MAXG];       // slab index of the output solved by cluster k
+};
+
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
-solve_alpha_kernel(const double* __restrict__ A, int64_t ld, int T, const double* __restrict__ Dinv,
-                   const double* __restrict__ y, double* __restrict__ z_out, double* __restrict__ alpha_out,
-                   double* __restrict__ quad, const int* __restrict__ info) {
+solve_alpha_kernel(const SolveParams sp) {
     extern __shared__ __align__(16) double sv[];
-    // every CTA of the cluster takes the same branch: no barrier is left dangling
-    if (*info != 0) return;
     const int C = (int)cluster_nctarank(), me = (int)cluster_ctarank();
+    const int o = sp.outs[blockIdx.x / C];
+    // every CTA of the cluster takes the same branch: no barrier is left dangling
+    if (sp.info[o] != 0) return;
+    const int64_t ld = sp.n_pad;
+    const int T = sp.T;
+    const double* __restrict__ A = sp.A + (int64_t)o * ld * ld;
+    const double* __restrict__ Dinv = sp.Dinv + (int64_t)o * ld * NB;
+    const double* __restrict__ y = sp.Y + (int64_t)o * ld;
+    double* __restrict__ z_out = sp.z + (int64_t)o * ld;
+    double* __restrict__ alpha_out = sp.alpha + (int64_t)o * ld;
+    double* __restrict__ quad = sp.scal + 2 * o + 1;
     const int nown = (T + C - 1) / C;        // blocks of the vector kept by one CTA (block j lives in CTA j % C, slot j / C)
     double* v = sv;                          // [nown][128]
     double* slots = v + (size_t)nown * NB;   // [C][128] partial sums received from the cluster
@@ -228,16 +248,22 @@ int solve_init() {
     return 0;
 }
 
-int solve_alpha(const double* A, int64_t n_pad, const double* Dinv, const double* y, double* z, double* alpha,
-                double* quad, const int* info, cudaStream_t st) {
+// z = L^-1 y, alpha = L^-T z, quad = z^T z for `count` outputs (slab indices outs[]): one cluster per output, one launch.
+int solve_alpha(const double* A_slab, int64_t n_pad, const double* Dinv_slab, const double* Y, double* z, double* alpha,
+                double* scal, const int* info, const int* outs, int count, cudaStream_t st) {
+    if (count < 1 || count > MAXG) return 1;
     const int T = (int)(n_pad / NB);
     int C = 1;
     while (C * 2 <= g_max_cluster && C * 4 <= T) C *= 2;   // at least two blocks of the vector per CTA
     const int nown = (T + C - 1) / C;
     const size_t smem = (size_t)(nown * NB + C * NB + NB + 4 * NB + 16) * sizeof(double);
     if (smem > 200 * 1024) return 2;
+    SolveParams sp{};
+    sp.A = A_slab; sp.Dinv = Dinv_slab; sp.Y = Y; sp.z = z; sp.alpha = alpha; sp.scal = scal; sp.info = info;
+    sp.n_pad = n_pad; sp.T = T;
+    for (int i = 0; i < count; i++) sp.outs[i] = outs[i];
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(C);
+    cfg.gridDim = dim3(C * count);
     cfg.blockDim = dim3(SOLVE_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -248,7 +274,7 @@ int solve_alpha(const double* A, int64_t n_pad, const double* Dinv, const double
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_alpha_kernel, A, n_pad, T, Dinv, y, z, alpha, quad, info);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_alpha_kernel, sp);
     return e == cudaSuccess ? 0 : 1;
 }
 
