@@ -98,7 +98,8 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out);
 int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params);
 
 /* accumulated device time per phase in ms since the last call with reset != 0:
- * out[0..7] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches */
+ * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),
+ *              predict host wall up to the last kernel's completion, predict result copy-out host wall */
 int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset);
 
 /* NCCL plumbing (no reference equivalent: the reference is single-device, multioutputgp_gpu.hpp:183). */

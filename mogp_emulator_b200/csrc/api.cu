@@ -1,6 +1,7 @@
 // C ABI of libmogp_b200 (see include/mogp_b200.h): handle management, the fit / predict orchestration
 // (one GP per stream for the factorisations, one batched launch per phase for predict) and getters.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -74,7 +75,7 @@ static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * 
 
 using namespace mogp;
 
-enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_COUNT };
+enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H, T_COUNT };
 
 struct mogp_handle {
     int device = 0, n_sms = 148;
@@ -543,8 +544,10 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
     for (int o = 0; o < h->E; o++)
         if (status) status[o] = h->fitted[o] ? MOGP_OK : MOGP_ERR_NOT_FIT;
     if (m == 0) return MOGP_OK;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = predict_device(h, Xs, m, want_var, include_nugget);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     if ((rc = grow(&h->h_res, &h->h_res_cap, sizeof(double) * (size_t)h->E * 2 * m, -1))) return rc;
     API_CUDA(cudaMemcpyAsync(h->h_res, h->res, sizeof(double) * (size_t)h->E * 2 * m, cudaMemcpyDeviceToHost, h->main));
     API_CUDA(cudaStreamSynchronize(h->main));
@@ -552,6 +555,9 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
         memcpy(mean + (size_t)o * m, h->h_res + (size_t)o * 2 * m, sizeof(double) * m);
         if (want_var) memcpy(var + (size_t)o * m, h->h_res + (size_t)o * 2 * m + m, sizeof(double) * m);
     }
+    const auto t2 = std::chrono::steady_clock::now();
+    h->timings[T_PRED_HOST] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    h->timings[T_PRED_D2H] += std::chrono::duration<double, std::milli>(t2 - t1).count();
     return MOGP_OK;
 }
 

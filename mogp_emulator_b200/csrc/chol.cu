@@ -42,11 +42,52 @@ struct Potf2Smem {
     int fail;
 };
 
+// (a1) of potf2_inv_block: Cholesky of the 16x16 diagonal sub-block at (j0, j0) by ONE warp.  Lane r (mod 16) owns
+// row j0+r in registers; pivots and multipliers travel by shuffle, so the 16-step dependency chain has no barrier.
+// Writes L11 back to sm.S and sm.Lr, the reciprocal pivots to sm.rd, or sets sm.fail (1-based failing column).
+__device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
+    const int r = lane & 15;
+    double a[SB];
+#pragma unroll
+    for (int jj = 0; jj < SB; jj++) a[jj] = (jj <= r) ? sm.S[(j0 + r) * PS + j0 + jj] : 0.0;
+    int fail = 0;
+#pragma unroll
+    for (int j = 0; j < SB; j++) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        // also catches NaN (LAPACK: ajj <= 0 or isnan); warp-uniform.  No early exit: the loop stays fully
+        // unrolled (register-resident a[]); what follows a failed pivot is never stored.
+        if (fail == 0 && !(d > 0.0)) fail = j0 + j + 1;
+        const double pv = sqrt(d);
+        const double ri = 1.0 / pv;
+        a[j] = (r == j) ? pv : a[j] * ri;   // LAPACK scales the column by the reciprocal pivot (entries above the diagonal are 0)
+        if (lane == 0) sm.rd[j0 + j] = ri;
+#pragma unroll
+        for (int c = j + 1; c < SB; c++) {
+            const double l = __shfl_sync(0xffffffffu, a[j], c);
+            // the entry that becomes a pivot is updated as a - round(l*l) (two roundings, the dot-then-subtract
+            // form of LAPACK's unblocked kernel) so that exactly duplicated rows fail the un-jittered
+            // factorisation the same way the CPU reference does.
+            const double two = __dsub_rn(a[c], __dmul_rn(a[j], l));
+            const double one = fma(-a[j], l, a[c]);
+            a[c] = (r == c) ? two : ((r > c) ? one : a[c]);
+        }
+    }
+    if (fail) {
+        if (lane == 0) sm.fail = fail;
+    } else if (lane < SB) {
+#pragma unroll
+        for (int jj = 0; jj < SB; jj++) {
+            if (jj <= r) sm.S[(j0 + r) * PS + j0 + jj] = a[jj];
+            sm.Lr[r * (SB + 1) + jj] = a[jj];
+        }
+    }
+}
+
 // On entry sm.S holds the lower triangle of the block (upper part zero).  On success (returns 0) sm.S holds
 // inv(L) (lower), Lout (global, row stride ld) has received L with a zero upper part, and *logdet_add is
 // 2*sum(log L_ii) on thread 0.  On failure returns the 1-based index of the failing pivot (LAPACK info).
-// BAR_ALL / BAR_ROW: named barrier ids for all NTHR threads / the first 128 threads.
-template <int NTHR, int BAR_ALL, int BAR_ROW>
+// BAR_ALL: named barrier id for the NTHR participating threads.
+template <int NTHR, int BAR_ALL>
 __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* __restrict__ Lout, int64_t ld,
                                                double* logdet_add) {
     constexpr int NG = NTHR / NB;   // thread groups of 128
@@ -57,61 +98,61 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
     // ---- factorisation: 8 sub-blocks of 16 columns -------------------------------------------
     for (int s = 0; s < NB / SB; s++) {
         const int j0 = s * SB;
-        if (tid < NB) {
-            // one thread per row; rows below j0 hold their 16 panel entries in registers
-            const int r = tid;
-            const bool active = r >= j0;
-            double a[SB];
-#pragma unroll
-            for (int jj = 0; jj < SB; jj++) a[jj] = active ? sm.S[r * PS + j0 + jj] : 0.0;
-#pragma unroll
-            for (int j = 0; j < SB; j++) {
-                if (r == j0 + j) {
-                    const double d = a[j];
-                    if (!(d > 0.0)) sm.fail = j0 + j + 1;  // also catches NaN (LAPACK: ajj <= 0 or isnan)
-                    const double p = sqrt(d);
-                    const double ri = 1.0 / p;
-                    a[j] = p;
-                    sm.ri = ri;
-                    sm.rd[r] = ri;
-                }
-                named_bar_sync(BAR_ROW, NB);
-                if (sm.fail) break;
-                const double ri = sm.ri;
-                if (r > j0 + j) a[j] *= ri;  // LAPACK scales the column by the reciprocal pivot
-                if (r >= j0 + j && r < j0 + SB) sm.Lr[(r - j0) * (SB + 1) + j] = a[j];
-                named_bar_sync(BAR_ROW, NB);
-                if (r > j0 + j) {
-#pragma unroll
-                    for (int c = j + 1; c < SB; c++) {
-                        const double l = sm.Lr[c * (SB + 1) + j];
-                        // the entry that becomes a pivot is updated as a - round(l*l) (two roundings, the
-                        // dot-then-subtract form of LAPACK's unblocked kernel) so that exactly duplicated
-                        // rows fail the un-jittered factorisation the same way the CPU reference does.
-                        if (r == j0 + c) a[c] = __dsub_rn(a[c], __dmul_rn(a[j], l));
-                        else a[c] = fma(-a[j], l, a[c]);
-                    }
-                }
-            }
-            if (active && !sm.fail) {
-#pragma unroll
-                for (int jj = 0; jj < SB; jj++) sm.S[r * PS + j0 + jj] = (j0 + jj <= r) ? a[jj] : 0.0;
-            }
-        }
+        // (a1) the 16x16 diagonal sub-block inside one warp: lane r (mod 16) owns row j0+r in registers, pivots and
+        //      multipliers travel by shuffle -- no barrier on the 16-step dependency chain.
+        if (tid < 32) potf2_diag16(sm, j0, tid);
         named_bar_sync(BAR_ALL, NTHR);
         if (sm.fail) break;
-        // trailing update inside the diagonal block: S[r][c] -= sum_kk S[r][j0+kk] * S[c][j0+kk]
+        // (a2) the rows below it: one thread per row, no cross-thread dependency (needs only L11 and the pivots)
+        if (tid < NB - j0 - SB) {
+            const int r = j0 + SB + tid;
+            double a[SB];
+#pragma unroll
+            for (int jj = 0; jj < SB; jj++) a[jj] = sm.S[r * PS + j0 + jj];
+#pragma unroll
+            for (int j = 0; j < SB; j++) {
+                a[j] *= sm.rd[j0 + j];
+#pragma unroll
+                for (int c = j + 1; c < SB; c++) a[c] = fma(-a[j], sm.Lr[c * (SB + 1) + j], a[c]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < SB; jj++) sm.S[r * PS + j0 + jj] = a[jj];
+        }
+        named_bar_sync(BAR_ALL, NTHR);
+        // (b) trailing update inside the diagonal block: S[r][c] -= sum_kk S[r][j0+kk] * S[c][j0+kk], c <= r.
+        //     Rows are folded in pairs (short + long) so every thread gets the same number of columns; four
+        //     independent dot products at a time hide the FP64 pipeline latency.
         {
-            const int r = tid & 127, q = tid >> 7;
-            if (r >= j0 + SB) {
-                double a[SB];
+            constexpr int NQ = NTHR / 64;            // column groups
+            const int t = tid & 63, q = tid >> 6;
+            const int nrow = NB - j0 - SB;           // rows below the panel (even)
+            if (t < nrow / 2) {
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    const int r = half ? (NB - 1 - t) : (j0 + SB + t);
+                    double a[SB];
 #pragma unroll
-                for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
-                for (int c = j0 + SB + q; c <= r; c += NG) {
-                    double dot = 0.0;
+                    for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
+                    int c = j0 + SB + q;
+                    for (; c + 3 * NQ <= r; c += 4 * NQ) {
+                        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                        const double* s0 = sm.S + c * PS + j0;
 #pragma unroll
-                    for (int kk = 0; kk < SB; kk++) dot = fma(a[kk], sm.S[c * PS + j0 + kk], dot);
-                    sm.S[r * PS + c] -= dot;
+                        for (int kk = 0; kk < SB; kk++) {
+                            d0 = fma(a[kk], s0[kk], d0);
+                            d1 = fma(a[kk], s0[NQ * PS + kk], d1);
+                            d2 = fma(a[kk], s0[2 * NQ * PS + kk], d2);
+                            d3 = fma(a[kk], s0[3 * NQ * PS + kk], d3);
+                        }
+                        double* dst = sm.S + r * PS + c;
+                        dst[0] -= d0; dst[NQ] -= d1; dst[2 * NQ] -= d2; dst[3 * NQ] -= d3;
+                    }
+                    for (; c <= r; c += NQ) {
+                        double dot = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < SB; kk++) dot = fma(a[kk], sm.S[c * PS + j0 + kk], dot);
+                        sm.S[r * PS + c] -= dot;
+                    }
                 }
             }
         }
@@ -167,6 +208,7 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
             double x[CW];
 #pragma unroll
             for (int cc = 0; cc < CW; cc++) x[cc] = 0.0;
+#pragma unroll 4
             for (int q = R0; q <= r; q++) {
                 const double a = sm.S[r * PS + q];
                 const double* bq = sm.S + q * PS + C0 + CW * cq;
@@ -299,7 +341,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     constexpr int SKIP = 1 << 30;
     if (warp >= Cfg::NCW) {
         // =========================== ticket + TMA producer ===========================
-        reg_dealloc<40>();
+        reg_dealloc<56>();
         if (warp == Cfg::NCW && lane == 0) {
             prefetch_tmap(&tmL);
             prefetch_tmap(&tmW);
@@ -393,7 +435,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     }
 
     // =========================== DMMA consumers ===========================
-    reg_alloc<232>();
+    reg_alloc<224>();
     const int ctid = threadIdx.x;   // 0..255
     const int wm = warp >> 1, wn = warp & 1;
     const int g = lane >> 2, t4 = lane & 3;
@@ -425,7 +467,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                     sm.S[r * PS + c] = (c <= r) ? __ldcg(Ablk + (int64_t)r * p.n_pad + c) : 0.0;
                 }
                 double ld_add = 0.0;
-                const int fail = potf2_inv_block<Cfg::NCW * 32, 2, 3>(sm, ctid, Ablk, p.n_pad, &ld_add);
+                const int fail = potf2_inv_block<Cfg::NCW * 32, 2>(sm, ctid, Ablk, p.n_pad, &ld_add);
                 if (fail) {
                     if (ctid == 0) p.info[o] = j * NB + fail;
                 } else {

@@ -111,7 +111,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
     constexpr int NCH = NB / KC;  // chunks per 128-wide K block
     if (warp >= Cfg::NCW) {
         // =========================== ticket + TMA producer ===========================
-        reg_dealloc<40>();
+        reg_dealloc<56>();
         if (warp == Cfg::NCW && lane == 0) {
             prefetch_tmap(&tmL);
             prefetch_tmap(&tmD);
@@ -189,7 +189,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
     }
 
     // =========================== DMMA consumers ===========================
-    reg_alloc<232>();
+    reg_alloc<224>();
     const int wm = warp >> 1, wn = warp & 1;
     const int g = lane >> 2, t4 = lane & 3;
     const int arow0 = wm * 32, bcol0 = wn * 8 * NT;

@@ -226,9 +226,10 @@ class Handle(object):
         return out
 
     def timings(self, reset=False):
-        out = np.zeros(9)
-        check(_lib.mogp_timings(self._h, dptr(out), 9, int(reset)))
-        keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms"]
+        out = np.zeros(11)
+        check(_lib.mogp_timings(self._h, dptr(out), 11, int(reset)))
+        keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms",
+                "predict_device_wall_ms", "predict_d2h_wall_ms"]
         return dict(zip(keys, out.tolist()))
 
 
