@@ -81,6 +81,11 @@ int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out);
 int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, int32_t include_nugget,
                  double* mean, double* var, int32_t* status);
 
+/* replaces DenseGP_GPU::predict_deriv (densegp_gpu.hpp:411-448) / MultiOutputGP_GPU::predict_deriv
+ * (multioutputgp_gpu.hpp:230-257): derivative of the posterior mean with respect to the test inputs.
+ * deriv: (n_out, m, d) caller-allocated; rows of unfit outputs are NaN.  At most 64 input dimensions. */
+int mogp_predict_deriv(mogp_handle* h, const double* Xs, int64_t m, double* deriv, int32_t* status);
+
 /* Sharded multi-output predict: every rank predicts its own outputs, then ONE ncclAllGather of the
  * packed per-rank [e_pad][2][m] block delivers all ranks' means and variances to every rank.
  * mean_all, var_all: (world * e_pad, m); status_all: (world * e_pad) (MOGP_ERR_ARG marks padding rows). */

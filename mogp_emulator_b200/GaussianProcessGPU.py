@@ -258,9 +258,10 @@ class GaussianProcessGPU(object):
         raise GPUUnavailableError("The Hessian calculation is not currently implemented in the GPU version of MOGP.")
 
     # -- prediction -------------------------------------------------------------------------------------
-    def predict(self, testing, unc=True, deriv=False, include_nugget=True):
-        """Posterior mean / variance at ``testing`` (GaussianProcess.predict, GaussianProcess.py:818-927).
-        Predictive derivatives are not built yet: ``deriv=True`` raises GPUUnavailableError."""
+    def predict(self, testing, unc=True, deriv=True, include_nugget=True):
+        """Posterior mean / variance at ``testing`` (GaussianProcess.predict, GaussianProcess.py:818-927) and, with
+        ``deriv=True`` (the reference GPU class's default, GaussianProcessGPU.py:582), the derivative of the mean
+        with respect to the test inputs, shape ``(m, D)`` (DenseGP_GPU::predict_deriv, densegp_gpu.hpp:411-448)."""
         if not self._theta.data_has_been_set():
             raise ValueError("hyperparameters have not been fit for this Gaussian Process")
         testing = libmogp.as_f64(testing)
@@ -270,10 +271,9 @@ class GaussianProcessGPU(object):
             testing = np.reshape(testing, (1, len(testing)))
         assert testing.ndim == 2
         assert testing.shape[1] == self.D
-        if deriv:
-            raise GPUUnavailableError("predictive derivatives are not implemented in this build")
         mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
-        return PredictResult(mean=mean[0], unc=(var[0] if unc else None), deriv=None)
+        dmean = self._handle.predict_deriv(testing)[0][0] if deriv else None
+        return PredictResult(mean=mean[0], unc=(var[0] if unc else None), deriv=dmean)
 
     def __call__(self, testing):
         return self.predict(testing, unc=False, deriv=False)[0]

@@ -220,7 +220,10 @@ class MultiOutputGP_GPU(object):
     _remote_fit = {}
 
     # -- prediction (MultiOutputGP_GPU.py:185-297; CPU semantics MultiOutputGP.py:182-319) ---------------
-    def predict(self, testing, unc=True, deriv=False, include_nugget=True, allow_not_fit=False, processes=None):
+    def predict(self, testing, unc=True, deriv=True, include_nugget=True, allow_not_fit=False, processes=None):
+        """Means / variances ``(n_emulators, m)`` and, with ``deriv=True`` (the reference's default,
+        MultiOutputGP_GPU.py:185), mean derivatives ``(n_emulators, m, D)``.  Sharded (``comm=``) emulators gather
+        means and variances only: pass ``deriv=False`` there."""
         testing = np.array(testing, dtype=np.float64)
         if self.D == 1 and testing.ndim == 1:
             testing = np.reshape(testing, (-1, 1))
@@ -228,14 +231,15 @@ class MultiOutputGP_GPU(object):
             testing = np.reshape(testing, (1, len(testing)))
         assert testing.ndim == 2, "testing must be a 2D array"
         assert testing.shape[1] == self.D, "second dimension of testing must be the same as the number of input parameters"
-        if deriv:
-            raise GPUUnavailableError("predictive derivatives are not implemented in this build")
         E, m = self.n_emulators, testing.shape[0]
         if self._comm is None:
             if not allow_not_fit and len(self.get_indices_not_fit()) > 0:
                 raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
             mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
-            return PredictResult(mean=mean, unc=var if unc else None, deriv=None)
+            dmean = self._handle.predict_deriv(testing)[0] if deriv else None
+            return PredictResult(mean=mean, unc=var if unc else None, deriv=dmean)
+        if deriv:
+            raise GPUUnavailableError("predictive derivatives are not gathered across ranks: pass deriv=False")
         # sharded: local predict + the one all-gather of the path
         if self._handle is None:
             raise RuntimeError("this rank holds no outputs: use at most n_emulators ranks")

@@ -561,6 +561,51 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
     return MOGP_OK;
 }
 
+int mogp_predict_deriv(mogp_handle* h, const double* Xs, int64_t m, double* deriv, int32_t* status) {
+    if (!h || (!Xs && m > 0) || m < 0 || !deriv) {
+        set_error("mogp_predict_deriv: bad arguments");
+        return MOGP_ERR_ARG;
+    }
+    const int d = h->d;
+    if (d > kderiv_max_dims()) {
+        set_error("mogp_predict_deriv: at most %d input dimensions are supported", kderiv_max_dims());
+        return MOGP_ERR_ARG;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    std::vector<int> fit_idx;
+    const double qnan = std::numeric_limits<double>::quiet_NaN();
+    for (int o = 0; o < h->E; o++) {
+        if (status) status[o] = h->fitted[o] ? MOGP_OK : MOGP_ERR_NOT_FIT;
+        if (h->fitted[o]) fit_idx.push_back(o);
+        else std::fill(deriv + (size_t)o * m * d, deriv + (size_t)(o + 1) * m * d, qnan);
+    }
+    if (m == 0 || fit_idx.empty()) return MOGP_OK;
+    int rc;
+    const int64_t xs_stride = round_up(m, 128);
+    if ((rc = grow(&h->XsT, &h->XsT_cap, sizeof(double) * d * xs_stride, h->device))) return rc;
+    if ((rc = grow(&h->h_XsT, &h->h_XsT_cap, sizeof(double) * d * xs_stride, -1))) return rc;
+    memset(h->h_XsT, 0, sizeof(double) * d * xs_stride);
+    for (int64_t i = 0; i < m; i++)
+        for (int k = 0; k < d; k++) h->h_XsT[(size_t)k * xs_stride + i] = Xs[i * d + k];
+    API_CUDA(cudaMemcpyAsync(h->XsT, h->h_XsT, sizeof(double) * d * xs_stride, cudaMemcpyHostToDevice, h->main));
+    for (size_t g0 = 0; g0 < fit_idx.size(); g0 += MAXG) {
+        const int cnt = (int)std::min<size_t>(MAXG, fit_idx.size() - g0);
+        const size_t bytes = sizeof(double) * (size_t)cnt * m * d;
+        if ((rc = grow(&h->W, &h->W_cap, bytes, h->device))) return rc;   // the predict workspace doubles as the result buffer
+        if (kmat_deriv(h->kernel, h->XsT, xs_stride, h->XT, h->n, h->n_pad, m, d, fit_idx.data() + g0, cnt, h->hyper,
+                       h->alpha, h->W, h->main)) {
+            set_error("deriv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MOGP_ERR_CUDA;
+        }
+        h->timings[T_NLAUNCH] += 1;
+        API_CUDA(cudaStreamSynchronize(h->main));
+        for (int k = 0; k < cnt; k++)
+            API_CUDA(cudaMemcpy(deriv + (size_t)fit_idx[g0 + k] * m * d, h->W + (size_t)k * m * d, sizeof(double) * m * d,
+                                cudaMemcpyDeviceToHost));
+    }
+    return MOGP_OK;
+}
+
 int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
     if (!h || idx < 0 || idx >= h->E || !out) return MOGP_ERR_ARG;
     if (!h->fitted[idx]) {

@@ -37,6 +37,11 @@ int kmat_cross(const CUtensorMap& tmXsT, const CUtensorMap& tmXT, int kernel, in
 int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int64_t m_pad, int64_t m, double* mean,
                 int64_t mean_stride, cudaStream_t st);
 
+int kderiv_max_dims();
+// d mean / d x* of `count` outputs at m test points: out[k][c][q], k-th listed output (XsT: [d][xs_stride] on the device)
+int kmat_deriv(int kernel, const double* XsT, int64_t xs_stride, const double* XT, int64_t n, int64_t n_pad, int64_t m,
+               int d, const int* outs, int count, const double* hyper, const double* alpha, double* out, cudaStream_t st);
+
 // ---- solve.cu ----
 int solve_init();
 int solve_alpha(const double* A_slab, int64_t n_pad, const double* Dinv_slab, const double* Y, double* z, double* alpha,

@@ -217,4 +217,111 @@ int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// Predictive derivatives d mean / d x*  (replaces cov_deriv_x_batch_gpu + cublasDgemv, reference
+// mogp_gpu/src/kernel.cu:69-100, 264-302 and densegp_gpu.hpp:411-448):
+//     dmu_c/dx*_q = sum_i alpha_i * sigma2 * k'(r2_ci) * 2 w_q (x*_cq - x_iq),   k' = dk/dr2
+// One thread per test point streams the training points (tiles of 32 staged in shared memory, broadcast reads)
+// and keeps 16 derivative components in registers; more than 16 input dimensions take further passes.  No
+// (m x n x d) derivative tensor is materialised (the reference allocates exactly that in work_mat_d).
+// ------------------------------------------------------------------------------------------
+constexpr int KD_TB = 32;    // training points per staged tile
+constexpr int KD_Q = 16;     // derivative components per pass
+constexpr int KD_MAXD = 64;
+
+struct DerivParams {
+    const double* XsT;     // [d][xs_stride] test points, transposed
+    int64_t xs_stride;
+    const double* XT;      // [d][n_pad]
+    const double* alpha;   // [E][n_pad]
+    const double* hyper;   // [E][d+2]
+    double* out;           // [count][m][d]
+    int64_t n, n_pad, m;
+    int d;
+    int outs[MAXG];
+};
+
+template <int KT>
+__global__ void __launch_bounds__(128) kderiv_kernel(const DerivParams p) {
+    extern __shared__ __align__(16) double kd_smem[];
+    const int d = p.d;
+    double* xs = kd_smem;              // [d][128]
+    double* xt = xs + d * 128;         // [d][KD_TB]
+    double* al = xt + d * KD_TB;       // [KD_TB]
+    double* w = al + KD_TB;            // [d]
+    const int tid = threadIdx.x;
+    const int o = p.outs[blockIdx.y];
+    const int64_t c = (int64_t)blockIdx.x * 128 + tid;
+    const double* hyp = p.hyper + (int64_t)o * (d + 2);
+    for (int i = tid; i < d; i += 128) w[i] = hyp[i];
+    for (int dd = 0; dd < d; dd++) xs[dd * 128 + tid] = (c < p.m) ? p.XsT[(int64_t)dd * p.xs_stride + c] : 0.0;
+    const double sigma2 = hyp[d];
+    __syncthreads();
+    for (int d0 = 0; d0 < d; d0 += KD_Q) {
+        double g[KD_Q];
+#pragma unroll
+        for (int q = 0; q < KD_Q; q++) g[q] = 0.0;
+        for (int64_t i0 = 0; i0 < p.n; i0 += KD_TB) {
+            __syncthreads();
+            for (int idx = tid; idx < d * KD_TB; idx += 128) {
+                const int dd = idx / KD_TB, ii = idx - dd * KD_TB;
+                xt[idx] = (i0 + ii < p.n) ? p.XT[(int64_t)dd * p.n_pad + i0 + ii] : 0.0;
+            }
+            if (tid < KD_TB) al[tid] = (i0 + tid < p.n) ? p.alpha[(int64_t)o * p.n_pad + i0 + tid] : 0.0;
+            __syncthreads();
+#pragma unroll 2
+            for (int ii = 0; ii < KD_TB; ii++) {
+                double r2 = 0.0;
+                for (int dd = 0; dd < d; dd++) {
+                    const double df = xs[dd * 128 + tid] - xt[dd * KD_TB + ii];
+                    r2 = fma(w[dd], df * df, r2);
+                }
+                double dk;
+                if (KT == MOGP_KERNEL_SQEXP) {
+                    dk = -0.5 * exp(-0.5 * r2);
+                } else {
+                    const double sq = sqrt(5.0 * r2);
+                    dk = -(5.0 / 6.0) * (1.0 + sq) * exp(-sq);
+                }
+                const double kp = sigma2 * dk * al[ii];   // al is zero past n
+#pragma unroll
+                for (int q = 0; q < KD_Q; q++)
+                    if (d0 + q < d) g[q] = fma(kp, xs[(d0 + q) * 128 + tid] - xt[(d0 + q) * KD_TB + ii], g[q]);
+            }
+        }
+        if (c < p.m) {
+            double* orow = p.out + ((int64_t)blockIdx.y * p.m + c) * d;
+#pragma unroll
+            for (int q = 0; q < KD_Q; q++)
+                if (d0 + q < d) orow[d0 + q] = 2.0 * w[d0 + q] * g[q];
+        }
+    }
+}
+
+int kderiv_max_dims() { return KD_MAXD; }
+
+int kmat_deriv(int kernel, const double* XsT, int64_t xs_stride, const double* XT, int64_t n, int64_t n_pad, int64_t m,
+               int d, const int* outs, int count, const double* hyper, const double* alpha, double* out, cudaStream_t st) {
+    if (count < 1 || count > MAXG || d > KD_MAXD) return 1;
+    static bool attr_done = false;
+    const size_t smem = sizeof(double) * ((size_t)d * 128 + (size_t)d * KD_TB + KD_TB + d);
+    if (!attr_done) {
+        const int maxs = (int)(sizeof(double) * ((size_t)KD_MAXD * 128 + KD_MAXD * KD_TB + KD_TB + KD_MAXD));
+        if (cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess ||
+            cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess)
+            return 1;
+        attr_done = true;
+    }
+    DerivParams p{};
+    p.XsT = XsT; p.xs_stride = xs_stride; p.XT = XT; p.alpha = alpha; p.hyper = hyper; p.out = out;
+    p.n = n; p.n_pad = n_pad; p.m = m; p.d = d;
+    for (int i = 0; i < count; i++) p.outs[i] = outs[i];
+    dim3 grid((unsigned)((m + 127) / 128), (unsigned)count);
+    if (kernel == MOGP_KERNEL_SQEXP)
+        kderiv_kernel<MOGP_KERNEL_SQEXP><<<grid, 128, smem, st>>>(p);
+    else
+        kderiv_kernel<MOGP_KERNEL_MATERN52><<<grid, 128, smem, st>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 }  // namespace mogp

@@ -50,6 +50,7 @@ SIGNATURES = {
     "mogp_is_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_int_p]),
     "mogp_predict": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                     _c_double_p, _c_double_p, _c_int_p]),
+    "mogp_predict_deriv": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_int_p]),
     "mogp_predict_allgather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_double_p, ctypes.c_int64,
                                               ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, _c_int_p]),
     "mogp_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p]),
@@ -202,6 +203,14 @@ class Handle(object):
         check(_lib.mogp_predict(self._h, dptr(testing), m, int(bool(want_var)), int(bool(include_nugget)), dptr(mean),
                                 dptr(var) if want_var else None, iptr(status)), "mogp_predict")
         return mean, var, status
+
+    def predict_deriv(self, testing):
+        testing = as_f64(testing)
+        m = testing.shape[0]
+        deriv = np.empty((self.n_out, m, self.d))
+        status = np.zeros(self.n_out, dtype=np.int32)
+        check(_lib.mogp_predict_deriv(self._h, dptr(testing), m, dptr(deriv), iptr(status)), "mogp_predict_deriv")
+        return deriv, status
 
     def predict_allgather(self, comm, testing, include_nugget, e_pad):
         testing = as_f64(testing)

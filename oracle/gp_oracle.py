@@ -392,6 +392,22 @@ class OracleGP(object):
             var = np.maximum(sigma_2 - np.sum(Ktest * Kinv_Ktest, axis=0), 0.0)
         return mu, var
 
+    def predict_deriv(self, testing):
+        """d mean / d x* at the test points, shape (m, D).  The CPU reference no longer provides this
+        (GaussianProcess.py:922-926 warns and returns None); the definition is the reference GPU path's
+        (mogp_gpu/src/densegp_gpu.hpp:411-448 with kernel.cu:69-100 / 264-302): sum_i alpha_i dk(x*, x_i)/dx*, where
+        dk/dx*_q = sigma2 * dK/dr2 * 2 exp(theta_q) (x*_q - x_iq)."""
+        testing = np.atleast_2d(np.asarray(testing, dtype=np.float64))
+        w = np.exp(self.theta[:self.D])
+        cov = np.exp(self.theta[self.D])
+        out = np.empty((testing.shape[0], self.D))
+        for c, x in enumerate(testing):                      # small cases only
+            diff = x[np.newaxis, :] - self.inputs            # (n, D)
+            r2 = np.sum(w * diff ** 2, axis=1)
+            coef = cov * calc_dKdr2(r2, self.kernel) * self.Kinv_t
+            out[c] = 2.0 * w * np.dot(coef, diff)
+        return out
+
 
 # ------------------------------------------------------------------------------------------------
 # multi-output fan-out

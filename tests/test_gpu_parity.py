@@ -237,3 +237,36 @@ def test_fit_GP_MAP_matches_cpu_optimiser(mogp):
         r = orc.OracleGP(X, Y[i], nugget=1e-5)
         rr = minimize(r.logposterior, np.zeros(3), method="L-BFGS-B", jac=r.logpost_deriv)
         assert_allclose(mo.logposterior(i), rr["fun"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("kernel,n,d,m", [
+    ("SquaredExponential", 200, 3, 77),
+    ("Matern52", 333, 5, 130),
+    ("SquaredExponential", 150, 20, 40),     # more than one 16-component pass
+])
+def test_predict_deriv_against_oracle_and_finite_differences(mogp, kernel, n, d, m):
+    """d mean / d x*: the GPU kernel vs the oracle's restatement of the reference GPU definition
+    (densegp_gpu.hpp:411-448) and vs central differences of the GPU's own posterior mean."""
+    X, Y, Xs = orc.make_workload(n, d, 2, m, seed=17 + d)
+    theta = np.append(np.linspace(0.5, 1.5, d), 0.2)
+    gp = mogp.GaussianProcessGPU(X, Y[0], kernel=kernel, nugget=1e-6)
+    gp.fit(theta)
+    res = gp.predict(Xs)                       # deriv=True is the reference GPU class's default
+    assert res.deriv.shape == (m, d)
+    ref = orc.OracleGP(X, Y[0], kernel=kernel, nugget=1e-6).fit(theta)
+    want = ref.predict_deriv(Xs)
+    assert_allclose(res.deriv, want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
+    h = 1e-5
+    for q in range(min(d, 3)):
+        e = np.zeros(d)
+        e[q] = h
+        fd = (gp.predict(Xs + e, unc=False, deriv=False).mean - gp.predict(Xs - e, unc=False, deriv=False).mean) / (2 * h)
+        assert_allclose(res.deriv[:, q], fd, rtol=2e-4, atol=2e-4 * np.abs(fd).max())
+    # multi-output: (E, m, D), NaN rows for an output that was never fit
+    mo = mogp.MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=1e-6)
+    mo.fit_emulator(1, theta)
+    r2 = mo.predict(Xs, allow_not_fit=True)
+    assert r2.deriv.shape == (2, m, d)
+    assert np.all(np.isnan(r2.deriv[0]))
+    ref1 = orc.OracleGP(X, Y[1], kernel=kernel, nugget=1e-6).fit(theta)
+    assert_allclose(r2.deriv[1], ref1.predict_deriv(Xs), rtol=1e-6, atol=1e-8 * np.abs(want).max())

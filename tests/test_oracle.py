@@ -174,3 +174,19 @@ def test_live_reference_if_present():
     assert_allclose(m, rm, rtol=1e-9, atol=1e-11)
     assert_allclose(v, rv, rtol=1e-6, atol=1e-10)
     assert_allclose(gp.logpost_deriv(theta), ref.logpost_deriv(theta), rtol=1e-7, atol=1e-7)
+
+
+def test_predict_deriv_vs_finite_differences():
+    """The oracle's mean-derivative restatement (reference GPU definition) against central differences of the
+    oracle's own posterior mean."""
+    for kernel in (orc.SQEXP, orc.MAT52):
+        X, Y, Xs = orc.make_workload(60, 3, 1, 9, seed=3)
+        theta = np.array([0.7, 1.1, 0.9, 0.3])
+        gp = orc.OracleGP(X, Y[0], kernel=kernel, nugget=1e-6).fit(theta)
+        got = gp.predict_deriv(Xs)
+        h = 1e-6
+        for q in range(3):
+            e = np.zeros(3)
+            e[q] = h
+            fd = (gp.predict(Xs + e, unc=False)[0] - gp.predict(Xs - e, unc=False)[0]) / (2 * h)
+            np.testing.assert_allclose(got[:, q], fd, rtol=1e-5, atol=1e-6)
