@@ -278,6 +278,12 @@ class GaussianProcessGPU(object):
     def __call__(self, testing):
         return self.predict(testing, unc=False, deriv=False)[0]
 
+    def close(self):
+        """Release the device object now (its buffers go back to the library's cache) instead of at garbage collection."""
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
     def __str__(self):
         return ("Gaussian Process with " + str(self.n) + " training examples and " + str(self.D) + " input variables")
 

@@ -262,6 +262,12 @@ class MultiOutputGP_GPU(object):
     def timings(self, reset=False):
         return self._handle.timings(reset) if self._handle is not None else {}
 
+    def close(self):
+        """Release the device object now (its buffers go back to the library's cache) instead of at garbage collection."""
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
     def __str__(self):
         return ("Multi-Output Gaussian Process with:\n" + str(self.n_emulators) + " emulators\n" +
                 str(self.n) + " training examples\n" + str(self.D) + " input variables")
