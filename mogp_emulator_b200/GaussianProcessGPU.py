@@ -225,6 +225,7 @@ class GaussianProcessGPU(object):
         if theta.shape != (self.n_params,):
             raise RuntimeError("bad shape for hyperparameters: expected %d values, got %d" % (self.n_params, theta.size))
         quad, logdet, nug, status = self._handle.fit(0, theta)
+        self.n_fit_calls = getattr(self, "n_fit_calls", 0) + 1
         if status[0] != libmogp.OK:
             self._theta.unset_data()
             self._logpost_data = None
@@ -252,6 +253,7 @@ class GaussianProcessGPU(object):
         if self._refit(theta):
             self.fit(theta)
         grad = self._handle.logpost_grad(0, self.n_params)
+        self.n_grad_calls = getattr(self, "n_grad_calls", 0) + 1
         return grad - self.priors.dlogpdtheta(self._theta)
 
     def logpost_hessian(self, theta):
