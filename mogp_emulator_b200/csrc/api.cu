@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -70,6 +71,27 @@ int make_2d_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols
 }
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+// MOGP_TRACE=1: host-side phase timings of the API calls on stderr
+static bool trace_on() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MOGP_TRACE");
+        on = (e && *e && *e != '0') ? 1 : 0;
+    }
+    return on == 1;
+}
+struct TraceClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char* what;
+    explicit TraceClock(const char* w) : what(w) {}
+    void mark(const char* label) {
+        if (!trace_on()) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mogp trace] %s: %s +%.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 }  // namespace mogp
 
@@ -155,6 +177,30 @@ int mogp_version(int32_t* major, int32_t* minor) {
 
 const char* mogp_last_error(void) { return g_err; }
 
+// cudaGetDeviceProperties costs 2-35 ms per call on this driver (it refreshes clocks / power state): ask the two
+// attributes we need instead, once per device and process.
+struct DevInfo {
+    int major = -1, sms = 0;
+};
+static const DevInfo& device_info(int device) {
+    static DevInfo cache[64];
+    DevInfo& d = cache[device & 63];
+    if (d.major < 0) {
+        int major = 0, sms = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) {
+            d.major = major;
+            d.sms = sms;
+        } else {
+            cudaGetLastError();
+            static DevInfo none;
+            none.major = 0;
+            return none;
+        }
+    }
+    return d;
+}
+
 int mogp_device_count(int32_t* count) {
     int c = 0;
     cudaError_t e = cudaGetDeviceCount(&c);
@@ -163,10 +209,8 @@ int mogp_device_count(int32_t* count) {
         c = 0;
     }
     int usable = 0;
-    for (int i = 0; i < c; i++) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) usable++;
-    }
+    for (int i = 0; i < c && i < 64; i++)
+        if (device_info(i).major == 10) usable++;
     if (count) *count = usable;
     return MOGP_OK;
 }
@@ -209,20 +253,24 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         set_error("mogp_create: CUDA device %d not available (%d visible)", device, ndev);
         return MOGP_ERR_CUDA;
     }
+    TraceClock tc("mogp_create");
     API_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    API_CUDA(cudaGetDeviceProperties(&prop, device));
+    tc.mark("cudaSetDevice");
+    const DevInfo& prop = device_info(device);
+    tc.mark("device attributes");
     if (prop.major != 10) {
-        set_error("mogp_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        set_error("mogp_create: device %d has compute capability major %d; this library contains sm_100a code only", device,
+                  prop.major);
         return MOGP_ERR_CUDA;
     }
     if (chol_init() || solve_init() || kmat_init() || predict_init() || grad_init()) {
         set_error("kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         return MOGP_ERR_CUDA;
     }
+    tc.mark("kernel attribute setup");
     mogp_handle* h = new mogp_handle();
     h->device = device;
-    h->n_sms = prop.multiProcessorCount;
+    h->n_sms = prop.sms;
     h->n = n;
     h->n_pad = round_up(n, NB);
     h->d = d;
@@ -260,6 +308,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     CREATE_CUDA(cudaEventCreate(&h->ev_b));
     CREATE_CUDA(cudaEventCreate(&h->ev_c));
     CREATE_CUDA(cudaEventCreate(&h->ev_d));
+    tc.mark("streams + events");
 #define CREATE_ALLOC(ptr, type, bytes, dev)                                                          \
     do {                                                                                             \
         ptr = (type*)pool_alloc((bytes), (dev));                                                     \
@@ -282,6 +331,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     CREATE_ALLOC(h->h_scal, double, sizeof(double) * n_out * 2, -1);
     CREATE_ALLOC(h->h_info, int, sizeof(int) * n_out, -1);
 #undef CREATE_ALLOC
+    tc.mark("allocations");
     {
         // transposed, zero-padded design matrix and zero-padded targets
         std::vector<double> xt((size_t)d * np, 0.0), yp((size_t)n_out * np, 0.0);
@@ -291,6 +341,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         CREATE_CUDA(cudaMemcpy(h->XT, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaMemcpy(h->Y, yp.data(), sizeof(double) * yp.size(), cudaMemcpyHostToDevice));
     }
+    tc.mark("H2D of X and Y");
     if (make_2d_tmap(&h->tmXT, h->XT, d, np, np, kmat_dbox(d), 128) ||
         chol_make_maps(&h->maps, h->A, h->Dinv, (int64_t)n_out * np, np)) {
         set_error("cuTensorMapEncodeTiled failed");
@@ -461,10 +512,17 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
     API_CUDA(cudaMemsetAsync(h->res, 0xFF, sizeof(double) * (size_t)h->E * 2 * m, h->main));  // all-ones == NaN
     if (fit_idx.empty() || m == 0) return MOGP_OK;
 
-    // group / chunk sizes under a workspace budget
-    size_t free_b = 0, total_b = 0;
-    API_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = (size_t)((free_b + h->W_cap + pool_cached_bytes()) * 0.6);
+    // group / chunk sizes under a workspace budget.  cudaMemGetInfo is a slow driver query (it can take tens of ms):
+    // when the workspace of the previous call already holds the whole job, reuse it without asking.
+    const size_t need_all = (size_t)(round_up(m, 128) + 128) * np * 8 * fit_idx.size();
+    size_t budget;
+    if (want_var && h->W_cap >= need_all && fit_idx.size() <= (size_t)MAXG) {
+        budget = h->W_cap;
+    } else {
+        size_t free_b = 0, total_b = 0;
+        API_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget = (size_t)((free_b + h->W_cap + pool_cached_bytes()) * 0.6);
+    }
     int64_t mc_max = m;
     while ((size_t)(round_up(mc_max, 128) + 128) * np * 8 > budget && mc_max > 128) mc_max = (mc_max + 1) / 2;
     for (int64_t m0 = 0; m0 < m; m0 += mc_max) {

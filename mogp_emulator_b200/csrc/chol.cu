@@ -95,15 +95,12 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
     if (tid == 0) sm.fail = 0;
     named_bar_sync(BAR_ALL, NTHR);
 
-    // ---- factorisation: 8 sub-blocks of 16 columns -------------------------------------------
-    for (int s = 0; s < NB / SB; s++) {
-        const int j0 = s * SB;
-        // (a1) the 16x16 diagonal sub-block inside one warp: lane r (mod 16) owns row j0+r in registers, pivots and
-        //      multipliers travel by shuffle -- no barrier on the 16-step dependency chain.
-        if (tid < 32) potf2_diag16(sm, j0, tid);
-        named_bar_sync(BAR_ALL, NTHR);
-        if (sm.fail) break;
-        // (a2) the rows below it: one thread per row, no cross-thread dependency (needs only L11 and the pivots)
+    // ---- factorisation: 8 panels of 16 columns ------------------------------------------------
+    // Per panel s (columns j0 = 16 s ..):  (a1) Cholesky of the 16x16 diagonal sub-block by warp 0 (potf2_diag16),
+    // (a2) the rows below it, one thread per row, (b) the trailing update of the block.  The 16-step dependency
+    // chain of (a1) is the long pole, so (b) is split: (b1) first the 16 columns the NEXT panel needs (all threads),
+    // then warp 0 runs (a1) of panel s+1 while warps 1.. run (b2), the rest of the trailing update.
+    auto rows_below = [&](int j0) {   // (a2): needs only L11 (sm.Lr) and the reciprocal pivots (sm.rd)
         if (tid < NB - j0 - SB) {
             const int r = j0 + SB + tid;
             double a[SB];
@@ -118,44 +115,70 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
 #pragma unroll
             for (int jj = 0; jj < SB; jj++) sm.S[r * PS + j0 + jj] = a[jj];
         }
-        named_bar_sync(BAR_ALL, NTHR);
-        // (b) trailing update inside the diagonal block: S[r][c] -= sum_kk S[r][j0+kk] * S[c][j0+kk], c <= r.
-        //     Rows are folded in pairs (short + long) so every thread gets the same number of columns; four
-        //     independent dot products at a time hide the FP64 pipeline latency.
+    };
+    // S[r][c] -= sum_kk S[r][j0+kk] * S[c][j0+kk] for c = c_lo + q, + nq, ... while c <= min(r, c_hi); 4 dots at a time
+    auto update_row = [&](int j0, int r, int c_lo, int c_hi, int q, int nq) {
+        double a[SB];
+#pragma unroll
+        for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
+        const int cmax = (r < c_hi) ? r : c_hi;
+        int c = c_lo + q;
+        for (; c + 3 * nq <= cmax; c += 4 * nq) {
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            const double* s0 = sm.S + c * PS + j0;
+            const double* s1 = s0 + nq * PS;
+            const double* s2 = s1 + nq * PS;
+            const double* s3 = s2 + nq * PS;
+#pragma unroll
+            for (int kk = 0; kk < SB; kk++) {
+                d0 = fma(a[kk], s0[kk], d0);
+                d1 = fma(a[kk], s1[kk], d1);
+                d2 = fma(a[kk], s2[kk], d2);
+                d3 = fma(a[kk], s3[kk], d3);
+            }
+            double* dst = sm.S + r * PS + c;
+            dst[0] -= d0; dst[nq] -= d1; dst[2 * nq] -= d2; dst[3 * nq] -= d3;
+        }
+        for (; c <= cmax; c += nq) {
+            double dot = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < SB; kk++) dot = fma(a[kk], sm.S[c * PS + j0 + kk], dot);
+            sm.S[r * PS + c] -= dot;
+        }
+    };
+
+    if (tid < 32) potf2_diag16(sm, 0, tid);
+    named_bar_sync(BAR_ALL, NTHR);
+    if (sm.fail) return sm.fail;
+    rows_below(0);
+    named_bar_sync(BAR_ALL, NTHR);
+    for (int s = 0; s + 1 < NB / SB; s++) {
+        const int j0 = s * SB;
+        const int nrow = NB - j0 - SB;   // rows below panel s
+        // (b1) columns of the next panel: thread (row, column parity)
         {
-            constexpr int NQ = NTHR / 64;            // column groups
-            const int t = tid & 63, q = tid >> 6;
-            const int nrow = NB - j0 - SB;           // rows below the panel (even)
-            if (t < nrow / 2) {
-#pragma unroll 1
-                for (int half = 0; half < 2; half++) {
-                    const int r = half ? (NB - 1 - t) : (j0 + SB + t);
-                    double a[SB];
-#pragma unroll
-                    for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
-                    int c = j0 + SB + q;
-                    for (; c + 3 * NQ <= r; c += 4 * NQ) {
-                        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-                        const double* s0 = sm.S + c * PS + j0;
-#pragma unroll
-                        for (int kk = 0; kk < SB; kk++) {
-                            d0 = fma(a[kk], s0[kk], d0);
-                            d1 = fma(a[kk], s0[NQ * PS + kk], d1);
-                            d2 = fma(a[kk], s0[2 * NQ * PS + kk], d2);
-                            d3 = fma(a[kk], s0[3 * NQ * PS + kk], d3);
-                        }
-                        double* dst = sm.S + r * PS + c;
-                        dst[0] -= d0; dst[NQ] -= d1; dst[2 * NQ] -= d2; dst[3 * NQ] -= d3;
-                    }
-                    for (; c <= r; c += NQ) {
-                        double dot = 0.0;
-#pragma unroll
-                        for (int kk = 0; kk < SB; kk++) dot = fma(a[kk], sm.S[c * PS + j0 + kk], dot);
-                        sm.S[r * PS + c] -= dot;
-                    }
-                }
+            constexpr int NQ1 = NTHR / NB;
+            const int t = tid & (NB - 1), q = tid >> 7;
+            if (t < nrow) update_row(j0, j0 + SB + t, j0 + SB, j0 + 2 * SB - 1, q, NQ1);
+        }
+        named_bar_sync(BAR_ALL, NTHR);
+        if (tid < 32) {
+            potf2_diag16(sm, j0 + SB, tid);                         // (a1) of panel s+1
+        } else {
+            // (b2) the remaining columns (>= j0+32); rows folded in pairs (short + long) so that every thread gets
+            // the same number of columns
+            constexpr int NT2 = NTHR - 32, PAIRS = 56, NQ2 = NT2 / PAIRS;
+            static_assert(NT2 % PAIRS == 0 && PAIRS >= (NB - 2 * SB) / 2, "update-warp mapping");
+            const int tt = tid - 32, t = tt % PAIRS, q = tt / PAIRS;
+            const int nrow2 = nrow - SB;
+            if (t < nrow2 / 2) {
+                update_row(j0, j0 + 2 * SB + t, j0 + 2 * SB, NB - 1, q, NQ2);
+                update_row(j0, NB - 1 - t, j0 + 2 * SB, NB - 1, q, NQ2);
             }
         }
+        named_bar_sync(BAR_ALL, NTHR);
+        if (sm.fail) return sm.fail;
+        rows_below(j0 + SB);                                        // (a2) of panel s+1
         named_bar_sync(BAR_ALL, NTHR);
     }
     if (sm.fail) return sm.fail;

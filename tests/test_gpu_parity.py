@@ -7,11 +7,16 @@ import os
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose
+from scipy.linalg import solve_triangular as _solve_triangular
 
 import gp_oracle as orc
 from golden import known_answers as ka
 
 pytestmark = pytest.mark.gpu
+
+def scipy_solve_triangular(L, B):
+    return _solve_triangular(L, B, lower=True)
+
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SINGLE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
@@ -270,3 +275,78 @@ def test_predict_deriv_against_oracle_and_finite_differences(mogp, kernel, n, d,
     assert np.all(np.isnan(r2.deriv[0]))
     ref1 = orc.OracleGP(X, Y[1], kernel=kernel, nugget=1e-6).fit(theta)
     assert_allclose(r2.deriv[1], ref1.predict_deriv(Xs), rtol=1e-6, atol=1e-8 * np.abs(want).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes, through size-independent properties (the oracle needs minutes there)
+# ---------------------------------------------------------------------------------------------------------------
+
+def _probe_factor(gp, X, y, nugget, rng):
+    """L L^T == K + nugget I and K alpha == y - nugget alpha, checked with random probe vectors on the host."""
+    L = gp.L
+    K = gp.get_K_matrix()
+    assert np.all(np.triu(L, 1) == 0.0)
+    V = rng.standard_normal((K.shape[0], 3))
+    lhs = L @ (L.T @ V)
+    rhs = K @ V + nugget * V
+    assert_allclose(lhs, rhs, rtol=1e-10, atol=1e-10 * np.abs(rhs).max())
+    alpha = gp.Kinv_t
+    assert_allclose(K @ alpha + nugget * alpha, y, rtol=1e-6, atol=1e-6 * np.abs(y).max())
+    return K, alpha
+
+
+def test_full_size_c3_shape_properties(mogp):
+    """n=4096, d=10 SqExp (one C2/C3 output): factor identity, normal equations, interpolation identity
+    mean(X) = y - nugget*alpha, 0 <= var, linearity of the mean in the targets and target-independence of the variance
+    across the outputs of a multi-output emulator."""
+    n, d, m, nug = 4096, 10, 1500, 1e-6
+    X, Y, Xs = orc.make_workload(n, d, 2, m, seed=2)
+    theta = np.append(np.full(d, 1.0), 0.0)
+    rng = np.random.default_rng(0)
+    gp = mogp.GaussianProcessGPU(X, Y[0], nugget=nug)
+    gp.fit(theta)
+    K, alpha = _probe_factor(gp, X, Y[0], nug, rng)
+    sub = rng.choice(n, 700, replace=False)
+    res = gp.predict(X[sub], deriv=False)
+    assert_allclose(res.mean, Y[0][sub] - nug * alpha[sub], rtol=1e-6, atol=1e-7)
+    assert np.all(res.unc >= 0.0) and np.all(res.unc < 1e-3)
+    # the log-determinant against the factor's diagonal, the quadratic form against alpha
+    want = 0.5 * (Y[0] @ alpha + 2.0 * np.log(np.diag(gp.L)).sum() + n * np.log(2.0 * np.pi)) - gp.priors.logp(gp.theta)
+    assert_allclose(gp.current_logpost, want, rtol=1e-10)
+    gp.close()
+    Y3 = np.vstack([Y[0], Y[1], 2.0 * Y[0] - 3.0 * Y[1]])
+    mo = mogp.MultiOutputGP_GPU(X, Y3, nugget=nug)
+    mo.fit(np.tile(theta, (3, 1)))
+    r = mo.predict(Xs, deriv=False)
+    scale = np.abs(r.mean).max()
+    assert_allclose(r.mean[2], 2.0 * r.mean[0] - 3.0 * r.mean[1], rtol=1e-7, atol=1e-7 * scale)
+    assert_allclose(r.unc[1], r.unc[0], rtol=1e-12, atol=0.0)
+    assert_allclose(r.unc[2], r.unc[0], rtol=1e-12, atol=0.0)
+    assert np.all(r.unc >= 0.0) and np.all(r.unc <= 1.0 + nug)
+    mo.close()
+
+
+def test_full_size_c4_shape_properties(mogp):
+    """n=16384, d=20 Matern-5/2, adaptive nugget (C4): well-conditioned data must pick exactly 0.0, two duplicated rows
+    must pick exactly 1e-6 * sigma^2 (linalg/cholesky.py:264-279); factor identity by probes; few right-hand sides."""
+    n, d, m = 16384, 20, 1000
+    X, Y, Xs = orc.make_workload(n, d, 1, m, seed=3)
+    theta = np.append(np.full(d, 1.0), 0.3)
+    rng = np.random.default_rng(1)
+    gp = mogp.GaussianProcessGPU(X, Y[0], kernel="Matern52", nugget="adaptive")
+    gp.fit(theta)
+    assert gp.nugget == 0.0
+    K, alpha = _probe_factor(gp, X, Y[0], 0.0, rng)
+    res = gp.predict(Xs, deriv=False)
+    kstar = np.exp(0.3) * orc.kernel_f(Xs[:64], X, theta[:d], orc.MAT52)          # (64, n) on the host
+    assert_allclose(res.mean[:64], kstar @ alpha, rtol=1e-9, atol=1e-9)
+    Linv_k = scipy_solve_triangular(gp.L, kstar.T)
+    assert_allclose(res.unc[:64], np.maximum(np.exp(0.3) - np.sum(Linv_k ** 2, axis=0), 0.0), rtol=1e-4, atol=1e-10)
+    gp.close()
+    Xd = X.copy()
+    Xd[1] = Xd[0]
+    gd = mogp.GaussianProcessGPU(Xd, Y[0], kernel="Matern52", nugget="adaptive")
+    gd.fit(theta)
+    assert gd.nugget == 1e-6 * np.exp(0.3)
+    assert np.all(gd.predict(Xs, deriv=False).unc >= 0.0)
+    gd.close()
