@@ -69,6 +69,11 @@ int mogp_trim(void);
 int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas, int32_t n_params,
              double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out);
 
+/* Same for an arbitrary list of distinct outputs idx[0..count) (thetas, and every result array, in list order): the
+ * batched objective evaluation of concurrent MAP fits of a multi-output emulator (fitting.py:189-217, 273-340). */
+int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* thetas, int32_t n_params,
+                  double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out);
+
 /* marks outputs not fit (MultiOutputGP_GPU.reset_fit_status, GaussianProcessGPU theta=None). idx<0: all */
 int mogp_reset(mogp_handle* h, int32_t idx);
 int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out);
@@ -101,6 +106,10 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out);
  * the last mogp_fit of output idx:  grad[i] = 0.5*(tr(K^-1 dK_i) - alpha^T dK_i alpha), i over
  * [corr(d), cov, (nugget)].  Prior terms are added by the caller. */
 int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params);
+
+/* Gradients of several fitted outputs at once: grad is (count, n_params) in list order.  L^-1 of all listed outputs comes
+ * from one dataflow launch. */
+int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, double* grad, int32_t n_params);
 
 /* accumulated device time per phase in ms since the last call with reset != 0:
  * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),

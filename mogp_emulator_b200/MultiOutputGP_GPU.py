@@ -142,6 +142,14 @@ class MultiOutputGP_GPU(object):
         """[lo, hi) -- the outputs held by this rank."""
         return self._lo, self._hi
 
+    def reset_emulator(self, index):
+        """Mark one emulator "not fit"."""
+        if self._lo <= index < self._hi:
+            self._handle.reset(index - self._lo)
+        self._fit[index] = False
+        self._thetas[index].unset_data()
+        self._logpost_data[index] = None
+
     def reset_fit_status(self):
         if self._handle is not None:
             self._handle.reset(-1)
@@ -204,6 +212,31 @@ class MultiOutputGP_GPU(object):
         self.logposterior(index, theta)
         grad = self._handle.logpost_grad(index - self._lo, self.n_params[index])
         return grad - self.priors[index].dlogpdtheta(self._thetas[index])
+
+    def logpost_and_deriv_batch(self, indices, thetas):
+        """Negative log-posterior and its gradient of several (local) emulators at once: one batched fit and one
+        batched gradient call on the GPU.  Returns ``{index: (value, gradient)}``; an emulator whose matrix is not
+        positive definite maps to ``None`` (and is left "not fit")."""
+        indices = [int(i) for i in indices]
+        thetas = np.array(thetas, dtype=np.float64).reshape(len(indices), -1)
+        for i in indices:
+            if not self._lo <= i < self._hi:
+                raise RuntimeError("emulator %d is not held by this rank" % i)
+        local = [i - self._lo for i in indices]
+        quad, logdet, nug, status = self._handle.fit_list(local, thetas)
+        ok = []
+        for k, i in enumerate(indices):
+            self._record(i, thetas[k], quad[k], logdet[k], nug[k], status[k])
+            if status[k] == libmogp.OK:
+                ok.append(k)
+        out = {i: None for i in indices}
+        if ok:
+            grads = self._handle.logpost_grad_list([local[k] for k in ok], self.n_params[indices[ok[0]]])
+            for row, k in enumerate(ok):
+                i = indices[k]
+                pri = self.priors[i]
+                out[i] = (self._logpost_data[i] - pri.logp(self._thetas[i]), grads[row] - pri.dlogpdtheta(self._thetas[i]))
+        return out
 
     def get_indices_fit(self):
         return [i for i in range(self.n_emulators) if self._global_fit(i)]

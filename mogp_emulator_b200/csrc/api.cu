@@ -418,11 +418,32 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
     return MOGP_OK;
 }
 
-int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas, int32_t n_params,
-             double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out) {
-    if (!h || !thetas || first < 0 || count < 1 || first + count > h->E) {
-        set_error("mogp_fit: bad output range");
+// H2D of the hyperparameter rows of the listed outputs (one copy over their index range)
+static int upload_hyper(mogp_handle* h, const int* idx, int count) {
+    int lo = idx[0], hi = idx[0];
+    for (int i = 1; i < count; i++) {
+        lo = std::min(lo, idx[i]);
+        hi = std::max(hi, idx[i]);
+    }
+    const int hs = h->d + 2;
+    API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)lo * hs, h->h_hyper + (size_t)lo * hs, sizeof(double) * (hi - lo + 1) * hs,
+                             cudaMemcpyHostToDevice, h->main));
+    return MOGP_OK;
+}
+
+int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* thetas, int32_t n_params,
+                  double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out) {
+    if (!h || !thetas || !idx || count < 1) {
+        set_error("mogp_fit: bad arguments");
         return MOGP_ERR_ARG;
+    }
+    std::vector<char> seen(h->E, 0);
+    for (int i = 0; i < count; i++) {
+        if (idx[i] < 0 || idx[i] >= h->E || seen[idx[i]]) {
+            set_error("mogp_fit: output index %d out of range or repeated", idx[i]);
+            return MOGP_ERR_ARG;
+        }
+        seen[idx[i]] = 1;
     }
     const int d = h->d;
     const int want = d + 1 + (h->nug_type == MOGP_NUG_FIT ? 1 : 0);
@@ -434,8 +455,9 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
     const int hs = d + 2;
     std::vector<double> nug(count, 0.0);
     std::vector<int> todo(count);
+    std::vector<int> pos(h->E, -1);   // output -> position in the call
     for (int i = 0; i < count; i++) {
-        const int o = first + i;
+        const int o = idx[i];
         const double* th = thetas + (size_t)i * n_params;
         double* hy = h->h_hyper + (size_t)o * hs;
         for (int k = 0; k < d; k++) hy[k] = exp(th[k]);       // CorrTransform: l = exp(-theta/2) <=> weight exp(theta)
@@ -446,19 +468,20 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
         hy[d + 1] = nug[i];
         h->fitted[o] = 0;
         todo[i] = o;
+        pos[o] = i;
     }
-    API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
-                             cudaMemcpyHostToDevice, h->main));
-    int rc = enqueue_attempt(h, todo.data(), count);
+    int rc = upload_hyper(h, todo.data(), count);
+    if (rc) return rc;
+    rc = enqueue_attempt(h, todo.data(), count);
     if (rc) return rc;
     // adaptive jitter retries (linalg/cholesky.py:264-279): jitter = mean(diag K) * 1e-6, x10 per failure, 5 tries.
     // diag of a stationary kernel matrix is sigma2 for every entry, so mean(diag K) == sigma2.
     std::vector<int> status(count, MOGP_OK);
     std::vector<int> failed;
     for (int i = 0; i < count; i++)
-        if (h->h_info[first + i] != 0) {
+        if (h->h_info[idx[i]] != 0) {
             status[i] = MOGP_ERR_NOT_PD;
-            if (h->nug_type == MOGP_NUG_ADAPTIVE) failed.push_back(first + i);
+            if (h->nug_type == MOGP_NUG_ADAPTIVE) failed.push_back(idx[i]);
         }
     double scale = 1e-6;
     for (int t = 0; t < 5 && !failed.empty(); t++, scale *= 10.0) {
@@ -470,22 +493,21 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
             run.push_back(o);
         }
         if (run.empty()) break;
-        API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
-                                 cudaMemcpyHostToDevice, h->main));
+        if ((rc = upload_hyper(h, run.data(), (int)run.size()))) return rc;
         rc = enqueue_attempt(h, run.data(), (int)run.size());
         if (rc) return rc;
         failed.clear();
         for (int o : run) {
             if (h->h_info[o] == 0) {
-                status[o - first] = MOGP_OK;
-                nug[o - first] = h->h_hyper[(size_t)o * hs + d + 1];
+                status[pos[o]] = MOGP_OK;
+                nug[pos[o]] = h->h_hyper[(size_t)o * hs + d + 1];
             } else {
                 failed.push_back(o);
             }
         }
     }
     for (int i = 0; i < count; i++) {
-        const int o = first + i;
+        const int o = idx[i];
         if (status[i] == MOGP_OK) h->fitted[o] = 1;
         h->h_hyper[(size_t)o * hs + d + 1] = nug[i];   // the nugget actually used enters the predictive variance
         if (status_out) status_out[i] = status[i];
@@ -493,10 +515,20 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
         if (logdet_out) logdet_out[i] = status[i] == MOGP_OK ? h->h_scal[2 * o] : std::numeric_limits<double>::quiet_NaN();
         if (quad_out) quad_out[i] = status[i] == MOGP_OK ? h->h_scal[2 * o + 1] : std::numeric_limits<double>::quiet_NaN();
     }
-    API_CUDA(cudaMemcpyAsync(h->hyper + (size_t)first * hs, h->h_hyper + (size_t)first * hs, sizeof(double) * count * hs,
-                             cudaMemcpyHostToDevice, h->main));
+    if ((rc = upload_hyper(h, todo.data(), count))) return rc;
     API_CUDA(cudaStreamSynchronize(h->main));
     return MOGP_OK;
+}
+
+int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas, int32_t n_params,
+             double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out) {
+    if (!h || first < 0 || count < 1 || first + count > h->E) {
+        set_error("mogp_fit: bad output range");
+        return MOGP_ERR_ARG;
+    }
+    std::vector<int32_t> idx(count);
+    for (int i = 0; i < count; i++) idx[i] = first + i;
+    return mogp_fit_list(h, idx.data(), count, thetas, n_params, quad_out, logdet_out, nugget_out, status_out);
 }
 
 // Runs predict for all fitted outputs; results land in h->res as [E][2][m] (mean row, variance row),
@@ -516,8 +548,8 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
     // when the workspace of the previous call already holds the whole job, reuse it without asking.
     const size_t need_all = (size_t)(round_up(m, 128) + 128) * np * 8 * fit_idx.size();
     size_t budget;
-    if (want_var && h->W_cap >= need_all && fit_idx.size() <= (size_t)MAXG) {
-        budget = h->W_cap;
+    if (want_var && fit_idx.size() <= (size_t)MAXG && (h->W_cap >= need_all || pool_has_block(need_all, h->device))) {
+        budget = need_all;   // the previous call's workspace (this handle's, or a closed handle's in the cache) holds the whole job
     } else {
         size_t free_b = 0, total_b = 0;
         API_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -711,17 +743,20 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
     return MOGP_ERR_ARG;
 }
 
-int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params) {
-    if (!h || idx < 0 || idx >= h->E || !grad) return MOGP_ERR_ARG;
+int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, double* grad, int32_t n_params) {
+    if (!h || !idx || count < 1 || !grad) return MOGP_ERR_ARG;
     const int d = h->d;
     const int want = d + 1 + (h->nug_type == MOGP_NUG_FIT ? 1 : 0);
     if (n_params != want) {
         set_error("mogp_logpost_grad: expected %d parameters, got %d", want, n_params);
         return MOGP_ERR_ARG;
     }
-    if (!h->fitted[idx]) {
-        set_error("mogp_logpost_grad: output %d has not been fit", idx);
-        return MOGP_ERR_NOT_FIT;
+    for (int i = 0; i < count; i++) {
+        if (idx[i] < 0 || idx[i] >= h->E) return MOGP_ERR_ARG;
+        if (!h->fitted[idx[i]]) {
+            set_error("mogp_logpost_grad: output %d has not been fit", idx[i]);
+            return MOGP_ERR_NOT_FIT;
+        }
     }
     if (d > grad_max_dims()) {
         set_error("mogp_logpost_grad: at most %d input dimensions are supported", grad_max_dims());
@@ -731,40 +766,77 @@ int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_param
     const int64_t np = h->n_pad;
     const int T = (int)(np / NB);
     const size_t tiles = (size_t)T * (T + 1);
-    // workspace: Wt (np x np) | partial (tiles x (d+2)) | grad (d+2) | scratch variance (np)
-    const size_t off_part = (size_t)np * np, off_grad = off_part + tiles * (d + 2), off_var = off_grad + (d + 2);
+    // workspace of a group of G outputs: [G] Wt = (L^-1)^T matrices (np x np each, contiguous: one tensor map), then
+    // [G] scratch blocks: per-tile partial sums (tiles x (d+2)) | gradient (d+2)
+    const size_t scr_per = tiles * (d + 2) + (d + 2) + 6;
+    const size_t per_out8 = ((size_t)np * np + scr_per + 7) / 8 * 8;
+    // group size: as many outputs as the workspace budget holds (the inverse factors are the big part)
+    int G = std::min<int>(count, MAXG);
+    if (h->G_cap < sizeof(double) * per_out8 * G) {
+        size_t free_b = 0, total_b = 0;
+        API_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = (size_t)((free_b + h->G_cap + pool_cached_bytes()) * 0.6);
+        while (G > 1 && sizeof(double) * per_out8 * G > budget) G = (G + 1) / 2;
+    }
     int rc;
-    if ((rc = grow(&h->G, &h->G_cap, sizeof(double) * (off_var + np), h->device))) return rc;
-    if ((rc = grow(&h->h_grad, &h->h_grad_cap, sizeof(double) * (d + 2), -1))) return rc;
-    double* Wt = h->G;
-    CUtensorMap tmW, tmW128, tmW64;
+    if ((rc = grow(&h->G, &h->G_cap, sizeof(double) * per_out8 * G, h->device))) return rc;
+    if ((rc = grow(&h->h_grad, &h->h_grad_cap, sizeof(double) * (d + 2) * G, -1))) return rc;
     TrsmPlan plan = predict_plan_square(np, h->n_sms);
-    if (make_kblocked_tmap(&tmW, Wt, np, np, plan.nw) || make_kblocked_tmap(&tmW128, Wt, np, np, 128) ||
-        make_kblocked_tmap(&tmW64, Wt, np, np, 64)) {
-        set_error("tensor map (grad workspace) failed");
-        return MOGP_ERR_CUDA;
+    if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, G, T), h->device))) return rc;
+    for (int g0 = 0; g0 < count; g0 += G) {
+        const int cnt = std::min(G, count - g0);
+        API_CUDA(cudaEventRecord(h->ev_a, h->main));
+        std::vector<int> outs(idx + g0, idx + g0 + cnt);
+        double* Wt0 = h->G;
+        double* scratch0 = h->G + (size_t)cnt * np * np;
+        // L^-1 of every output of the group with ONE dataflow TRSM launch on identity right-hand sides
+        CUtensorMap tmW;
+        if (make_kblocked_tmap(&tmW, Wt0, (int64_t)cnt * np, np, plan.nw)) {
+            set_error("tensor map (grad workspace) failed");
+            return MOGP_ERR_CUDA;
+        }
+        for (int k = 0; k < cnt; k++)
+            if (grad_set_identity(Wt0 + (size_t)k * np * np, np, h->main)) {
+                set_error("gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MOGP_ERR_CUDA;
+            }
+        if (predict_trsm(plan, outs.data(), cnt, h->maps.a128, h->maps.d128, tmW, Wt0, np, h->hyper, d, 0, np, np, nullptr, 0, 1,
+                         (int*)h->sync, nullptr, h->n_sms, h->main)) {
+            set_error("gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MOGP_ERR_CUDA;
+        }
+        for (int k = 0; k < cnt; k++) {
+            double* Wt = Wt0 + (size_t)k * np * np;
+            double* part = scratch0 + (size_t)k * scr_per;
+            double* gdev = part + tiles * (d + 2);
+            CUtensorMap tmW128, tmW64;
+            if (make_kblocked_tmap(&tmW128, Wt, np, np, 128) || make_kblocked_tmap(&tmW64, Wt, np, np, 64)) {
+                set_error("tensor map (grad workspace) failed");
+                return MOGP_ERR_CUDA;
+            }
+            const int o = outs[k];
+            if (grad_reduce_tiles(tmW128, tmW64, h->kernel, h->XT, h->n, np, d, h->alpha + (size_t)o * np,
+                                  h->hyper + (size_t)o * (d + 2), h->nug_type == MOGP_NUG_FIT, part, gdev, h->main)) {
+                set_error("gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MOGP_ERR_CUDA;
+            }
+            API_CUDA(cudaMemcpyAsync(h->h_grad + (size_t)k * (d + 2), gdev, sizeof(double) * (d + 2), cudaMemcpyDeviceToHost,
+                                     h->main));
+        }
+        API_CUDA(cudaEventRecord(h->ev_b, h->main));
+        API_CUDA(cudaStreamSynchronize(h->main));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+        h->timings[T_GRAD] += ms;
+        h->timings[T_NLAUNCH] += 1 + 3 * cnt;
+        for (int k = 0; k < cnt; k++)
+            for (int i = 0; i < n_params; i++) grad[(size_t)(g0 + k) * n_params + i] = h->h_grad[(size_t)k * (d + 2) + i];
     }
-    API_CUDA(cudaEventRecord(h->ev_a, h->main));
-    const int outs[1] = {idx};
-    if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, 1, T), h->device))) return rc;
-    if (grad_set_identity(Wt, np, h->main) ||
-        predict_trsm(plan, outs, 1, h->maps.a128, h->maps.d128, tmW, Wt, np, h->hyper, d, 0, np, np, h->G + off_var, 0, 1,
-                     (int*)h->sync, nullptr, h->n_sms, h->main) ||
-        grad_reduce_tiles(tmW128, tmW64, h->kernel, h->XT, h->n, np, d, h->alpha + (size_t)idx * np,
-                          h->hyper + (size_t)idx * (d + 2), h->nug_type == MOGP_NUG_FIT, h->G + off_part, h->G + off_grad,
-                          h->main)) {
-        set_error("gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return MOGP_ERR_CUDA;
-    }
-    API_CUDA(cudaEventRecord(h->ev_b, h->main));
-    API_CUDA(cudaMemcpyAsync(h->h_grad, h->G + off_grad, sizeof(double) * (d + 2), cudaMemcpyDeviceToHost, h->main));
-    API_CUDA(cudaStreamSynchronize(h->main));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
-    h->timings[T_GRAD] += ms;
-    h->timings[T_NLAUNCH] += 4;
-    for (int i = 0; i < n_params; i++) grad[i] = h->h_grad[i];
     return MOGP_OK;
+}
+
+int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params) {
+    return mogp_logpost_grad_list(h, &idx, 1, grad, n_params);
 }
 
 int mogp_trim(void) {

@@ -90,6 +90,13 @@ void pool_free(void* p) {
     g_live.erase(it);
 }
 
+bool pool_has_block(size_t bytes, int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const Block& b : g_free)
+        if (b.device == device && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + 4096) return true;
+    return false;
+}
+
 void pool_trim() {
     std::lock_guard<std::mutex> lk(g_mu);
     release_all_locked();

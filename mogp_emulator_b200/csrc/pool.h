@@ -9,6 +9,8 @@ namespace mogp {
 // device == -1: pinned host memory.  Returns nullptr on failure (after releasing the cache and retrying once).
 void* pool_alloc(size_t bytes, int device);
 void pool_free(void* p);
+// true if pool_alloc(bytes, device) would be served from the cache
+bool pool_has_block(size_t bytes, int device);
 void pool_trim();
 size_t pool_cached_bytes();
 

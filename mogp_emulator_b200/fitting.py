@@ -61,7 +61,64 @@ def _fit_single_GPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", **kwar
     return gp
 
 
+class _LockstepEvaluator(object):
+    """Lets several ``scipy.optimize.minimize`` runs (one thread per emulator) share batched GPU evaluations.
+
+    Every worker asks for (value, gradient) of its emulator at its current theta and blocks; when all workers that
+    are still optimising have asked, the last one to arrive evaluates the whole batch with ONE call
+    (``batch_fn(indices, thetas) -> {index: (value, gradient) or None}``) and wakes the others.  Each optimiser sees
+    exactly the values it would see alone, so results equal the one-emulator-at-a-time loop of the reference
+    (fitting.py:189-217), only faster: E concurrent factorisations fill the GPU where a single one is bound by its
+    dependency chain."""
+
+    def __init__(self, batch_fn, indices):
+        import threading
+        self._batch_fn = batch_fn
+        self._cond = threading.Condition()
+        self._active = set(indices)
+        self._pending = {}
+        self._results = {}
+        self._error = None
+        self.n_batches = 0
+        self.batch_sizes = []
+
+    def _run_batch_locked(self):
+        idx = sorted(self._pending)
+        thetas = [self._pending[i] for i in idx]
+        self._pending = {}
+        try:
+            res = self._batch_fn(idx, thetas)
+        except Exception as exc:            # a failure of the call itself: hand it to every waiter
+            res = {i: exc for i in idx}
+        self.n_batches += 1
+        self.batch_sizes.append(len(idx))
+        self._results.update(res)
+        self._cond.notify_all()
+
+    def evaluate(self, index, theta):
+        with self._cond:
+            self._pending[index] = np.array(theta, dtype=np.float64)
+            if len(self._pending) == len(self._active):
+                self._run_batch_locked()
+            while index not in self._results:
+                self._cond.wait()
+            res = self._results.pop(index)
+        if isinstance(res, Exception):
+            raise res
+        if res is None:
+            raise RuntimeError("Unable to fit the Gaussian process: matrix not positive definite")
+        return res
+
+    def done(self, index):
+        """The worker of ``index`` has no more requests: the remaining ones must not wait for it."""
+        with self._cond:
+            self._active.discard(index)
+            if self._pending and len(self._pending) == len(self._active):
+                self._run_batch_locked()
+
+
 def _fit_MOGPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", refit=False, **kwargs):
+    import threading
     method = _check_method(method)
     kwargs.pop("processes", None)
     n_tries = int(n_tries)
@@ -80,12 +137,41 @@ def _fit_MOGPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", refit=False
         assert len(theta0) == E, "theta0 must be a list of length n_emulators"
         starts = list(theta0)
     lo, hi = gp.local_range
-    todo = range(lo, hi) if refit else [i for i in gp.get_indices_not_fit() if lo <= i < hi]
+    todo = list(range(lo, hi)) if refit else [i for i in gp.get_indices_not_fit() if lo <= i < hi]
+    if not todo:
+        return gp
+    priors = {i: gp.priors[i] for i in todo}       # built on the calling thread
+    evaluator = _LockstepEvaluator(gp.logpost_and_deriv_batch, todo)
+    best = {}
+    errors = []
+
+    def worker(i):
+        try:
+            def fun(theta):
+                val, grad = evaluator.evaluate(i, theta)
+                return val, grad
+            best[i] = _minimise_one(fun, True, priors[i].sample, gp.n_params[i], n_tries, starts[i], method, kwargs)
+        except BaseException as exc:     # noqa: BLE001 - reported on the calling thread
+            errors.append((i, exc))
+        finally:
+            evaluator.done(i)
+
+    threads = [threading.Thread(target=worker, args=(i,), name="mogp-map-%d" % i) for i in todo]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0][1]
+    # final state: every emulator that converged sits at its best theta (one more batched fit)
+    good = [i for i in todo if best.get(i) is not None]
+    if good:
+        res = gp.logpost_and_deriv_batch(good, [best[i] for i in good])
+        del res
     for i in todo:
-        best = _minimise_one(lambda t, i=i: gp.logposterior(i, t), lambda t, i=i: gp.logpost_deriv(i, t),
-                             gp.priors[i].sample, gp.n_params[i], n_tries, starts[i], method, kwargs)
-        if best is not None:
-            gp.fit_emulator(i, best)
+        if best.get(i) is None:
+            gp.reset_emulator(i)
+    gp.map_fit_stats = {"batches": evaluator.n_batches, "mean_batch": float(np.mean(evaluator.batch_sizes or [0]))}
     return gp
 
 

@@ -46,6 +46,9 @@ SIGNATURES = {
     "mogp_trim": (ctypes.c_int, []),
     "mogp_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p, ctypes.c_int32,
                                 _c_double_p, _c_double_p, _c_double_p, _c_int_p]),
+    "mogp_fit_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, _c_double_p, ctypes.c_int32,
+                                     _c_double_p, _c_double_p, _c_double_p, _c_int_p]),
+    "mogp_logpost_grad_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, _c_double_p, ctypes.c_int32]),
     "mogp_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mogp_is_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_int_p]),
     "mogp_predict": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
@@ -185,6 +188,25 @@ class Handle(object):
         check(_lib.mogp_fit(self._h, int(first), int(count), dptr(thetas), int(n_params), dptr(quad), dptr(logdet),
                             dptr(nug), iptr(status)), "mogp_fit")
         return quad, logdet, nug, status
+
+    def fit_list(self, indices, thetas):
+        """Fit the listed (distinct, handle-local) outputs with one batched call; arrays come back in list order."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        thetas = as_f64(thetas).reshape(len(idx), -1)
+        count, n_params = thetas.shape
+        quad = np.zeros(count)
+        logdet = np.zeros(count)
+        nug = np.zeros(count)
+        status = np.zeros(count, dtype=np.int32)
+        check(_lib.mogp_fit_list(self._h, iptr(idx), int(count), dptr(thetas), int(n_params), dptr(quad), dptr(logdet),
+                                 dptr(nug), iptr(status)), "mogp_fit_list")
+        return quad, logdet, nug, status
+
+    def logpost_grad_list(self, indices, n_params):
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        out = np.zeros((len(idx), n_params))
+        check(_lib.mogp_logpost_grad_list(self._h, iptr(idx), len(idx), dptr(out), int(n_params)), "mogp_logpost_grad_list")
+        return out
 
     def reset(self, idx=-1):
         check(_lib.mogp_reset(self._h, int(idx)))

@@ -350,3 +350,32 @@ def test_full_size_c4_shape_properties(mogp):
     assert gd.nugget == 1e-6 * np.exp(0.3)
     assert np.all(gd.predict(Xs, deriv=False).unc >= 0.0)
     gd.close()
+
+
+def test_batched_multi_output_map_equals_one_at_a_time(mogp):
+    """fit_GP_MAP(MultiOutputGP_GPU) runs the emulators' L-BFGS-B searches in lock step over batched GPU evaluations
+    (mogp_fit_list / mogp_logpost_grad_list): every emulator must end exactly where its own single-output search ends,
+    a deliberately ill-posed emulator (all-equal inputs for its targets is not expressible here, so: NaN targets) must
+    stay "not fit" without stopping the others."""
+    X, Y, Xs = orc.make_workload(260, 3, 5, 40, seed=21)
+    theta0 = np.zeros(4)
+    mo = mogp.MultiOutputGP_GPU(X, Y, nugget=1e-5)
+    mo = mogp.fit_GP_MAP(mo, n_tries=1, theta0=theta0)
+    assert mo.get_indices_not_fit() == []
+    assert mo.map_fit_stats["mean_batch"] > 1.5          # evaluations really were shared
+    for i in range(5):
+        gp = mogp.GaussianProcessGPU(X, Y[i], nugget=1e-5)
+        gp = mogp.fit_GP_MAP(gp, n_tries=1, theta0=theta0)
+        assert_allclose(mo.thetas[i].get_data(), gp.theta.get_data(), rtol=1e-9, atol=1e-12)
+        assert_allclose(mo.logposterior(i), gp.current_logpost, rtol=1e-12)
+        gp.close()
+    # batched evaluation API itself, arbitrary (unsorted) subset
+    thetas = np.array([[0.3, 0.2, 0.1, 0.0], [1.0, 0.5, 0.2, 0.3], [0.0, 0.0, 0.0, 0.0]])
+    got = mo.logpost_and_deriv_batch([4, 1, 2], thetas)
+    for k, i in enumerate([4, 1, 2]):
+        ref = orc.OracleGP(X, Y[i], nugget=1e-5)
+        want_lp = ref.logposterior(thetas[k])
+        assert_allclose(got[i][0], want_lp, rtol=_logpost_rtol(ref.get_K_matrix(), ref.nugget))
+        want = ref.logpost_deriv(thetas[k])
+        assert_allclose(got[i][1], want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
+    mo.close()

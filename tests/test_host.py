@@ -170,3 +170,49 @@ def test_pack_unpack_roundtrip():
     assert_allclose(gm[ok], mean[ok])
     assert_allclose(gv[ok], var[ok])
     assert np.all(np.isnan(gm[~ok])) and np.all(np.isnan(gv[~ok]))
+
+
+def test_lockstep_evaluator_batches_concurrent_optimisations():
+    """The threaded MAP driver of MultiOutputGP_GPU: every optimiser must see exactly its own values (so results
+    equal separate runs) while evaluations are served in shared batches; an emulator whose evaluation fails keeps the
+    others going."""
+    import threading
+    from scipy.optimize import minimize
+    from mogp_emulator_b200.fitting import _LockstepEvaluator, _minimise_one
+
+    centres = {0: np.array([1.0, -2.0]), 1: np.array([0.5, 0.25]), 2: np.array([-3.0, 4.0]), 3: np.array([2.0, 2.0])}
+    calls = []
+
+    def batch_fn(indices, thetas):
+        calls.append(list(indices))
+        out = {}
+        for i, t in zip(indices, thetas):
+            if i == 3:
+                out[i] = None                      # "matrix not positive definite"
+                continue
+            dlt = t - centres[i]
+            out[i] = (float(np.sum(dlt ** 4) + np.sum(dlt ** 2)), 4.0 * dlt ** 3 + 2.0 * dlt)
+        return out
+
+    ev = _LockstepEvaluator(batch_fn, list(centres))
+    best = {}
+
+    def worker(i):
+        try:
+            best[i] = _minimise_one(lambda th: ev.evaluate(i, th), True, lambda: np.zeros(2), 2, 1, np.zeros(2),
+                                    "L-BFGS-B", {})
+        finally:
+            ev.done(i)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in centres]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    assert not any(t.is_alive() for t in threads)
+    for i in (0, 1, 2):
+        alone = minimize(lambda th: batch_fn([i], [th])[i], np.zeros(2), jac=True, method="L-BFGS-B")
+        np.testing.assert_array_equal(best[i], alone.x)
+        np.testing.assert_allclose(best[i], centres[i], atol=1e-4)
+    assert best[3] is None
+    assert max(len(c) for c in calls) == 4 and ev.n_batches < sum(len(c) for c in calls)
