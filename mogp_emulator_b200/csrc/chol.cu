@@ -32,9 +32,11 @@ namespace mogp {
 constexpr int PS = NB + 1;  // shared-memory row stride (doubles): odd => conflict-free column walks
 constexpr int SB = 16;      // sub-block width inside the diagonal block
 
+constexpr int NSB = NB / SB;                  // 8 sub-blocks per side
+
 struct Potf2Smem {
-    double S[NB * PS];
-    double X[NB * (SB + 1)];
+    double S[NB * PS];                         // lower: L, then its diagonal-block inverses; upper blocks: inv(L) blocks (see (ii))
+    double Tmp[(NSB - 1) * SB * (SB + 1)];     // per (b, J) pair of a step: sum_b' L_bb' X_b'J
     double Lr[SB * (SB + 1)];
     double rd[NB];
     double red[32];
@@ -83,8 +85,8 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
     }
 }
 
-// On entry sm.S holds the lower triangle of the block (upper part zero).  On success (returns 0) sm.S holds
-// inv(L) (lower), Lout (global, row stride ld) has received L with a zero upper part, and *logdet_add is
+// On entry sm.S holds the lower triangle of the block (upper part zero).  On success (returns 0) the diagonal 16x16
+// blocks of sm.S hold inv(L)'s diagonal blocks and its upper blocks (J, b) the off-diagonal blocks X_bJ, Lout (global, row stride ld) has received L with a zero upper part, and *logdet_add is
 // 2*sum(log L_ii) on thread 0.  On failure returns the 1-based index of the failing pivot (LAPACK info).
 // BAR_ALL: named barrier id for the NTHR participating threads.
 template <int NTHR, int BAR_ALL>
@@ -222,35 +224,72 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
         }
         named_bar_sync(BAR_ALL, NTHR);
     }
-    // (ii) block columns right to left:  Inv21 = -Inv22 * L21 * Inv11
-    constexpr int CW = SB / NG;   // columns of the 16-wide block column handled per thread
-    for (int J = NB / SB - 2; J >= 0; J--) {
-        const int R0 = SB * (J + 1), C0 = SB * J;
-        const int r = tid & 127, cq = tid >> 7;
-        if (r >= R0) {
-            double x[CW];
+    // (ii) off-diagonal blocks by distance from the diagonal:  X_bJ = -Inv_bb * sum_{b'=J}^{b-1} L_bb' X_b'J  (X_JJ = Inv_JJ).
+    //      All pairs (b, J = b - dist) of one distance are independent: one warp per pair, every lane a 2x4 micro-tile
+    //      (rows ti, ti+8; columns 4tc..4tc+3) so each shared-memory operand feeds several FMAs -- with one element
+    //      per thread this phase was bound by shared-memory bandwidth.  X_bJ is parked in the unused UPPER block
+    //      (J, b) of sm.S (element [i][c] at S[J*16+i][b*16+c]); the L blocks stay intact for the larger distances.
+    {
+        static_assert(NTHR / 32 >= NSB - 1, "one warp per (b, J) pair");
+        const int w = tid >> 5, lane = tid & 31;
+        const int ti = lane >> 2, tc = lane & 3;
+        for (int dist = 1; dist < NSB; dist++) {
+            const int b = dist + w, J = w;          // pair handled by this warp
+            if (b < NSB) {
+                const double* L0 = sm.S + (b * SB + ti) * PS;
+                const double* L1 = L0 + 8 * PS;
+                double t[2][4];
 #pragma unroll
-            for (int cc = 0; cc < CW; cc++) x[cc] = 0.0;
-#pragma unroll 4
-            for (int q = R0; q <= r; q++) {
-                const double a = sm.S[r * PS + q];
-                const double* bq = sm.S + q * PS + C0 + CW * cq;
+                for (int a = 0; a < 2; a++)
 #pragma unroll
-                for (int cc = 0; cc < CW; cc++) x[cc] = fma(a, bq[cc], x[cc]);
-            }
-            double* xr = sm.X + r * (SB + 1) + CW * cq;
+                    for (int q = 0; q < 4; q++) t[a][q] = 0.0;
+                for (int bp = J; bp < b; bp++) {
+                    // X_b'J[k][c]: the inverted diagonal block (b' == J, zero above its diagonal) or the parked block (J, b')
+                    const double* xs = sm.S + (J * SB) * PS + bp * SB + 4 * tc;
+                    const double* l0 = L0 + bp * SB;
+                    const double* l1 = L1 + bp * SB;
 #pragma unroll
-            for (int cc = 0; cc < CW; cc++) xr[cc] = x[cc];
-        }
-        named_bar_sync(BAR_ALL, NTHR);
-        if (r >= R0) {
-            const double* xr = sm.X + r * (SB + 1);
+                    for (int k = 0; k < SB; k++) {
+                        const double a0 = l0[k], a1 = l1[k];
+                        const double* x = xs + k * PS;
 #pragma unroll
-            for (int cc = 0; cc < CW; cc++) {
-                const int c = CW * cq + cc;
-                double y = 0.0;
-                for (int kk = c; kk < SB; kk++) y = fma(xr[kk], sm.S[(C0 + kk) * PS + C0 + c], y);
-                sm.S[r * PS + C0 + c] = -y;
+                        for (int q = 0; q < 4; q++) {
+                            t[0][q] = fma(a0, x[q], t[0][q]);
+                            t[1][q] = fma(a1, x[q], t[1][q]);
+                        }
+                    }
+                }
+                double* tp = sm.Tmp + w * SB * (SB + 1);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    tp[ti * (SB + 1) + 4 * tc + q] = t[0][q];
+                    tp[(ti + 8) * (SB + 1) + 4 * tc + q] = t[1][q];
+                }
+                __syncwarp();
+                const double* i0 = sm.S + (b * SB + ti) * PS + b * SB;     // rows ti, ti+8 of Inv_bb (lower triangular)
+                const double* i1 = i0 + 8 * PS;
+                double y[2][4];
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) y[a][q] = 0.0;
+#pragma unroll
+                for (int k = 0; k < SB; k++) {
+                    const double a0 = i0[k], a1 = i1[k];                   // zero for k beyond the row index
+                    const double* x = tp + k * (SB + 1) + 4 * tc;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        y[0][q] = fma(a0, x[q], y[0][q]);
+                        y[1][q] = fma(a1, x[q], y[1][q]);
+                    }
+                }
+                double* xo = sm.S + (J * SB) * PS + b * SB + 4 * tc;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    xo[ti * PS + q] = -y[0][q];
+                    xo[(ti + 8) * PS + q] = -y[1][q];
+                }
+                __syncwarp();   // block column J = w of the inverse is produced and consumed by this warp alone
             }
         }
         named_bar_sync(BAR_ALL, NTHR);
@@ -272,10 +311,12 @@ struct CholCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int VS_BYTES = NB * BN * 8;
     static constexpr int BAR_BYTES = (2 * NS + 2 + 4 + 1) * 8 + 16;
-    static constexpr int SMEM_BYTES = NS * STAGE_BYTES + VS_BYTES + BAR_BYTES + 128;
+    // the diagonal-block factorisation borrows the ring + staging buffer (and some more behind them)
+    static constexpr int TILE_BYTES = NS * STAGE_BYTES + VS_BYTES;
+    static constexpr int REGION_BYTES = ((int)sizeof(Potf2Smem) > TILE_BYTES ? ((int)sizeof(Potf2Smem) + 127) / 128 * 128 : TILE_BYTES);
+    static constexpr int SMEM_BYTES = REGION_BYTES + BAR_BYTES + 128;
 };
-static_assert(sizeof(Potf2Smem) <= CholCfg::NS * CholCfg::STAGE_BYTES + CholCfg::VS_BYTES,
-              "the diagonal-block factorisation borrows the ring + staging buffer");
+static_assert(CholCfg::SMEM_BYTES <= 232448, "shared memory per CTA");
 
 constexpr int CH_HDR = 32;   // ints in front of the per-output progress blocks (word 0 = ticket counter)
 
@@ -330,7 +371,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     extern __shared__ __align__(128) unsigned char chol_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(chol_smem_raw) + 127) & ~uintptr_t(127));
     double* VS = reinterpret_cast<double*>(base + NS * Cfg::STAGE_BYTES);  // [128/8][BN][8]
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + NS * Cfg::STAGE_BYTES + Cfg::VS_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + Cfg::REGION_BYTES);
     uint64_t* empty = full + NS;
     uint64_t* ks_full = empty + NS;
     uint64_t* vs_free = ks_full + 1;
@@ -497,7 +538,11 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                     double* Dblk = p.Dinv + (rb + (int64_t)j * NB) * NB;
                     for (int idx = ctid; idx < NB * NB; idx += Cfg::NCW * 32) {
                         const int r = idx >> 7, c = idx & 127;
-                        Dblk[idx] = (c <= r) ? sm.S[r * PS + c] : 0.0;
+                        const int b = r >> 4, J = c >> 4;
+                        double v = 0.0;
+                        if (b == J) v = (c <= r) ? sm.S[r * PS + c] : 0.0;
+                        else if (b > J) v = sm.S[(J * SB + (r & 15)) * PS + b * SB + (c & 15)];   // parked in the upper block (J, b)
+                        Dblk[idx] = v;
                     }
                     // the D tiles of one output run strictly in order: plain read-modify-write is race-free
                     if (ctid == 0) p.scal[2 * o] = (j > 0 ? __ldcg(p.scal + 2 * o) : 0.0) + ld_add;

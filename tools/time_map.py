@@ -11,8 +11,11 @@ mo = MultiOutputGP_GPU(X, Y, nugget=1e-6)
 mo.priors
 fit_GP_MAP(mo, n_tries=1, theta0=theta0, maxiter=20)       # warm-up
 mo.reset_fit_status()
+mo.timings(reset=True)
 t0 = time.perf_counter(); fit_GP_MAP(mo, n_tries=1, theta0=theta0, maxiter=20); t1 = time.perf_counter()
 print("batched: %d emulators n=%d d=%d: %.3f s, stats %s" % (E, n, d, t1 - t0, mo.map_fit_stats))
+tm = mo.timings()
+print("  device ms: fit %.1f (kmat %.1f chol %.1f solve %.1f) grad %.1f" % (tm["fit_ms"], tm["kmat_ms"], tm["chol_ms"], tm["solve_ms"], tm["grad_ms"]))
 tb = mo.thetas[0].get_data().copy()
 mo.close()
 gp = GaussianProcessGPU(X, Y[0], nugget=1e-6); gp.priors
