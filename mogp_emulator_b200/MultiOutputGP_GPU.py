@@ -277,17 +277,13 @@ class MultiOutputGP_GPU(object):
         if self._handle is None:
             raise RuntimeError("this rank holds no outputs: use at most n_emulators ranks")
         mean_all, var_all, status_all = self._handle.predict_allgather(self._comm, testing, include_nugget, self._e_pad)
-        rows = []
-        self._remote_fit = {}
-        for r in range(self._comm.world):
-            lo, hi, _ = shard_bounds(E, r, self._comm.world)
-            for k in range(hi - lo):
-                rows.append(r * self._e_pad + k)
-                self._remote_fit[lo + k] = bool(status_all[r * self._e_pad + k] == libmogp.OK)
-        rows = np.array(rows, dtype=np.int64)
-        if not allow_not_fit and np.any(status_all[rows] != libmogp.OK):
+        # rank r's block starts at row r*e_pad == its first global output index (block partition, sharding.py), so the
+        # gathered rows are already in output order; only the last rank's padding rows trail behind: slice, no copy
+        status = status_all[:E]
+        self._remote_fit = {i: bool(status[i] == libmogp.OK) for i in range(E)}
+        if not allow_not_fit and np.any(status != libmogp.OK):
             raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
-        return PredictResult(mean=mean_all[rows], unc=var_all[rows] if unc else None, deriv=None)
+        return PredictResult(mean=mean_all[:E], unc=var_all[:E] if unc else None, deriv=None)
 
     def __call__(self, testing, processes=None):
         return self.predict(testing, unc=False, deriv=False, processes=processes)[0]

@@ -379,3 +379,25 @@ def test_batched_multi_output_map_equals_one_at_a_time(mogp):
         want = ref.logpost_deriv(thetas[k])
         assert_allclose(got[i][1], want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
     mo.close()
+
+
+def test_more_outputs_than_one_launch_group(mogp):
+    """More outputs than one batched launch holds (70 > 64): fit, predict and batched gradients run in groups."""
+    X, Y, Xs = orc.make_workload(90, 2, 70, 33, seed=8)
+    thetas = np.zeros((70, 3))
+    thetas[:, 0] = np.linspace(-0.5, 1.5, 70)
+    mo = mogp.MultiOutputGP_GPU(X, Y, nugget=1e-6)
+    mo.fit(thetas)
+    assert mo.get_indices_not_fit() == []
+    r = mo.predict(Xs, deriv=False)
+    for i in (0, 63, 64, 69):
+        ref = orc.OracleGP(X, Y[i], nugget=1e-6).fit(thetas[i])
+        rm, rv = ref.predict(Xs)
+        assert_allclose(r.mean[i], rm, rtol=1e-6, atol=1e-6 * np.abs(rm).max())
+        assert_allclose(r.unc[i], rv, rtol=1e-4, atol=1e-10)
+    got = mo.logpost_and_deriv_batch(list(range(70)), thetas)
+    for i in (0, 64, 69):
+        ref = orc.OracleGP(X, Y[i], nugget=1e-6)
+        want = ref.logpost_deriv(thetas[i])
+        assert_allclose(got[i][1], want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
+    mo.close()

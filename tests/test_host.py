@@ -216,3 +216,12 @@ def test_lockstep_evaluator_batches_concurrent_optimisations():
         np.testing.assert_allclose(best[i], centres[i], atol=1e-4)
     assert best[3] is None
     assert max(len(c) for c in calls) == 4 and ev.n_batches < sum(len(c) for c in calls)
+
+
+def test_gathered_rows_are_already_in_output_order():
+    """MultiOutputGP_GPU.predict slices the gathered (world*e_pad, m) block with [:E] instead of copying rows: that is
+    only right because a block partition puts rank r's first output at row r*e_pad."""
+    from mogp_emulator_b200 import sharding
+    for E in (1, 2, 5, 8, 31, 32, 33, 256):
+        for world in (1, 2, 3, 4, 8):
+            assert sharding.gathered_rows(E, world) == list(range(E))
