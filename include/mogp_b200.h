@@ -88,7 +88,7 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
 
 /* replaces DenseGP_GPU::predict_deriv (densegp_gpu.hpp:411-448) / MultiOutputGP_GPU::predict_deriv
  * (multioutputgp_gpu.hpp:230-257): derivative of the posterior mean with respect to the test inputs.
- * deriv: (n_out, m, d) caller-allocated; rows of unfit outputs are NaN.  At most 64 input dimensions. */
+ * deriv: (n_out, m, d) caller-allocated; rows of unfit outputs are NaN. */
 int mogp_predict_deriv(mogp_handle* h, const double* Xs, int64_t m, double* deriv, int32_t* status);
 
 /* Sharded multi-output predict: every rank predicts its own outputs, then ONE ncclAllGather of the

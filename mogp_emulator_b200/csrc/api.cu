@@ -392,7 +392,7 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
             return MOGP_ERR_CUDA;
         }
         API_CUDA(cudaEventRecord(h->ev_c, h->main));
-        int rs = solve_alpha(h->A, np, h->Dinv, h->Y, h->z, h->alpha, h->scal, h->info, og, cnt, h->main);
+        int rs = solve_alpha(h->A, np, h->Dinv, h->Y, h->z, h->alpha, h->scal, h->info, og, cnt, h->n_sms, h->main);
         if (rs) {
             set_error(rs == 2 ? "n too large for the cluster solver" : "solve launch failed");
             return rs == 2 ? MOGP_ERR_ARG : MOGP_ERR_CUDA;

@@ -45,7 +45,7 @@ int kmat_deriv(int kernel, const double* XsT, int64_t xs_stride, const double* X
 // ---- solve.cu ----
 int solve_init();
 int solve_alpha(const double* A_slab, int64_t n_pad, const double* Dinv_slab, const double* Y, double* z, double* alpha,
-                double* scal, const int* info, const int* outs, int count, cudaStream_t st);
+                double* scal, const int* info, const int* outs, int count, int n_sms, cudaStream_t st);
 
 // ---- predict.cu ----
 int predict_init();

@@ -222,12 +222,13 @@ int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int
 // mogp_gpu/src/kernel.cu:69-100, 264-302 and densegp_gpu.hpp:411-448):
 //     dmu_c/dx*_q = sum_i alpha_i * sigma2 * k'(r2_ci) * 2 w_q (x*_cq - x_iq),   k' = dk/dr2
 // One thread per test point streams the training points (tiles of 32 staged in shared memory, broadcast reads)
-// and keeps 16 derivative components in registers; more than 16 input dimensions take further passes.  No
+// and keeps 16 derivative components in registers (its own coordinates come through L1); more than 16 input
+// dimensions take further passes.  No
 // (m x n x d) derivative tensor is materialised (the reference allocates exactly that in work_mat_d).
 // ------------------------------------------------------------------------------------------
 constexpr int KD_TB = 32;    // training points per staged tile
 constexpr int KD_Q = 16;     // derivative components per pass
-constexpr int KD_MAXD = 64;
+constexpr int KD_MAXD = 256;   // == the library's limit on input dimensions
 
 struct DerivParams {
     const double* XsT;     // [d][xs_stride] test points, transposed
@@ -245,8 +246,7 @@ template <int KT>
 __global__ void __launch_bounds__(128) kderiv_kernel(const DerivParams p) {
     extern __shared__ __align__(16) double kd_smem[];
     const int d = p.d;
-    double* xs = kd_smem;              // [d][128]
-    double* xt = xs + d * 128;         // [d][KD_TB]
+    double* xt = kd_smem;              // [d][KD_TB]
     double* al = xt + d * KD_TB;       // [KD_TB]
     double* w = al + KD_TB;            // [d]
     const int tid = threadIdx.x;
@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(128) kderiv_kernel(const DerivParams p) {
     const int64_t c = (int64_t)blockIdx.x * 128 + tid;
     const double* hyp = p.hyper + (int64_t)o * (d + 2);
     for (int i = tid; i < d; i += 128) w[i] = hyp[i];
-    for (int dd = 0; dd < d; dd++) xs[dd * 128 + tid] = (c < p.m) ? p.XsT[(int64_t)dd * p.xs_stride + c] : 0.0;
+    // this thread's test point: coalesced, L1-resident reads of XsT (zero-padded up to xs_stride)
+    const double* xs = p.XsT + ((c < p.xs_stride) ? c : 0);
+    const int64_t xss = p.xs_stride;
     const double sigma2 = hyp[d];
     __syncthreads();
     for (int d0 = 0; d0 < d; d0 += KD_Q) {
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(128) kderiv_kernel(const DerivParams p) {
             for (int ii = 0; ii < KD_TB; ii++) {
                 double r2 = 0.0;
                 for (int dd = 0; dd < d; dd++) {
-                    const double df = xs[dd * 128 + tid] - xt[dd * KD_TB + ii];
+                    const double df = __ldg(xs + dd * xss) - xt[dd * KD_TB + ii];
                     r2 = fma(w[dd], df * df, r2);
                 }
                 double dk;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(128) kderiv_kernel(const DerivParams p) {
                 const double kp = sigma2 * dk * al[ii];   // al is zero past n
 #pragma unroll
                 for (int q = 0; q < KD_Q; q++)
-                    if (d0 + q < d) g[q] = fma(kp, xs[(d0 + q) * 128 + tid] - xt[(d0 + q) * KD_TB + ii], g[q]);
+                    if (d0 + q < d) g[q] = fma(kp, __ldg(xs + (d0 + q) * xss) - xt[(d0 + q) * KD_TB + ii], g[q]);
             }
         }
         if (c < p.m) {
@@ -304,9 +306,9 @@ int kmat_deriv(int kernel, const double* XsT, int64_t xs_stride, const double* X
                int d, const int* outs, int count, const double* hyper, const double* alpha, double* out, cudaStream_t st) {
     if (count < 1 || count > MAXG || d > KD_MAXD) return 1;
     static bool attr_done = false;
-    const size_t smem = sizeof(double) * ((size_t)d * 128 + (size_t)d * KD_TB + KD_TB + d);
+    const size_t smem = sizeof(double) * ((size_t)d * KD_TB + KD_TB + d);
     if (!attr_done) {
-        const int maxs = (int)(sizeof(double) * ((size_t)KD_MAXD * 128 + KD_MAXD * KD_TB + KD_TB + KD_MAXD));
+        const int maxs = (int)(sizeof(double) * ((size_t)KD_MAXD * KD_TB + KD_TB + KD_MAXD));
         if (cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess ||
             cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess)
             return 1;

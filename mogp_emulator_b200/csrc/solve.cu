@@ -250,11 +250,12 @@ int solve_init() {
 
 // z = L^-1 y, alpha = L^-T z, quad = z^T z for `count` outputs (slab indices outs[]): one cluster per output, one launch.
 int solve_alpha(const double* A_slab, int64_t n_pad, const double* Dinv_slab, const double* Y, double* z, double* alpha,
-                double* scal, const int* info, const int* outs, int count, cudaStream_t st) {
+                double* scal, const int* info, const int* outs, int count, int n_sms, cudaStream_t st) {
     if (count < 1 || count > MAXG) return 1;
     const int T = (int)(n_pad / NB);
     int C = 1;
     while (C * 2 <= g_max_cluster && C * 4 <= T) C *= 2;   // at least two blocks of the vector per CTA
+    while (C > 1 && C * count > n_sms) C /= 2;             // many outputs: all clusters resident at once beats wide clusters
     const int nown = (T + C - 1) / C;
     const size_t smem = (size_t)(nown * NB + C * NB + NB + 4 * NB + 16) * sizeof(double);
     if (smem > 200 * 1024) return 2;

@@ -248,6 +248,7 @@ def test_fit_GP_MAP_matches_cpu_optimiser(mogp):
     ("SquaredExponential", 200, 3, 77),
     ("Matern52", 333, 5, 130),
     ("SquaredExponential", 150, 20, 40),     # more than one 16-component pass
+    ("Matern52", 120, 70, 25),               # more input dimensions than the gradient kernel's 64
 ])
 def test_predict_deriv_against_oracle_and_finite_differences(mogp, kernel, n, d, m):
     """d mean / d x*: the GPU kernel vs the oracle's restatement of the reference GPU definition
