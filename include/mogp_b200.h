@@ -91,6 +91,13 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
  * deriv: (n_out, m, d) caller-allocated; rows of unfit outputs are NaN. */
 int mogp_predict_deriv(mogp_handle* h, const double* Xs, int64_t m, double* deriv, int32_t* status);
 
+/* Full predictive covariance of ONE output at m test points (the CPU GaussianProcess.predict(full_cov=True),
+ * GaussianProcess.py:899-911; the reference GPU class has no equivalent):
+ *   cov = sigma2 k(X*, X*) [+ nugget I] - K*^T K^-1 K*,   (m, m), not clipped;   mean: (m).
+ * V = L^-1 K* by the dataflow TRSM, then one FP64 tensor-pipe SYRK. */
+int mogp_predict_cov(mogp_handle* h, int32_t idx, const double* Xs, int64_t m, int32_t include_nugget, double* mean,
+                     double* cov);
+
 /* Sharded multi-output predict: every rank predicts its own outputs, then ONE ncclAllGather of the
  * packed per-rank [e_pad][2][m] block delivers all ranks' means and variances to every rank.
  * mean_all, var_all: (world * e_pad, m); status_all: (world * e_pad) (MOGP_ERR_ARG marks padding rows). */

@@ -260,7 +260,7 @@ class GaussianProcessGPU(object):
         raise GPUUnavailableError("The Hessian calculation is not currently implemented in the GPU version of MOGP.")
 
     # -- prediction -------------------------------------------------------------------------------------
-    def predict(self, testing, unc=True, deriv=True, include_nugget=True):
+    def predict(self, testing, unc=True, deriv=True, include_nugget=True, full_cov=False):
         """Posterior mean / variance at ``testing`` (GaussianProcess.predict, GaussianProcess.py:818-927) and, with
         ``deriv=True`` (the reference GPU class's default, GaussianProcessGPU.py:582), the derivative of the mean
         with respect to the test inputs, shape ``(m, D)`` (DenseGP_GPU::predict_deriv, densegp_gpu.hpp:411-448)."""
@@ -273,8 +273,12 @@ class GaussianProcessGPU(object):
             testing = np.reshape(testing, (1, len(testing)))
         assert testing.ndim == 2
         assert testing.shape[1] == self.D
-        mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
         dmean = self._handle.predict_deriv(testing)[0][0] if deriv else None
+        if unc and full_cov:
+            # the CPU class's full_cov=True (GaussianProcess.py:899-911): (m, m) covariance, not clipped
+            mean1, cov = self._handle.predict_cov(0, testing, include_nugget=include_nugget)
+            return PredictResult(mean=mean1, unc=cov, deriv=dmean)
+        mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
         return PredictResult(mean=mean[0], unc=(var[0] if unc else None), deriv=dmean)
 
     def __call__(self, testing):

@@ -253,7 +253,8 @@ class MultiOutputGP_GPU(object):
     _remote_fit = {}
 
     # -- prediction (MultiOutputGP_GPU.py:185-297; CPU semantics MultiOutputGP.py:182-319) ---------------
-    def predict(self, testing, unc=True, deriv=True, include_nugget=True, allow_not_fit=False, processes=None):
+    def predict(self, testing, unc=True, deriv=True, include_nugget=True, allow_not_fit=False, processes=None,
+                full_cov=False):
         """Means / variances ``(n_emulators, m)`` and, with ``deriv=True`` (the reference's default,
         MultiOutputGP_GPU.py:185), mean derivatives ``(n_emulators, m, D)``.  Sharded (``comm=``) emulators gather
         means and variances only: pass ``deriv=False`` there."""
@@ -268,8 +269,15 @@ class MultiOutputGP_GPU(object):
         if self._comm is None:
             if not allow_not_fit and len(self.get_indices_not_fit()) > 0:
                 raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
-            mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
             dmean = self._handle.predict_deriv(testing)[0] if deriv else None
+            if unc and full_cov:
+                # (E, m, m) covariances, one output at a time (MultiOutputGP.py:183, 303); NaN for unfit emulators
+                mean = np.full((E, m), np.nan)
+                cov = np.full((E, m, m), np.nan)
+                for i in self.get_indices_fit():
+                    mean[i], cov[i] = self._handle.predict_cov(i, testing, include_nugget=include_nugget)
+                return PredictResult(mean=mean, unc=cov, deriv=dmean)
+            mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
             return PredictResult(mean=mean, unc=var if unc else None, deriv=dmean)
         if deriv:
             raise GPUUnavailableError("predictive derivatives are not gathered across ranks: pass deriv=False")

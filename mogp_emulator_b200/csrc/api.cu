@@ -696,6 +696,67 @@ int mogp_predict_deriv(mogp_handle* h, const double* Xs, int64_t m, double* deri
     return MOGP_OK;
 }
 
+int mogp_predict_cov(mogp_handle* h, int32_t idx, const double* Xs, int64_t m, int32_t include_nugget, double* mean,
+                     double* cov) {
+    if (!h || idx < 0 || idx >= h->E || !Xs || m < 1 || !mean || !cov) {
+        set_error("mogp_predict_cov: bad arguments");
+        return MOGP_ERR_ARG;
+    }
+    if (!h->fitted[idx]) {
+        set_error("mogp_predict_cov: output %d has not been fit", idx);
+        return MOGP_ERR_NOT_FIT;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t np = h->n_pad;
+    const int d = h->d;
+    const int n_tiles = (int)(np / 128);
+    const int64_t m_pad = round_up(m, 128);
+    const int64_t w_stride = m_pad + 128;
+    const int outs[1] = {idx};
+    int rc;
+    // workspace: V = L^-1 K* (test-major, w_stride x n_pad) in W, the m_pad x m_pad covariance in G
+    if ((rc = grow(&h->W, &h->W_cap, sizeof(double) * (size_t)w_stride * np, h->device))) return rc;
+    if ((rc = grow(&h->G, &h->G_cap, sizeof(double) * (size_t)m_pad * m_pad, h->device))) return rc;
+    if ((rc = grow(&h->XsT, &h->XsT_cap, sizeof(double) * d * w_stride, h->device))) return rc;
+    if ((rc = grow(&h->h_XsT, &h->h_XsT_cap, sizeof(double) * d * w_stride, -1))) return rc;
+    if ((rc = grow(&h->part, &h->part_cap, sizeof(double) * (size_t)n_tiles * w_stride, h->device))) return rc;
+    if ((rc = grow(&h->res, &h->res_cap, sizeof(double) * (size_t)h->E * 2 * m, h->device))) return rc;
+    if ((rc = grow(&h->normacc, &h->normacc_cap, sizeof(double) * (size_t)w_stride, h->device))) return rc;
+    TrsmPlan plan = predict_plan(m, 1, (int)np, h->n_sms);
+    if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, 1, n_tiles), h->device))) return rc;
+    memset(h->h_XsT, 0, sizeof(double) * d * w_stride);
+    for (int64_t i = 0; i < m; i++)
+        for (int k = 0; k < d; k++) h->h_XsT[(size_t)k * w_stride + i] = Xs[i * d + k];
+    API_CUDA(cudaMemcpyAsync(h->XsT, h->h_XsT, sizeof(double) * d * w_stride, cudaMemcpyHostToDevice, h->main));
+    CUtensorMap tmXsT, tmW, tmW128, tmW64;
+    if (make_2d_tmap(&tmXsT, h->XsT, d, w_stride, w_stride, kmat_dbox(d), 128) ||
+        make_kblocked_tmap(&tmW, h->W, w_stride, np, plan.nw) || make_kblocked_tmap(&tmW128, h->W, w_stride, np, 128) ||
+        make_kblocked_tmap(&tmW64, h->W, w_stride, np, 64)) {
+        set_error("tensor map (predict_cov) failed");
+        return MOGP_ERR_CUDA;
+    }
+    double* res_row = h->res + (size_t)idx * 2 * m;   // [mean | variance] rows of this output
+    if (kmat_cross(tmXsT, h->tmXT, h->kernel, h->n, np, w_stride, d, outs, 1, h->hyper, h->W, w_stride, 1, h->alpha, np,
+                   h->part, h->main) ||
+        mean_reduce(h->part, outs, 1, n_tiles, w_stride, m, h->res, 2 * m, h->main) ||
+        predict_trsm(plan, outs, 1, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d, include_nugget, np, m,
+                     h->res + m, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms, h->main, 1) ||
+        // sigma2 * k(X*, X*) [+ nugget I] (lower tiles), then minus V^T V
+        kmat_sym(tmXsT, h->kernel, m, m_pad, d, h->hyper, outs, 1, include_nugget ? 1 : 0, h->G, 0, h->main) ||
+        cov_syrk_sub(tmW128, tmW64, 0, m_pad, np, h->G, h->main)) {
+        set_error("predict_cov launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MOGP_ERR_CUDA;
+    }
+    h->timings[T_NLAUNCH] += 5;
+    API_CUDA(cudaMemcpyAsync(mean, res_row, sizeof(double) * m, cudaMemcpyDeviceToHost, h->main));
+    API_CUDA(cudaMemcpy2DAsync(cov, sizeof(double) * m, h->G, sizeof(double) * m_pad, sizeof(double) * m, m,
+                               cudaMemcpyDeviceToHost, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    for (int64_t i = 0; i < m; i++)
+        for (int64_t j = i + 1; j < m; j++) cov[i * m + j] = cov[j * m + i];
+    return MOGP_OK;
+}
+
 int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
     if (!h || idx < 0 || idx >= h->E || !out) return MOGP_ERR_ARG;
     if (!h->fitted[idx]) {

@@ -34,6 +34,10 @@ struct GradParams {
     int64_t n, n_pad;
     int d, kernel;
     int row_base;         // first row of Wt inside its tensor map (0)
+    // MODE 1 (full predictive covariance): C (lower 128x64 tiles, row stride ldc) -= W_I . W_J^T over k_chunks chunks
+    double* C;
+    int64_t ldc;
+    int k_chunks;
 };
 
 template <int KT>
@@ -49,7 +53,7 @@ __device__ __forceinline__ void kval_and_deriv(double r2, double& k, double& dk)
     }
 }
 
-template <int KT>
+template <int KT, int MODE>
 __global__ void __launch_bounds__((G_NCW + 4) * 32, 2)
 grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GradParams p) {
     extern __shared__ __align__(128) unsigned char grad_smem_raw[];
@@ -70,8 +74,9 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int J2 = id - I * (I + 1);
     const int row0 = I * G_BM, col0 = J2 * G_BN;
     const int T = (int)(p.n_pad / NB);
-    const int nchunk = (T - I) * (NB / KC);   // contraction over r >= 128*I (Wt is upper triangular)
-    const int kout0 = I * (NB / 8);
+    // MODE 0: contraction over r >= 128*I (Wt is upper triangular); MODE 1: over the whole row of W
+    const int nchunk = (MODE == 0) ? (T - I) * (NB / KC) : p.k_chunks;
+    const int kout0 = (MODE == 0) ? I * (NB / 8) : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_NS; s++) {
@@ -80,9 +85,11 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < G_BM + G_BN; i += blockDim.x)
-        al_r[i] = (i < G_BM) ? p.alpha[row0 + i] : p.alpha[col0 + i - G_BM];
-    for (int i = threadIdx.x; i < G_MAXD; i += blockDim.x) w_s[i] = (i < p.d) ? p.hyper[i] : 0.0;
+    if (MODE == 0) {
+        for (int i = threadIdx.x; i < G_BM + G_BN; i += blockDim.x)
+            al_r[i] = (i < G_BM) ? p.alpha[row0 + i] : p.alpha[col0 + i - G_BM];
+        for (int i = threadIdx.x; i < G_MAXD; i += blockDim.x) w_s[i] = (i < p.d) ? p.hyper[i] : 0.0;
+    }
     __syncthreads();
 
     if (warp >= G_NCW) {
@@ -123,6 +130,23 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ps.advance();
     }
 
+    if (MODE == 1) {
+        // full predictive covariance: C_tile -= W_I . W_J^T   (GaussianProcess.py:899-911)
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double* rowp = p.C + (int64_t)(row0 + arow0 + mt * 16 + g + h * 8) * p.ldc + col0 + 2 * t;
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    double2 v = *reinterpret_cast<const double2*>(rowp + nt * 8);
+                    v.x -= acc[mt][nt][2 * h];
+                    v.y -= acc[mt][nt][2 * h + 1];
+                    *reinterpret_cast<double2*>(rowp + nt * 8) = v;
+                }
+            }
+        return;
+    }
     // ---- epilogue: all TMA traffic has landed and been consumed; park the X tiles in the ring ----
     named_bar_sync(1, G_NCW * 32);
     const int d = p.d;
@@ -246,8 +270,9 @@ __global__ void set_identity_kernel(double* __restrict__ W, int64_t n_pad) {
 int grad_init() {
     static bool done = false;
     if (done) return 0;
-    if (cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_SQEXP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_MATERN52, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_SQEXP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess)
         return 1;
     done = true;
     return 0;
@@ -271,10 +296,22 @@ int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int k
     const int T = (int)(n_pad / NB);
     const int tiles = T * (T + 1);
     if (kernel == MOGP_KERNEL_SQEXP)
-        grad_tile_kernel<MOGP_KERNEL_SQEXP><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
+        grad_tile_kernel<MOGP_KERNEL_SQEXP, 0><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
     else
-        grad_tile_kernel<MOGP_KERNEL_MATERN52><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
+        grad_tile_kernel<MOGP_KERNEL_MATERN52, 0><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
     grad_reduce_kernel<<<d + 2, 256, 0, st>>>(partial, tiles, d, alpha, n, hyper, fit_nugget, grad);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// C (m_pad x m_pad, lower 128x64 tiles) -= W W^T with W = the rows [row_base, row_base + m_pad) of a K-blocked tensor
+// map (box 128 / box 64), contraction over k_len columns: the SYRK of predict(full_cov=True).
+int cov_syrk_sub(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int row_base, int64_t m_pad, int64_t k_len, double* C,
+                 cudaStream_t st) {
+    GradParams p{};
+    p.row_base = row_base; p.n_pad = m_pad; p.C = C; p.ldc = m_pad; p.k_chunks = (int)(k_len / KC);
+    const int T = (int)(m_pad / NB);
+    const int tiles = T * (T + 1);
+    grad_tile_kernel<MOGP_KERNEL_SQEXP, 1><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

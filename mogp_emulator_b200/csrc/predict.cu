@@ -50,6 +50,7 @@ struct PredParams {
     int d;
     int include_nugget;
     int tri_rhs;            // right-hand side is the identity: panel c0 starts its walk at block row c0/128
+    int keep_v;             // also store the last block row of V (full predictive covariance needs all of V)
     double* var;            // result rows: var of output o at var + o*var_stride
     int64_t var_stride;
     int* sync;              // [SYNC_HDR + count*panels*T]: ticket counter, then one ready-flag per tile (zeroed per launch)
@@ -293,7 +294,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
                 }
             }
         }
-        if (!last || p.tri_rhs) {   // the last block row is only needed when V itself is the result
+        if (!last || p.tri_rhs || p.keep_v) {   // the last block row is only needed when V itself is the result
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
@@ -374,8 +375,9 @@ TrsmPlan predict_plan_square(int64_t n_pad, int n_sms) {
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
                  int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, int* sync, double* normacc,
-                 int n_sms, cudaStream_t st) {
+                 int n_sms, cudaStream_t st, int keep_v) {
     PredParams p{};
+    p.keep_v = keep_v;
     p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m; p.T = (int)(n_pad / NB);
     p.panels = plan.panels; p.count = count;
     for (int i = 0; i < count; i++) p.outs[i] = outs[i];

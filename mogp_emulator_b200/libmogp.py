@@ -54,6 +54,8 @@ SIGNATURES = {
     "mogp_predict": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                     _c_double_p, _c_double_p, _c_int_p]),
     "mogp_predict_deriv": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_int_p]),
+    "mogp_predict_cov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int64, ctypes.c_int32,
+                                        _c_double_p, _c_double_p]),
     "mogp_predict_allgather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_double_p, ctypes.c_int64,
                                               ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, _c_int_p]),
     "mogp_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p]),
@@ -233,6 +235,15 @@ class Handle(object):
         status = np.zeros(self.n_out, dtype=np.int32)
         check(_lib.mogp_predict_deriv(self._h, dptr(testing), m, dptr(deriv), iptr(status)), "mogp_predict_deriv")
         return deriv, status
+
+    def predict_cov(self, idx, testing, include_nugget=True):
+        testing = as_f64(testing)
+        m = testing.shape[0]
+        mean = np.empty(m)
+        cov = np.empty((m, m))
+        check(_lib.mogp_predict_cov(self._h, int(idx), dptr(testing), m, int(bool(include_nugget)), dptr(mean), dptr(cov)),
+              "mogp_predict_cov")
+        return mean, cov
 
     def predict_allgather(self, comm, testing, include_nugget, e_pad):
         testing = as_f64(testing)

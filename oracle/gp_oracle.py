@@ -374,7 +374,7 @@ class OracleGP(object):
         return partials
 
     # -- GaussianProcess.predict, GaussianProcess.py:818-927 (full_cov=False, zero mean) ---------
-    def predict(self, testing, unc=True, include_nugget=True):
+    def predict(self, testing, unc=True, include_nugget=True, full_cov=False):
         if self.theta is None:
             raise ValueError("hyperparameters have not been fit for this Gaussian Process")
         testing = np.array(testing, dtype=np.float64)
@@ -387,6 +387,12 @@ class OracleGP(object):
         if unc:
             Kinv_Ktest = cho_solve(self.L, Ktest)
             sigma_2 = np.exp(self.theta[self.D])
+            if full_cov:                                     # GaussianProcess.py:899-911 (zero mean: no R term)
+                sigma_2 = sigma_2 * kernel_f(testing, testing, self.theta[:self.D], self.kernel, self.chunked)
+                if include_nugget:
+                    sigma_2 = sigma_2 + np.eye(testing.shape[0]) * self.nugget
+                Linv_Ktest = scipy.linalg.solve_triangular(self.L, Ktest, lower=True)
+                return mu, sigma_2 - np.dot(Linv_Ktest.T, Linv_Ktest)
             if include_nugget:
                 sigma_2 = sigma_2 + self.nugget
             var = np.maximum(sigma_2 - np.sum(Ktest * Kinv_Ktest, axis=0), 0.0)

@@ -53,11 +53,12 @@ def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with
     gp.fit(theta)
     mean, var, _ = gp.predict(Xs)
     mean_nn, var_nn, _ = gp.predict(Xs, include_nugget=False)
+    _, cov_full, _ = gp.predict(Xs, full_cov=True)
     out = dict(X=X, y=y, Xs=Xs, theta=np.array(theta), kernel=kernel,
                nugget_in=np.array(nugget if not isinstance(nugget, str) else np.nan),
                nugget_type=gp.nugget_type, nugget_out=np.array(gp.nugget),
                K=gp.get_K_matrix(), L=gp.Kinv.L, Kinv_t=gp.Kinv_t, logpost=np.array(gp.current_logpost),
-               mean=mean, var=var, var_no_nugget=var_nn)
+               mean=mean, var=var, var_no_nugget=var_nn, cov_full=cov_full)
     corr, nug = prior_params(gp)
     out["prior_corr"] = corr
     out["prior_nugget"] = nug

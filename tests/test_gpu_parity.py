@@ -72,6 +72,13 @@ def test_single_output_matches_reference_golden(mogp, name):
     assert gp.predict(g["Xs"], unc=False).unc is None
     assert_allclose(gp.predict(g["Xs"], unc=False).mean, mean, rtol=1e-12, atol=1e-12 * scale)
     assert mean.shape == (g["Xs"].shape[0],) and var.shape == mean.shape and n == gp.n
+    # full predictive covariance (the CPU class's full_cov=True), not clipped
+    res = gp.predict(g["Xs"], deriv=False, full_cov=True)
+    m = g["Xs"].shape[0]
+    assert res.unc.shape == (m, m)
+    assert_allclose(res.unc, g["cov_full"], rtol=1e-4, atol=1e-4 * max(nug, 1e-8))
+    assert_allclose(res.unc, res.unc.T, rtol=0, atol=0)
+    assert_allclose(res.mean, g["mean"], rtol=1e-6, atol=1e-6 * scale)
 
 
 @pytest.mark.parametrize("name", MULTI)
@@ -401,4 +408,30 @@ def test_more_outputs_than_one_launch_group(mogp):
         ref = orc.OracleGP(X, Y[i], nugget=1e-6)
         want = ref.logpost_deriv(thetas[i])
         assert_allclose(got[i][1], want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
+    mo.close()
+
+
+def test_full_cov_at_size(mogp):
+    """predict(full_cov=True) beyond one tile in both directions (n=700, m=300): against the oracle, diagonal equal to
+    the un-clipped pointwise variance, positive semi-definite up to rounding; multi-output shape (E, m, m)."""
+    X, Y, Xs = orc.make_workload(700, 4, 2, 300, seed=31)
+    theta = np.array([0.8, 1.1, 0.9, 1.0, 0.1])
+    gp = mogp.GaussianProcessGPU(X, Y[0], kernel="Matern52", nugget=1e-5)
+    gp.fit(theta)
+    res = gp.predict(Xs, deriv=False, full_cov=True)
+    ref = orc.OracleGP(X, Y[0], kernel="Matern52", nugget=1e-5).fit(theta)
+    rmean, rcov = ref.predict(Xs, full_cov=True)
+    assert_allclose(res.unc, rcov, rtol=1e-4, atol=1e-9)
+    assert_allclose(res.mean, rmean, rtol=1e-6, atol=1e-8)
+    pointwise = gp.predict(Xs, deriv=False).unc
+    assert_allclose(np.diag(res.unc), pointwise, rtol=1e-9, atol=1e-12)
+    assert np.linalg.eigvalsh(res.unc).min() > -1e-9
+    nn = gp.predict(Xs, deriv=False, full_cov=True, include_nugget=False).unc
+    assert_allclose(res.unc - nn, 1e-5 * np.eye(300), rtol=0, atol=1e-12)
+    gp.close()
+    mo = mogp.MultiOutputGP_GPU(X, Y, kernel="Matern52", nugget=1e-5)
+    mo.fit_emulator(0, theta)
+    r = mo.predict(Xs, deriv=False, full_cov=True, allow_not_fit=True)
+    assert r.unc.shape == (2, 300, 300) and np.all(np.isnan(r.unc[1]))
+    assert_allclose(r.unc[0], res.unc, rtol=1e-12, atol=1e-14)
     mo.close()

@@ -93,6 +93,9 @@ def test_oracle_matches_reference_golden_single(name):
     assert_allclose(var, g["var"], rtol=1e-4, atol=1e-4 * nug + 1e-10)
     _, var_nn = gp.predict(g["Xs"], include_nugget=False)
     assert_allclose(var_nn, g["var_no_nugget"], rtol=1e-4, atol=1e-4 * nug + 1e-10)
+    mean_fc, cov = gp.predict(g["Xs"], full_cov=True)
+    assert_allclose(cov, g["cov_full"], rtol=1e-4, atol=1e-4 * nug + 1e-10)
+    assert_allclose(mean_fc, g["mean"], rtol=1e-6, atol=1e-9)
     if "deriv" in g:
         assert_allclose(gp.logpost_deriv(g["theta"]), g["deriv"], rtol=1e-6, atol=1e-6)
 
