@@ -280,10 +280,11 @@ class OracleGP(object):
     produced by default_priors().
     """
 
-    def __init__(self, inputs, targets, kernel=SQEXP, nugget="adaptive", priors=None, chunked=False):
+    def __init__(self, inputs, targets, kernel=SQEXP, nugget="adaptive", priors=None, chunked=False, mean=None):
         self.inputs = np.array(inputs, dtype=np.float64)
         if self.inputs.ndim == 1:
             self.inputs = self.inputs.reshape(-1, 1)
+        self.mean = mean
         self.targets = np.array(targets, dtype=np.float64)
         assert self.targets.ndim == 1 and self.targets.shape[0] == self.inputs.shape[0]
         self.n, self.D = self.inputs.shape
@@ -306,6 +307,20 @@ class OracleGP(object):
         self.L = None
         self.Kinv_t = None
         self.current_logpost = None
+
+    # -- GaussianProcess.get_design_matrix, GaussianProcess.py:485-514: zero mean (no columns) or the constant mean;
+    #    formula means need patsy and are out of scope.  Mean priors are the reference's default (weak) ones.
+    def get_design_matrix(self, inputs):
+        inputs = np.atleast_2d(np.asarray(inputs, dtype=np.float64))
+        if self.mean is None or self.mean in ("0", "-1"):
+            return np.zeros((inputs.shape[0], 0))
+        if self.mean in ("1", "-0"):
+            return np.ones((inputs.shape[0], 1))
+        raise ValueError("only the zero and the constant mean function are restated here")
+
+    @property
+    def n_mean(self):
+        return self.get_design_matrix(self.inputs[:1]).shape[1]
 
     # -- GaussianProcess.get_cov_matrix / get_K_matrix, GaussianProcess.py:517-558 ---------------
     def get_cov_matrix(self, other):
@@ -330,8 +345,25 @@ class OracleGP(object):
         if self.nugget_type == "adaptive":
             self.nugget = float(newnugget)
         self.Kinv_t = cho_solve(self.L, self.targets)
-        self.current_logpost = 0.5 * (np.dot(self.targets, self.Kinv_t) + logdet(self.L)
-                                      + self.n * np.log(2.0 * np.pi))
+        dm = self.get_design_matrix(self.inputs)
+        self.theta_mean = np.zeros(0)
+        self.Kinv_t_mean = self.Kinv_t
+        self.LA = None
+        if dm.shape[1] == 0:
+            self.current_logpost = 0.5 * (np.dot(self.targets, self.Kinv_t) + logdet(self.L)
+                                          + self.n * np.log(2.0 * np.pi))
+        else:
+            # analytic mean with weak priors (GaussianProcess.py:657-685; linalg_utils.py:5-168): m = 0, B^-1 = 0
+            self.Kinv_H = cho_solve(self.L, dm)                                   # (n, M)
+            A = np.dot(dm.T, self.Kinv_H)                                         # calc_Ainv
+            self.LA = scipy.linalg.cholesky(A, lower=True)
+            H_Kinv_t = np.dot(dm.T, self.Kinv_t)
+            self.theta_mean = cho_solve(self.LA, H_Kinv_t)                        # calc_mean_params
+            self.Kinv_t_mean = cho_solve(self.L, self.targets - np.dot(dm, self.theta_mean))
+            self.current_logpost = 0.5 * (np.dot(self.targets, self.Kinv_t)
+                                          - np.dot(H_Kinv_t, cho_solve(self.LA, H_Kinv_t))
+                                          + logdet(self.L) + logdet(self.LA)
+                                          + (self.n - dm.shape[1]) * np.log(2.0 * np.pi))
         self.current_logpost -= priors_logp(self.priors, theta[:self.D], self.nugget)
         return self
 
@@ -362,14 +394,20 @@ class OracleGP(object):
         r2 = calc_r2_chunked(self.inputs, self.inputs, self.theta[:D])
         dKdr2 = cov * calc_dKdr2(r2, self.kernel)                       # Kernel.py:133-173
         Kinv = cho_solve(self.L, np.eye(n))
-        G = Kinv - np.outer(self.Kinv_t, self.Kinv_t)
+        if self.LA is None:
+            G = Kinv - np.outer(self.Kinv_t, self.Kinv_t)
+        else:
+            # GaussianProcess.py:743-778 collected: -(t-q)^T dK (t-q) + tr(K^-1 dK) + tr(A^-1 dA), dA = -H^T K^-1 dK K^-1 H,
+            # t - q = Kinv_t_mean for weak mean priors
+            U = scipy.linalg.solve_triangular(self.LA, self.Kinv_H.T, lower=True).T      # W L_A^-T, (n, M)
+            G = Kinv - np.dot(U, U.T) - np.outer(self.Kinv_t_mean, self.Kinv_t_mean)
         for i in range(D):
             diff2 = (self.inputs[:, i][:, None] - self.inputs[:, i][None, :]) ** 2
             partials[i] = 0.5 * np.sum(G * dKdr2 * (exp_theta[i] * diff2))   # Kernel.py:487-530
         Kmat = cov * calc_K(r2, self.kernel)
         partials[D] = 0.5 * np.sum(G * Kmat)                             # GaussianProcess.py:759-767
         if self.nugget_type == "fit":                                    # GaussianProcess.py:769-778
-            partials[-1] = 0.5 * self.nugget * (np.trace(Kinv) - np.dot(self.Kinv_t, self.Kinv_t))
+            partials[-1] = 0.5 * self.nugget * np.trace(G)
         partials -= priors_dlogpdtheta(self.priors, self.theta[:D], self.nugget, self.n_params)
         return partials
 
@@ -382,20 +420,26 @@ class OracleGP(object):
             testing = testing.reshape(-1, 1) if self.D == 1 else testing.reshape(1, -1)
         assert testing.ndim == 2 and testing.shape[1] == self.D
         Ktest = self.get_cov_matrix(testing)                     # (n, m)
-        mu = np.dot(Ktest.T, self.Kinv_t)
+        dmtest = self.get_design_matrix(testing)
+        mu = np.dot(dmtest, self.theta_mean) + np.dot(Ktest.T, self.Kinv_t_mean)
         var = None
         if unc:
             Kinv_Ktest = cho_solve(self.L, Ktest)
+            extra = 0.0
+            if self.LA is not None:                              # calc_R, linalg_utils.py:132-168; GaussianProcess.py:897-920
+                R = dmtest.T - np.dot(self.get_design_matrix(self.inputs).T, Kinv_Ktest)
+                LAinv_R = scipy.linalg.solve_triangular(self.LA, R, lower=True)
+                extra = np.dot(LAinv_R.T, LAinv_R) if full_cov else np.sum(LAinv_R ** 2, axis=0)
             sigma_2 = np.exp(self.theta[self.D])
             if full_cov:                                     # GaussianProcess.py:899-911 (zero mean: no R term)
                 sigma_2 = sigma_2 * kernel_f(testing, testing, self.theta[:self.D], self.kernel, self.chunked)
                 if include_nugget:
                     sigma_2 = sigma_2 + np.eye(testing.shape[0]) * self.nugget
                 Linv_Ktest = scipy.linalg.solve_triangular(self.L, Ktest, lower=True)
-                return mu, sigma_2 - np.dot(Linv_Ktest.T, Linv_Ktest)
+                return mu, sigma_2 - np.dot(Linv_Ktest.T, Linv_Ktest) + extra
             if include_nugget:
                 sigma_2 = sigma_2 + self.nugget
-            var = np.maximum(sigma_2 - np.sum(Ktest * Kinv_Ktest, axis=0), 0.0)
+            var = np.maximum(sigma_2 - np.sum(Ktest * Kinv_Ktest, axis=0) + extra, 0.0)
         return mu, var
 
     def predict_deriv(self, testing):

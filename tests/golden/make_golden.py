@@ -42,14 +42,14 @@ def prior_params(gp):
     return np.array(corr, dtype=np.float64), np.array(nug, dtype=np.float64)
 
 
-def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with_deriv=True):
+def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with_deriv=True, mean_fn=None):
     X, Y, Xs = workload(n, d, 1, m, seed)
     y = Y[0]
     if dup_rows:
         X[1] = X[0]
         y[1] = y[0]
     kern = SquaredExponential() if kernel == "SquaredExponential" else Matern52()
-    gp = mogp.GaussianProcess(X, y, kernel=kern, nugget=nugget)
+    gp = mogp.GaussianProcess(X, y, mean=mean_fn, kernel=kern, nugget=nugget)
     gp.fit(theta)
     mean, var, _ = gp.predict(Xs)
     mean_nn, var_nn, _ = gp.predict(Xs, include_nugget=False)
@@ -59,6 +59,10 @@ def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with
                nugget_type=gp.nugget_type, nugget_out=np.array(gp.nugget),
                K=gp.get_K_matrix(), L=gp.Kinv.L, Kinv_t=gp.Kinv_t, logpost=np.array(gp.current_logpost),
                mean=mean, var=var, var_no_nugget=var_nn, cov_full=cov_full)
+    if mean_fn is not None:
+        out["mean_spec"] = mean_fn
+        out["theta_mean"] = np.array(gp.theta.mean)
+        out["Kinv_t_mean"] = gp.Kinv_t_mean
     corr, nug = prior_params(gp)
     out["prior_corr"] = corr
     out["prior_nugget"] = nug
@@ -101,5 +105,11 @@ if __name__ == "__main__":
     single_case("mat52_fit_n130_d3", 130, 3, 25, 12, "Matern52", "fit", [0.2, 0.4, 0.6, 0.3, -7.0])
     single_case("sqexp_fixed_n1_d2", 1, 2, 5, 13, "SquaredExponential", 1e-6, [0.0, 0.0, 0.0], with_deriv=False)
     single_case("sqexp_fixed_n2_d1", 2, 1, 6, 14, "SquaredExponential", 0.0, [0.5, 0.1], with_deriv=False)
+    # constant mean function with the default (weak) mean priors: analytic mean parameter.  The
+    # reference's own logpost_deriv fails for n_mean > 0 under scipy >= 1.15 (calc_A_deriv), so no gradient is stored.
+    single_case("cmean_sqexp_fixed_n170_d3", 170, 3, 30, 41, "SquaredExponential", 1e-5, [0.4, 0.9, 0.6, 0.2],
+                with_deriv=False, mean_fn="1")
+    single_case("cmean_mat52_adaptive_n140_d2", 140, 2, 25, 42, "Matern52", "adaptive", [0.7, 0.3, -0.2],
+                with_deriv=False, mean_fn="1")
     multi_case("multi_sqexp_fixed_e4_n120_d3", 120, 3, 4, 30, 20, "SquaredExponential", 1e-6, 0.5)
     multi_case("multi_mat52_adaptive_e3_n90_d2", 90, 2, 3, 17, 21, "Matern52", "adaptive", 0.5)

@@ -77,8 +77,12 @@ MULTI = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 
 @pytest.mark.parametrize("name", SINGLE)
 def test_oracle_matches_reference_golden_single(name):
     g = _load(name)
-    gp = orc.OracleGP(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
+    mean_spec = str(g["mean_spec"]) if "mean_spec" in g else None
+    gp = orc.OracleGP(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g), mean=mean_spec)
     gp.fit(g["theta"])
+    if mean_spec is not None:       # analytic mean parameter of the constant mean function
+        assert_allclose(gp.theta_mean, g["theta_mean"], rtol=1e-8)
+        assert_allclose(gp.Kinv_t_mean, g["Kinv_t_mean"], rtol=1e-7, atol=1e-9 * np.abs(g["Kinv_t_mean"]).max())
     assert_allclose(gp.get_K_matrix(), g["K"], rtol=1e-13, atol=1e-300)
     assert_allclose(gp.L, g["L"], rtol=1e-9, atol=1e-12)
     assert_allclose(gp.Kinv_t, g["Kinv_t"], rtol=1e-7, atol=1e-9)
@@ -193,3 +197,19 @@ def test_predict_deriv_vs_finite_differences():
             e[q] = h
             fd = (gp.predict(Xs + e, unc=False)[0] - gp.predict(Xs - e, unc=False)[0]) / (2 * h)
             np.testing.assert_allclose(got[:, q], fd, rtol=1e-5, atol=1e-6)
+
+
+def test_constant_mean_logpost_deriv_vs_finite_differences():
+    """With a mean function the reference's own logpost_deriv cannot run here (calc_A_deriv under scipy >= 1.15), so the
+    oracle's collected form of GaussianProcess.py:743-778 is pinned by central differences of its log-posterior (whose
+    values ARE pinned by the cmean_* goldens)."""
+    for kernel, nugget in ((orc.SQEXP, 1e-3), (orc.MAT52, "fit")):
+        X, Y, _ = orc.make_workload(70, 2, 1, 5, seed=12)
+        gp = orc.OracleGP(X, Y[0] + 3.0, kernel=kernel, nugget=nugget, mean="1")
+        theta = np.array([0.6, 0.9, 0.1] + ([-6.0] if nugget == "fit" else []))
+        got = gp.logpost_deriv(theta)
+        for i in range(theta.size):
+            e = np.zeros(theta.size)
+            e[i] = 1e-4
+            fd = (gp.logposterior(theta + e) - gp.logposterior(theta - e)) / 2e-4
+            assert_allclose(got[i], fd, rtol=1e-6, atol=1e-8)
