@@ -81,7 +81,8 @@ int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out);
 /* replaces DenseGP_GPU::predict_batch / predict_variance_batch (densegp_gpu.hpp:300-408) and
  * MultiOutputGP_GPU::predict_batch / predict_variance_batch (multioutputgp_gpu.hpp:183-228);
  * values follow the CPU GaussianProcess.predict (GaussianProcess.py:889-920): variance clipped at 0.
- * Xs: (m, d).  mean, var: (n_out, m) caller-allocated; var may be NULL when want_var == 0.
+ * Xs: (m, d).  mean, var: (n_out, m) caller-allocated; var may be NULL when want_var == 0; want_var == 2 returns the
+ * variance before the clip at 0 (the front-end adds the mean-function term first, GaussianProcess.py:913-920).
  * status: (n_out) -- MOGP_ERR_NOT_FIT rows are filled with NaN (MultiOutputGP.py:476-546). */
 int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, int32_t include_nugget,
                  double* mean, double* var, int32_t* status);
@@ -117,6 +118,21 @@ int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_param
 /* Gradients of several fitted outputs at once: grad is (count, n_params) in list order.  L^-1 of all listed outputs comes
  * from one dataflow launch. */
 int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, double* grad, int32_t n_params);
+
+/* ---- analytic mean function (the CPU GaussianProcess with a design matrix H, GaussianProcess.py:657-685, 887-920;
+ * linalg_utils.py:5-168 calc_Ainv / calc_mean_params / calc_R).  The host front-end keeps H and the n_mean x n_mean
+ * algebra; these are the device primitives it needs.  All index lists are distinct handle-local outputs. ---- */
+/* out[i] = K_i^-1 rhs[i] for fitted outputs (rhs, out: (count, n)) -- Kinv.solve(dm) */
+int mogp_solve_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* rhs, double* out);
+/* replace the stored K^-1 y of the listed outputs (used by the posterior mean, its derivative and the gradient) with
+ * alpha[i] (count, n) -- Kinv_t_mean = K^-1 (y - H beta) */
+int mogp_set_alpha_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* alpha);
+/* vectors u_q (count, n_vec, n), n_vec <= 4, with K^-1 H A^-1 H^T K^-1 = sum_q u_q u_q^T: mogp_logpost_grad_list then
+ * differentiates the mean-integrated likelihood.  Every mogp_fit of an output clears its vectors. */
+int mogp_set_mean_vectors_list(mogp_handle* h, const int32_t* idx, int32_t count, int32_t n_vec, const double* U);
+/* out[o][q][c] = sum_i k_o(x*_c, x_i) vecs[o][q][i] for every fitted output o (vecs: (n_out, n_vec, n); out: (n_out, n_vec,
+ * m), NaN rows for unfit outputs) -- H^T K^-1 K* of calc_R, without materialising K*. */
+int mogp_kstar_dot(mogp_handle* h, const double* Xs, int64_t m, const double* vecs, int32_t n_vec, double* out);
 
 /* accumulated device time per phase in ms since the last call with reset != 0:
  * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),

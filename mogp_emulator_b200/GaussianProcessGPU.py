@@ -10,6 +10,7 @@ import numpy as np
 from . import libmogp
 from .hyper import GPParams, GPPriors, make_priors
 from .kernels import SquaredExponential, Matern52, interpret_kernel
+from .meanfunc import interpret_mean, design_matrix, MeanFit
 
 
 class GPUUnavailableError(RuntimeError):
@@ -69,11 +70,8 @@ def interpret_nugget(nugget):
 
 
 def _check_mean(mean):
-    if mean is None:
-        return
-    if isinstance(mean, str) and mean.replace(" ", "") in ("0", "-1"):
-        return
-    raise ValueError("the B200 GPU emulator supports the zero mean function only (mean=None)")
+    """-> canonical mean spec (None or "1"); ValueError for formula means (see meanfunc.py)."""
+    return interpret_mean(mean)
 
 
 class GaussianProcessGPU(object):
@@ -93,12 +91,14 @@ class GaussianProcessGPU(object):
         targets = libmogp.as_f64(targets)
         assert targets.ndim == 1
         assert targets.shape[0] == inputs.shape[0]
-        _check_mean(mean)
+        self._mean_spec = _check_mean(mean)
         self._inputs = inputs
         self._targets = targets
+        self._dm = design_matrix(self._mean_spec, inputs)
+        self._meanfit = None
         self._max_batch_size = max_batch_size    # kept for signature compatibility; predict is chunked natively
         self._device = int(device)
-        self.mean = None
+        self.mean = self._mean_spec
         self.kernel_type, self.kernel = interpret_kernel(kernel)
         self._nugget_type, self._init_nugget_size = interpret_nugget(nugget)
         self._priors_arg = priors
@@ -187,6 +187,7 @@ class GaussianProcessGPU(object):
             self._handle.reset(0)
             self._theta.unset_data()
             self._logpost_data = None
+            self._meanfit = None
         else:
             self.fit(theta)
 
@@ -197,7 +198,22 @@ class GaussianProcessGPU(object):
         return self._handle.get(0, libmogp.GET_L)
 
     @property
+    def n_mean(self):
+        return self._dm.shape[1]
+
+    def get_design_matrix(self, inputs):
+        return design_matrix(self._mean_spec, inputs)
+
+    @property
     def Kinv_t(self):
+        """K^-1 (y - m), with m = 0 for the weak mean priors (GaussianProcess.py:666)."""
+        if not self._theta.data_has_been_set():
+            return None
+        return self._handle.get(0, libmogp.GET_ALPHA) if self._meanfit is None else self._Kinv_t_host
+
+    @property
+    def Kinv_t_mean(self):
+        """K^-1 (y - H beta) (GaussianProcess.py:672)."""
         if not self._theta.data_has_been_set():
             return None
         return self._handle.get(0, libmogp.GET_ALPHA)
@@ -226,6 +242,7 @@ class GaussianProcessGPU(object):
             raise RuntimeError("bad shape for hyperparameters: expected %d values, got %d" % (self.n_params, theta.size))
         quad, logdet, nug, status = self._handle.fit(0, theta)
         self.n_fit_calls = getattr(self, "n_fit_calls", 0) + 1
+        self._meanfit = None
         if status[0] != libmogp.OK:
             self._theta.unset_data()
             self._logpost_data = None
@@ -233,7 +250,19 @@ class GaussianProcessGPU(object):
                                (", even with jitter." if self.nugget_type == "adaptive" else ""))
         self._theta.set_data(theta)
         self._theta.nugget = float(nug[0])
-        self._logpost_data = 0.5 * (float(quad[0]) + float(logdet[0]) + self.n * np.log(2.0 * np.pi))
+        if self.n_mean == 0:
+            self._logpost_data = 0.5 * (float(quad[0]) + float(logdet[0]) + self.n * np.log(2.0 * np.pi))
+        else:
+            # analytic mean (GaussianProcess.py:657-685): K^-1 H on the device, the n_mean x n_mean algebra here, then the
+            # device's alpha becomes K^-1 (y - H beta) and it learns the rank-n_mean correction of the gradient
+            self._Kinv_t_host = self._handle.get(0, libmogp.GET_ALPHA)
+            W = np.column_stack([self._handle.solve_list([0], self._dm[:, q])[0] for q in range(self.n_mean)])
+            mf = MeanFit(self._dm, self._targets, self._Kinv_t_host, W, self.n)
+            self._handle.set_alpha_list([0], mf.alpha_mean)
+            self._handle.set_mean_vectors_list([0], mf.U.T[np.newaxis])
+            self._meanfit = mf
+            self._theta.mean = mf.beta.copy()
+            self._logpost_data = mf.data_logpost(float(quad[0]), float(logdet[0]), self.n)
 
     def _refit(self, theta):
         return (not self._theta.data_has_been_set()
@@ -274,12 +303,22 @@ class GaussianProcessGPU(object):
         assert testing.ndim == 2
         assert testing.shape[1] == self.D
         dmean = self._handle.predict_deriv(testing)[0][0] if deriv else None
+        mf = self._meanfit
+        mshift = 0.0 if mf is None else np.dot(self.get_design_matrix(testing), mf.beta)
+        extra = None
+        if mf is not None and unc:
+            # R^T A^-1 R, R = H*^T - H^T K^-1 K*  (GaussianProcess.py:897-920)
+            HtKinvKs = self._handle.kstar_dot(testing, mf.W.T[np.newaxis])[0]
+            extra = mf.variance_term(self.get_design_matrix(testing), HtKinvKs, full_cov=full_cov)
         if unc and full_cov:
             # the CPU class's full_cov=True (GaussianProcess.py:899-911): (m, m) covariance, not clipped
             mean1, cov = self._handle.predict_cov(0, testing, include_nugget=include_nugget)
-            return PredictResult(mean=mean1, unc=cov, deriv=dmean)
-        mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
-        return PredictResult(mean=mean[0], unc=(var[0] if unc else None), deriv=dmean)
+            return PredictResult(mean=mean1 + mshift, unc=cov if extra is None else cov + extra, deriv=dmean)
+        if extra is None:
+            mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
+            return PredictResult(mean=mean[0] + mshift, unc=(var[0] if unc else None), deriv=dmean)
+        mean, var, _ = self._handle.predict(testing, want_var=2, include_nugget=include_nugget)   # variance before the clip
+        return PredictResult(mean=mean[0] + mshift, unc=np.maximum(var[0] + extra, 0.0), deriv=dmean)
 
     def __call__(self, testing):
         return self.predict(testing, unc=False, deriv=False)[0]

@@ -97,6 +97,7 @@ struct TraceClock {
 
 using namespace mogp;
 
+constexpr int MAXM = 4;   // mean-function vectors per output (grad_max_mean())
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H, T_COUNT };
 
 struct mogp_handle {
@@ -123,6 +124,11 @@ struct mogp_handle {
     double *sync = nullptr, *normacc = nullptr;   // TRSM ticket/flag words (used as int) and running column norms
     double* csync = nullptr;                       // Cholesky ticket/progress words (used as int)
     size_t csync_cap = 0;
+    // analytic mean function (set by the host front-end after a fit, cleared by every fit of that output)
+    double* U = nullptr;                           // [E][MAXM][n_pad]: u_q with K^-1 H A^-1 H^T K^-1 = sum_q u_q u_q^T
+    std::vector<int> n_u;                          // vectors stored per output
+    double* aux = nullptr;                         // scratch for mogp_solve_list / mogp_kstar_dot
+    size_t aux_cap = 0;
     size_t XsT_cap = 0, W_cap = 0, part_cap = 0, res_cap = 0, h_res_cap = 0, h_XsT_cap = 0, sync_cap = 0, normacc_cap = 0;
     // grad workspace
     double* G = nullptr;
@@ -226,7 +232,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->sync, h->normacc, h->csync, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
+                    h->sync, h->normacc, h->csync, h->U, h->aux, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -279,6 +285,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     h->nug_type = nugget_type;
     h->nug_fixed = nugget;
     h->fitted.assign(n_out, 0);
+    h->n_u.assign(n_out, 0);
     const int64_t np = h->n_pad;
     int S = n_streams > 0 ? n_streams : 16;
     if (S > n_out) S = n_out;
@@ -467,6 +474,7 @@ int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const doubl
         else nug[i] = 0.0;
         hy[d + 1] = nug[i];
         h->fitted[o] = 0;
+        h->n_u[o] = 0;
         todo[i] = o;
         pos[o] = i;
     }
@@ -604,7 +612,7 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 if ((rc = grow(&h->normacc, &h->normacc_cap, sizeof(double) * (size_t)cnt * w_stride, h->device))) return rc;
                 if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
                                  include_nugget, np, mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms,
-                                 h->main)) {
+                                 h->main, 0, want_var == 2 ? 1 : 0)) {
                     set_error("predict_trsm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     return MOGP_ERR_CUDA;
                 }
@@ -757,6 +765,130 @@ int mogp_predict_cov(mogp_handle* h, int32_t idx, const double* Xs, int64_t m, i
     return MOGP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// primitives for the analytic mean function (GaussianProcess.py:657-685, 887-920; linalg_utils.py:5-168): the host
+// front-end does the n_mean x n_mean algebra, the device the solves and the kernel-matrix products.
+// ---------------------------------------------------------------------------------------------
+int mogp_solve_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* rhs, double* out) {
+    if (!h || !idx || count < 1 || !rhs || !out) return MOGP_ERR_ARG;
+    for (int i = 0; i < count; i++)
+        if (idx[i] < 0 || idx[i] >= h->E || !h->fitted[idx[i]]) {
+            set_error("mogp_solve_list: output %d out of range or not fit", idx[i]);
+            return idx[i] < 0 || idx[i] >= h->E ? MOGP_ERR_ARG : MOGP_ERR_NOT_FIT;
+        }
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t np = h->n_pad, n = h->n;
+    const size_t slab = (size_t)h->E * np;                 // rhs | z | solution, each [E][n_pad]; then [E][2] scalars
+    int rc;
+    if ((rc = grow(&h->aux, &h->aux_cap, sizeof(double) * (3 * slab + 2 * h->E), h->device))) return rc;
+    double *Y2 = h->aux, *z2 = h->aux + slab, *x2 = h->aux + 2 * slab, *scal2 = h->aux + 3 * slab;
+    for (int i = 0; i < count; i++) {
+        API_CUDA(cudaMemsetAsync(Y2 + (size_t)idx[i] * np, 0, sizeof(double) * np, h->main));
+        API_CUDA(cudaMemcpyAsync(Y2 + (size_t)idx[i] * np, rhs + (size_t)i * n, sizeof(double) * n, cudaMemcpyHostToDevice, h->main));
+    }
+    for (int g0 = 0; g0 < count; g0 += MAXG) {
+        const int cnt = std::min(MAXG, count - g0);
+        int rs = solve_alpha(h->A, np, h->Dinv, Y2, z2, x2, scal2, h->info, idx + g0, cnt, h->n_sms, h->main);
+        if (rs) {
+            set_error("solve launch failed");
+            return MOGP_ERR_CUDA;
+        }
+        h->timings[T_NLAUNCH] += 1;
+    }
+    API_CUDA(cudaStreamSynchronize(h->main));
+    for (int i = 0; i < count; i++)
+        API_CUDA(cudaMemcpy(out + (size_t)i * n, x2 + (size_t)idx[i] * np, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return MOGP_OK;
+}
+
+int mogp_set_alpha_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* alpha) {
+    if (!h || !idx || count < 1 || !alpha) return MOGP_ERR_ARG;
+    API_CUDA(cudaSetDevice(h->device));
+    for (int i = 0; i < count; i++) {
+        if (idx[i] < 0 || idx[i] >= h->E) return MOGP_ERR_ARG;
+        API_CUDA(cudaMemcpy(h->alpha + (size_t)idx[i] * h->n_pad, alpha + (size_t)i * h->n, sizeof(double) * h->n,
+                            cudaMemcpyHostToDevice));
+    }
+    return MOGP_OK;
+}
+
+int mogp_set_mean_vectors_list(mogp_handle* h, const int32_t* idx, int32_t count, int32_t n_vec, const double* U) {
+    if (!h || !idx || count < 1 || n_vec < 0 || n_vec > MAXM || (n_vec > 0 && !U)) {
+        set_error("mogp_set_mean_vectors: at most %d vectors per output", MAXM);
+        return MOGP_ERR_ARG;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t np = h->n_pad;
+    if (!h->U) {
+        h->U = (double*)pool_alloc(sizeof(double) * (size_t)h->E * MAXM * np, h->device);
+        if (!h->U) return MOGP_ERR_NOMEM;
+        API_CUDA(cudaMemset(h->U, 0, sizeof(double) * (size_t)h->E * MAXM * np));
+    }
+    for (int i = 0; i < count; i++) {
+        if (idx[i] < 0 || idx[i] >= h->E) return MOGP_ERR_ARG;
+        for (int q = 0; q < n_vec; q++)
+            API_CUDA(cudaMemcpy(h->U + ((size_t)idx[i] * MAXM + q) * np, U + ((size_t)i * n_vec + q) * h->n, sizeof(double) * h->n,
+                                cudaMemcpyHostToDevice));
+        h->n_u[idx[i]] = n_vec;
+    }
+    return MOGP_OK;
+}
+
+int mogp_kstar_dot(mogp_handle* h, const double* Xs, int64_t m, const double* vecs, int32_t n_vec, double* out) {
+    if (!h || !Xs || m < 1 || !vecs || n_vec < 1 || !out) return MOGP_ERR_ARG;
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t np = h->n_pad, n = h->n;
+    const int d = h->d, E = h->E;
+    const int n_tiles = (int)(np / 128);
+    const int64_t w_stride = round_up(m, 128);
+    std::vector<int> fit_idx;
+    for (int o = 0; o < E; o++)
+        if (h->fitted[o]) fit_idx.push_back(o);
+    const double qnan = std::numeric_limits<double>::quiet_NaN();
+    std::fill(out, out + (size_t)E * n_vec * m, qnan);
+    if (fit_idx.empty()) return MOGP_OK;
+    int rc;
+    // aux: vectors [E][n_vec][n_pad] | results [E][n_vec][m]
+    const size_t vbytes = sizeof(double) * (size_t)E * n_vec * np, rbytes = sizeof(double) * (size_t)E * n_vec * m;
+    if ((rc = grow(&h->aux, &h->aux_cap, vbytes + rbytes, h->device))) return rc;
+    double* V = h->aux;
+    double* R = h->aux + (size_t)E * n_vec * np;
+    API_CUDA(cudaMemsetAsync(V, 0, vbytes, h->main));
+    API_CUDA(cudaMemcpy2DAsync(V, sizeof(double) * np, vecs, sizeof(double) * n, sizeof(double) * n, (size_t)E * n_vec,
+                               cudaMemcpyHostToDevice, h->main));
+    if ((rc = grow(&h->XsT, &h->XsT_cap, sizeof(double) * d * w_stride, h->device))) return rc;
+    if ((rc = grow(&h->h_XsT, &h->h_XsT_cap, sizeof(double) * d * w_stride, -1))) return rc;
+    if ((rc = grow(&h->part, &h->part_cap, sizeof(double) * (size_t)std::min<size_t>(fit_idx.size(), MAXG) * n_tiles * w_stride,
+                   h->device)))
+        return rc;
+    memset(h->h_XsT, 0, sizeof(double) * d * w_stride);
+    for (int64_t i = 0; i < m; i++)
+        for (int k = 0; k < d; k++) h->h_XsT[(size_t)k * w_stride + i] = Xs[i * d + k];
+    API_CUDA(cudaMemcpyAsync(h->XsT, h->h_XsT, sizeof(double) * d * w_stride, cudaMemcpyHostToDevice, h->main));
+    CUtensorMap tmXsT;
+    if (make_2d_tmap(&tmXsT, h->XsT, d, w_stride, w_stride, kmat_dbox(d), 128)) {
+        set_error("tensor map (XsT) failed");
+        return MOGP_ERR_CUDA;
+    }
+    for (size_t g0 = 0; g0 < fit_idx.size(); g0 += MAXG) {
+        const int cnt = (int)std::min<size_t>(MAXG, fit_idx.size() - g0);
+        for (int q = 0; q < n_vec; q++) {
+            // K*^T v_q without storing K*: the fused partial dots of the kernel-matrix kernel, vector q of every output
+            if (kmat_cross(tmXsT, h->tmXT, h->kernel, n, np, w_stride, d, fit_idx.data() + g0, cnt, h->hyper, nullptr, w_stride, 0,
+                           V + (size_t)q * np, (int64_t)n_vec * np, h->part, h->main) ||
+                mean_reduce(h->part, fit_idx.data() + g0, cnt, n_tiles, w_stride, m, R + (size_t)q * m, (int64_t)n_vec * m, h->main)) {
+                set_error("kstar_dot launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MOGP_ERR_CUDA;
+            }
+            h->timings[T_NLAUNCH] += 2;
+        }
+    }
+    API_CUDA(cudaStreamSynchronize(h->main));
+    for (int o : fit_idx)
+        API_CUDA(cudaMemcpy(out + (size_t)o * n_vec * m, R + (size_t)o * n_vec * m, sizeof(double) * n_vec * m, cudaMemcpyDeviceToHost));
+    return MOGP_OK;
+}
+
 int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
     if (!h || idx < 0 || idx >= h->E || !out) return MOGP_ERR_ARG;
     if (!h->fitted[idx]) {
@@ -877,7 +1009,8 @@ int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, do
             }
             const int o = outs[k];
             if (grad_reduce_tiles(tmW128, tmW64, h->kernel, h->XT, h->n, np, d, h->alpha + (size_t)o * np,
-                                  h->hyper + (size_t)o * (d + 2), h->nug_type == MOGP_NUG_FIT, part, gdev, h->main)) {
+                                  h->hyper + (size_t)o * (d + 2), h->nug_type == MOGP_NUG_FIT, part, gdev,
+                                  h->n_u[o] ? h->U + (size_t)o * MAXM * np : nullptr, h->n_u[o], np, h->main)) {
                 set_error("gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return MOGP_ERR_CUDA;
             }

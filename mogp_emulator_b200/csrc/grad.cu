@@ -23,7 +23,8 @@ namespace mogp {
 constexpr int G_BM = 128, G_BN = 64, G_NS = 4, G_NCW = 4;
 constexpr int G_A_BYTES = G_BM * KC * 8, G_B_BYTES = G_BN * KC * 8, G_STAGE = G_A_BYTES + G_B_BYTES;
 constexpr int G_MAXD = 64;  // X tiles of all dims are parked in the (idle) ring during the epilogue
-constexpr int G_SMEM = G_NS * G_STAGE + 2 * G_NS * 8 + 128 + (G_BM + G_BN) * 8 + 32 * 8 * G_NCW + G_MAXD * 8;
+constexpr int G_MAXM = 4;   // mean-function vectors u_q (G -= sum_q u_q u_q^T), see mogp_set_mean_vectors
+constexpr int G_SMEM = G_NS * G_STAGE + 2 * G_NS * 8 + 128 + (G_BM + G_BN) * 8 * (1 + G_MAXM) + 32 * 8 * G_NCW + G_MAXD * 8;
 constexpr int G_DCH = 8;    // parameters reduced per epilogue pass
 
 struct GradParams {
@@ -34,6 +35,9 @@ struct GradParams {
     int64_t n, n_pad;
     int d, kernel;
     int row_base;         // first row of Wt inside its tensor map (0)
+    const double* U;      // [n_u][u_stride] mean-function vectors of this output (or null)
+    int n_u;
+    int64_t u_stride;
     // MODE 1 (full predictive covariance): C (lower 128x64 tiles, row stride ldc) -= W_I . W_J^T over k_chunks chunks
     double* C;
     int64_t ldc;
@@ -62,7 +66,8 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = full + G_NS;
     double* al_r = reinterpret_cast<double*>(empty + G_NS);  // [128]
     double* al_c = al_r + G_BM;                               // [64]
-    double* red = al_c + G_BN;                                // [G_NCW][32]
+    double* u_rc = al_c + G_BN;                               // [G_MAXM][128 + 64]
+    double* red = u_rc + G_MAXM * (G_BM + G_BN);              // [G_NCW][32]
     double* w_s = red + 32 * G_NCW;                           // [G_MAXD] exp(theta_i)
     double* Xs = reinterpret_cast<double*>(base);            // epilogue: [d][192] (rows then cols), aliases the ring
 
@@ -88,6 +93,10 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (MODE == 0) {
         for (int i = threadIdx.x; i < G_BM + G_BN; i += blockDim.x)
             al_r[i] = (i < G_BM) ? p.alpha[row0 + i] : p.alpha[col0 + i - G_BM];
+        for (int i = threadIdx.x; i < p.n_u * (G_BM + G_BN); i += blockDim.x) {
+            const int q = i / (G_BM + G_BN), k = i - q * (G_BM + G_BN);
+            u_rc[i] = p.U[(int64_t)q * p.u_stride + ((k < G_BM) ? row0 + k : col0 + k - G_BM)];
+        }
         for (int i = threadIdx.x; i < G_MAXD; i += blockDim.x) w_s[i] = (i < p.d) ? p.hyper[i] : 0.0;
     }
     __syncthreads();
@@ -179,7 +188,9 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 double kv, dk;
                 kval_and_deriv<KT>(r2, kv, dk);
                 const double kinv = acc[mt][nt][e];
-                const double G = kinv - al_r[rl] * al_c[cl];
+                double G = kinv - al_r[rl] * al_c[cl];
+                for (int q = 0; q < p.n_u; q++)    // analytic mean function: K^-1 -> K^-1 - K^-1 H A^-1 H^T K^-1
+                    G = fma(-u_rc[q * (G_BM + G_BN) + rl], u_rc[q * (G_BM + G_BN) + G_BM + cl], G);
                 s_cov = fma(w * G, sigma2 * kv, s_cov);
                 if (k == j && j < p.n) s_tr += kinv;
                 acc[mt][nt][e] = w * G * sigma2 * dk;
@@ -232,16 +243,20 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-// grad[i] = 0.5 * sum_tiles partial[tile][i]; fitted nugget: 0.5 * nugget * (tr K^-1 - alpha^T alpha)
+// grad[i] = 0.5 * sum_tiles partial[tile][i]; fitted nugget: 0.5 * nugget * (tr K^-1 - alpha^T alpha - sum_q u_q^T u_q)
 __global__ void grad_reduce_kernel(const double* __restrict__ partial, int tiles, int d, const double* __restrict__ alpha,
-                                   int64_t n, const double* __restrict__ hyper, int fit_nugget, double* __restrict__ grad) {
+                                   int64_t n, const double* __restrict__ hyper, int fit_nugget, double* __restrict__ grad,
+                                   const double* __restrict__ U, int n_u, int64_t u_stride) {
     __shared__ double sh[256];
     const int i = blockIdx.x;  // 0..d+1
     double s = 0.0;
     for (int tI = threadIdx.x; tI < tiles; tI += 256) s += partial[(int64_t)tI * (d + 2) + i];
     double aa = 0.0;
     if (i == d + 1)
-        for (int64_t r = threadIdx.x; r < n; r += 256) aa = fma(alpha[r], alpha[r], aa);
+        for (int64_t r = threadIdx.x; r < n; r += 256) {
+            aa = fma(alpha[r], alpha[r], aa);
+            for (int q = 0; q < n_u; q++) aa = fma(U[q * u_stride + r], U[q * u_stride + r], aa);
+        }
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -279,6 +294,7 @@ int grad_init() {
 }
 
 int grad_max_dims() { return G_MAXD; }
+int grad_max_mean() { return G_MAXM; }
 
 int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st) {
     const int64_t total = n_pad * n_pad;
@@ -289,8 +305,10 @@ int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st) {
 // Wt: (L^-1)^T, row-major n_pad x n_pad; partial: [T(T+1)][d+2] scratch; grad: device [d+2]
 int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int kernel, const double* XT, int64_t n,
                       int64_t n_pad, int d, const double* alpha, const double* hyper, int fit_nugget, double* partial,
-                      double* grad, cudaStream_t st) {
+                      double* grad, const double* U, int n_u, int64_t u_stride, cudaStream_t st) {
+    if (n_u > G_MAXM) return 1;
     GradParams p{};
+    p.U = U; p.n_u = n_u; p.u_stride = u_stride;
     p.XT = XT; p.alpha = alpha; p.hyper = hyper; p.partial = partial; p.n = n; p.n_pad = n_pad; p.d = d; p.kernel = kernel;
     p.row_base = 0;
     const int T = (int)(n_pad / NB);
@@ -299,7 +317,7 @@ int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int k
         grad_tile_kernel<MOGP_KERNEL_SQEXP, 0><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
     else
         grad_tile_kernel<MOGP_KERNEL_MATERN52, 0><<<tiles, (G_NCW + 4) * 32, G_SMEM, st>>>(tmW128, tmW64, p);
-    grad_reduce_kernel<<<d + 2, 256, 0, st>>>(partial, tiles, d, alpha, n, hyper, fit_nugget, grad);
+    grad_reduce_kernel<<<d + 2, 256, 0, st>>>(partial, tiles, d, alpha, n, hyper, fit_nugget, grad, U, n_u, u_stride);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

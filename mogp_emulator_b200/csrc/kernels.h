@@ -60,7 +60,7 @@ size_t predict_sync_bytes(const TrsmPlan& plan, int count, int T);
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
                  int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, int* sync, double* normacc,
-                 int n_sms, cudaStream_t st, int keep_v = 0);
+                 int n_sms, cudaStream_t st, int keep_v = 0, int no_clip = 0);
 
 // ---- grad.cu ----
 int grad_init();
@@ -68,7 +68,8 @@ int grad_max_dims();
 int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st);
 int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int kernel, const double* XT, int64_t n,
                       int64_t n_pad, int d, const double* alpha, const double* hyper, int fit_nugget, double* partial,
-                      double* grad, cudaStream_t st);
+                      double* grad, const double* U, int n_u, int64_t u_stride, cudaStream_t st);
+int grad_max_mean();
 
 int cov_syrk_sub(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int row_base, int64_t m_pad, int64_t k_len, double* C,
                  cudaStream_t st);

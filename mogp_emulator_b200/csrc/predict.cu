@@ -50,6 +50,7 @@ struct PredParams {
     int d;
     int include_nugget;
     int tri_rhs;            // right-hand side is the identity: panel c0 starts its walk at block row c0/128
+    int no_clip;            // write sigma2 [+ nugget] - ||V_c||^2 without the max(., 0) (the caller adds the mean-function term first)
     int keep_v;             // also store the last block row of V (full predictive covariance needs all of V)
     double* var;            // result rows: var of output o at var + o*var_stride
     int64_t var_stride;
@@ -290,7 +291,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
                     const int o = p.outs[o_local];
                     const double* hyp = p.hyper + (int64_t)o * p.hyper_stride;
                     const double top = hyp[p.d] + (p.include_nugget ? hyp[p.d + 1] : 0.0);
-                    p.var[(int64_t)o * p.var_stride + cg] = fmax(top - nrm, 0.0);
+                    p.var[(int64_t)o * p.var_stride + cg] = p.no_clip ? (top - nrm) : fmax(top - nrm, 0.0);
                 }
             }
         }
@@ -375,9 +376,10 @@ TrsmPlan predict_plan_square(int64_t n_pad, int n_sms) {
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
                  int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, int* sync, double* normacc,
-                 int n_sms, cudaStream_t st, int keep_v) {
+                 int n_sms, cudaStream_t st, int keep_v, int no_clip) {
     PredParams p{};
     p.keep_v = keep_v;
+    p.no_clip = no_clip;
     p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m; p.T = (int)(n_pad / NB);
     p.panels = plan.panels; p.count = count;
     for (int i = 0; i < count; i++) p.outs[i] = outs[i];

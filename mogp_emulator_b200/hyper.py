@@ -5,7 +5,8 @@ Scalar support code for the hot path (never on the GPU): the raw <-> scaled tran
 terms that enter ``current_logpost`` and its gradient (mogp_emulator/Priors.py:86-152, 291-418, 583-1188;
 C++ twin mogp_gpu/src/gppriors.hpp).  Raw layout: ``[theta_corr (D), theta_cov, (theta_nugget)]`` with
 correlation length ``l = exp(-theta/2)``, ``sigma^2 = exp(theta_cov)``, ``nugget = exp(theta_nugget)``.
-Mean functions are out of scope (zero mean), so ``n_mean`` is always 0.
+Mean parameters are integrated out analytically (meanfunc.py), never part of the hyperparameter vector, so ``n_mean``
+(the reference GPU binding's count of mean entries inside theta) is always 0; ``mean`` holds the fitted coefficients.
 """
 import numpy as np
 import scipy.stats
@@ -65,6 +66,7 @@ class GPParams(object):
     def __init__(self, n_corr, nugget_type, nugget=None):
         assert nugget_type in ("adaptive", "fit", "fixed")
         self.n_mean = 0
+        self.mean = np.zeros(0)          # analytic mean coefficients of the last fit (GaussianProcess.py:670-671)
         self.n_corr = int(n_corr)
         self.nugget_type = nugget_type
         self._nugget = None if nugget_type != "fixed" else float(nugget)
@@ -103,6 +105,7 @@ class GPParams(object):
         """Reference GPU semantics: data zeroed, flag cleared (gpparams.hpp:217-221)."""
         self._data = np.zeros(self.n_data)
         self._set = False
+        self.mean = np.zeros(0)
         if self.nugget_type != "fixed":
             self._nugget = None
 
@@ -287,7 +290,7 @@ class GPPriors(object):
 
     def __init__(self, corr=None, cov=None, nugget=None, n_corr=None, nugget_type="fit", mean=None):
         if mean is not None:
-            raise ValueError("mean-function priors are not supported by the GPU emulator (zero mean only)")
+            raise ValueError("informative mean-function priors are not supported by the GPU emulator (weak priors only)")
         assert nugget_type in ("adaptive", "fit", "fixed"), "Bad value for nugget type in GPPriors"
         if corr is None:
             assert n_corr is not None and n_corr > 0, "need n_corr when no correlation priors are given"

@@ -49,6 +49,10 @@ SIGNATURES = {
     "mogp_fit_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, _c_double_p, ctypes.c_int32,
                                      _c_double_p, _c_double_p, _c_double_p, _c_int_p]),
     "mogp_logpost_grad_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, _c_double_p, ctypes.c_int32]),
+    "mogp_solve_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, _c_double_p, _c_double_p]),
+    "mogp_set_alpha_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, _c_double_p]),
+    "mogp_set_mean_vectors_list": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, ctypes.c_int32, ctypes.c_int32, _c_double_p]),
+    "mogp_kstar_dot": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, _c_double_p, ctypes.c_int32, _c_double_p]),
     "mogp_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mogp_is_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_int_p]),
     "mogp_predict": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
@@ -210,6 +214,36 @@ class Handle(object):
         check(_lib.mogp_logpost_grad_list(self._h, iptr(idx), len(idx), dptr(out), int(n_params)), "mogp_logpost_grad_list")
         return out
 
+    # -- primitives of the analytic mean function ------------------------------------------------------
+    def solve_list(self, indices, rhs):
+        """K_i^-1 rhs[i] for the listed fitted outputs; rhs (count, n)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        rhs = as_f64(rhs).reshape(len(idx), self.n)
+        out = np.empty_like(rhs)
+        check(_lib.mogp_solve_list(self._h, iptr(idx), len(idx), dptr(rhs), dptr(out)), "mogp_solve_list")
+        return out
+
+    def set_alpha_list(self, indices, alpha):
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        alpha = as_f64(alpha).reshape(len(idx), self.n)
+        check(_lib.mogp_set_alpha_list(self._h, iptr(idx), len(idx), dptr(alpha)), "mogp_set_alpha_list")
+
+    def set_mean_vectors_list(self, indices, U):
+        """U: (count, n_vec, n)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        U = as_f64(U)
+        n_vec = U.shape[1]
+        check(_lib.mogp_set_mean_vectors_list(self._h, iptr(idx), len(idx), int(n_vec), dptr(U)), "mogp_set_mean_vectors_list")
+
+    def kstar_dot(self, testing, vecs):
+        """vecs (n_out, n_vec, n) -> (n_out, n_vec, m): k_o(X*, X) vecs[o][q] for every fitted output."""
+        testing = as_f64(testing)
+        vecs = as_f64(vecs).reshape(self.n_out, -1, self.n)
+        out = np.empty((self.n_out, vecs.shape[1], testing.shape[0]))
+        check(_lib.mogp_kstar_dot(self._h, dptr(testing), testing.shape[0], dptr(vecs), int(vecs.shape[1]), dptr(out)),
+              "mogp_kstar_dot")
+        return out
+
     def reset(self, idx=-1):
         check(_lib.mogp_reset(self._h, int(idx)))
 
@@ -224,7 +258,7 @@ class Handle(object):
         mean = np.empty((self.n_out, m))
         var = np.empty((self.n_out, m)) if want_var else None
         status = np.zeros(self.n_out, dtype=np.int32)
-        check(_lib.mogp_predict(self._h, dptr(testing), m, int(bool(want_var)), int(bool(include_nugget)), dptr(mean),
+        check(_lib.mogp_predict(self._h, dptr(testing), m, int(want_var) if want_var in (0, 1, 2) else 1, int(bool(include_nugget)), dptr(mean),
                                 dptr(var) if want_var else None, iptr(status)), "mogp_predict")
         return mean, var, status
 

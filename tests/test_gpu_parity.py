@@ -51,9 +51,13 @@ def _nugget_arg(g):
 @pytest.mark.parametrize("name", SINGLE)
 def test_single_output_matches_reference_golden(mogp, name):
     g = _load(name)
-    gp = mogp.GaussianProcessGPU(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
+    mean_spec = str(g["mean_spec"]) if "mean_spec" in g else None
+    gp = mogp.GaussianProcessGPU(g["X"], g["y"], mean=mean_spec, kernel=str(g["kernel"]), nugget=_nugget_arg(g))
     gp.fit(g["theta"])
     n = g["X"].shape[0]
+    if mean_spec is not None:      # constant mean function: analytic coefficient (GaussianProcess.py:670-672)
+        assert_allclose(gp.theta.mean, g["theta_mean"], rtol=1e-7)
+        assert_allclose(gp.Kinv_t_mean, g["Kinv_t_mean"], rtol=1e-6, atol=1e-6 * np.abs(g["Kinv_t_mean"]).max())
     # kernel matrix (no nugget), factor, alpha, log-posterior with the reference's default priors
     assert_allclose(gp.get_K_matrix(), g["K"], rtol=1e-13, atol=1e-15)
     nug = float(g["nugget_out"])
@@ -190,7 +194,7 @@ def test_multi_output_not_fit_semantics(mogp):
         gp.fit(np.zeros((4, 7)))
 
 
-@pytest.mark.parametrize("name", [s for s in SINGLE if "n1_" not in s and "n2_" not in s])
+@pytest.mark.parametrize("name", [s for s in SINGLE if "n1_" not in s and "n2_" not in s and not s.startswith("cmean_")])
 def test_logpost_deriv_matches_reference_golden(mogp, name):
     g = _load(name)
     gp = mogp.GaussianProcessGPU(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
@@ -435,3 +439,37 @@ def test_full_cov_at_size(mogp):
     assert r.unc.shape == (2, 300, 300) and np.all(np.isnan(r.unc[1]))
     assert_allclose(r.unc[0], res.unc, rtol=1e-12, atol=1e-14)
     mo.close()
+
+
+@pytest.mark.parametrize("kernel,nugget", [("SquaredExponential", 1e-4), ("Matern52", "fit")])
+def test_constant_mean_gradient_and_map(mogp, kernel, nugget):
+    """Constant mean function: log-posterior and its gradient (rank-1 corrected K^-1 on the device) against the oracle
+    (whose values are pinned by the cmean_* goldens and whose gradient is pinned by finite differences), variance clipped
+    after the mean-function term, and a MAP fit that lands where the CPU optimiser lands."""
+    from scipy.optimize import minimize
+    X, Y, Xs = orc.make_workload(220, 3, 1, 60, seed=33)
+    y = Y[0] + 2.5
+    theta = np.array([0.6, 0.9, 0.3, 0.1] + ([-7.0] if nugget == "fit" else []))
+    gp = mogp.GaussianProcessGPU(X, y, mean="1", kernel=kernel, nugget=nugget)
+    ref = orc.OracleGP(X, y, mean="1", kernel=kernel, nugget=nugget)
+    assert_allclose(gp.logposterior(theta), ref.logposterior(theta), rtol=1e-9)
+    want = ref.logpost_deriv(theta)
+    assert_allclose(gp.logpost_deriv(theta), want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
+    assert_allclose(gp.theta.mean, ref.theta_mean, rtol=1e-8)
+    res = gp.predict(Xs)
+    rmean, rvar = ref.predict(Xs)
+    assert_allclose(res.mean, rmean, rtol=1e-6, atol=1e-8)
+    assert_allclose(res.unc, rvar, rtol=1e-4, atol=1e-4 * ref.nugget)
+    _, rcov = ref.predict(Xs, full_cov=True)
+    assert_allclose(gp.predict(Xs, deriv=False, full_cov=True).unc, rcov, rtol=1e-4, atol=1e-4 * ref.nugget)
+    h = 1e-5
+    e = np.array([h, 0.0, 0.0])
+    fd = (gp.predict(Xs + e, unc=False, deriv=False).mean - gp.predict(Xs - e, unc=False, deriv=False).mean) / (2 * h)
+    assert_allclose(res.deriv[:, 0], fd, rtol=2e-4, atol=2e-4 * np.abs(fd).max())
+    theta0 = np.zeros(theta.size)
+    if nugget == "fit":
+        theta0[-1] = -6.0
+    rr = minimize(ref.logposterior, theta0, method="L-BFGS-B", jac=ref.logpost_deriv)
+    gp = mogp.fit_GP_MAP(gp, n_tries=1, theta0=theta0)
+    assert_allclose(gp.current_logpost, rr["fun"], rtol=1e-6)
+    gp.close()

@@ -40,7 +40,8 @@ def test_prior_terms_reproduce_reference_logpost(path):
     g = np.load(path)
     ntype = str(g["nugget_type"])
     nug = float(g["nugget_in"]) if ntype == "fixed" else ntype
-    ref = orc.OracleGP(g["X"], g["y"], kernel=str(g["kernel"]), nugget=nug, priors="weak").fit(g["theta"])
+    mean_spec = str(g["mean_spec"]) if "mean_spec" in g.files else None
+    ref = orc.OracleGP(g["X"], g["y"], kernel=str(g["kernel"]), nugget=nug, priors="weak", mean=mean_spec).fit(g["theta"])
     D = g["X"].shape[1]
     theta = hyper.GPParams(D, ntype, float(g["nugget_in"]) if ntype == "fixed" else None)
     theta.set_data(g["theta"])
