@@ -13,6 +13,7 @@ from . import libmogp
 from .GaussianProcessGPU import PredictResult, GPUUnavailableError, _check_mean
 from .hyper import GPParams, GPPriors, make_priors
 from .kernels import interpret_kernel
+from .meanfunc import design_matrix, MeanFit
 from .sharding import shard_bounds
 
 
@@ -50,9 +51,13 @@ class MultiOutputGP_GPU(object):
             nugtype, nugsize = libmogp.nugget_type.fixed, float(nugget)
         else:
             raise TypeError("nugget parameter must be a string or a non-negative float")
-        _check_mean(mean)
+        self._mean_spec = _check_mean(mean)      # one mean function shared by all emulators: None or the constant "1"
         self._inputs = np.ascontiguousarray(inputs)
         self._targets = np.ascontiguousarray(targets)
+        self._dm = design_matrix(self._mean_spec, self._inputs)
+        if comm is not None and self._dm.shape[1] > 0:
+            raise ValueError("a mean function is not supported together with a communicator (sharded predict gathers "
+                             "zero-mean posteriors)")
         self._nugget_type = nugtype
         self._nugget_size = nugsize
         self.kernel_type, self.kernel = interpret_kernel(kernel)
@@ -68,6 +73,7 @@ class MultiOutputGP_GPU(object):
                         for _ in range(E)]
         self._logpost_data = [None] * E
         self._fit = [False] * E
+        self._meanfit = [None] * E
         if isinstance(priors, (GPPriors, dict)) or priors is None:
             priorslist = E * [priors]
         else:
@@ -149,6 +155,7 @@ class MultiOutputGP_GPU(object):
         self._fit[index] = False
         self._thetas[index].unset_data()
         self._logpost_data[index] = None
+        self._meanfit[index] = None
 
     def reset_fit_status(self):
         if self._handle is not None:
@@ -157,9 +164,32 @@ class MultiOutputGP_GPU(object):
             self._fit[i] = False
             self._thetas[i].unset_data()
             self._logpost_data[i] = None
+            self._meanfit[i] = None
 
     # -- fitting (MultiOutputGP_GPU.py:309-326; CPU semantics MultiOutputGP.py:331-360) -----------------
+    def _apply_mean(self, indices, quad, logdet):
+        """Analytic mean coefficients of freshly fitted (local) emulators: one batched K^-1 H solve per design-matrix
+        column, the n_mean x n_mean algebra on the host (meanfunc.MeanFit), then the device's alpha / gradient vectors."""
+        if self._dm.shape[1] == 0 or not indices:
+            return
+        local = [i - self._lo for i in indices]
+        M = self._dm.shape[1]
+        cols = [self._handle.solve_list(local, np.tile(self._dm[:, q], (len(local), 1))) for q in range(M)]
+        alphas, Us = [], []
+        for k, i in enumerate(indices):
+            t = self._handle.get(local[k], libmogp.GET_ALPHA)
+            W = np.column_stack([cols[q][k] for q in range(M)])
+            mf = MeanFit(self._dm, self._targets[i], t, W, self.n)
+            self._meanfit[i] = mf
+            self._thetas[i].mean = mf.beta.copy()
+            self._logpost_data[i] = mf.data_logpost(float(quad[k]), float(logdet[k]), self.n)
+            alphas.append(mf.alpha_mean)
+            Us.append(mf.U.T)
+        self._handle.set_alpha_list(local, np.array(alphas))
+        self._handle.set_mean_vectors_list(local, np.array(Us))
+
     def _record(self, index, theta, quad, logdet, nug, status):
+        self._meanfit[index] = None
         if status == libmogp.OK:
             self._thetas[index].set_data(theta)
             self._thetas[index].nugget = float(nug)
@@ -184,6 +214,8 @@ class MultiOutputGP_GPU(object):
             quad, logdet, nug, status = self._handle.fit(0, thetas[self._lo:self._hi])
             for k, i in enumerate(range(self._lo, self._hi)):
                 self._record(i, thetas[i], quad[k], logdet[k], nug[k], status[k])
+            ok = [k for k in range(self._hi - self._lo) if status[k] == libmogp.OK]
+            self._apply_mean([self._lo + k for k in ok], quad[ok], logdet[ok])
 
     def fit_emulator(self, index, theta):
         theta = np.array(theta, dtype=np.float64).reshape(-1)
@@ -194,6 +226,8 @@ class MultiOutputGP_GPU(object):
         if self._lo <= index < self._hi:
             quad, logdet, nug, status = self._handle.fit(index - self._lo, theta)
             self._record(index, theta, quad[0], logdet[0], nug[0], status[0])
+            if status[0] == libmogp.OK:
+                self._apply_mean([index], quad, logdet)
 
     def logposterior(self, index, theta=None):
         """current_logpost of one (local) emulator, fitting it first when theta is given and differs."""
@@ -230,6 +264,7 @@ class MultiOutputGP_GPU(object):
             if status[k] == libmogp.OK:
                 ok.append(k)
         out = {i: None for i in indices}
+        self._apply_mean([indices[k] for k in ok], quad[ok], logdet[ok])
         if ok:
             grads = self._handle.logpost_grad_list([local[k] for k in ok], self.n_params[indices[ok[0]]])
             for row, k in enumerate(ok):
@@ -270,6 +305,8 @@ class MultiOutputGP_GPU(object):
             if not allow_not_fit and len(self.get_indices_not_fit()) > 0:
                 raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
             dmean = self._handle.predict_deriv(testing)[0] if deriv else None
+            if self._dm.shape[1] > 0:
+                return self._predict_with_mean(testing, unc, include_nugget, full_cov, dmean)
             if unc and full_cov:
                 # (E, m, m) covariances, one output at a time (MultiOutputGP.py:183, 303); NaN for unfit emulators
                 mean = np.full((E, m), np.nan)
@@ -292,6 +329,35 @@ class MultiOutputGP_GPU(object):
         if not allow_not_fit and np.any(status != libmogp.OK):
             raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
         return PredictResult(mean=mean_all[:E], unc=var_all[:E] if unc else None, deriv=None)
+
+    def _predict_with_mean(self, testing, unc, include_nugget, full_cov, dmean):
+        """Posterior with the analytic mean function (GaussianProcess.py:887-920): mean shifted by H* beta, variance plus
+        R^T A^-1 R with R = H*^T - H^T K^-1 K* (one fused kernel-matrix pass per design-matrix column), clipped last."""
+        E, m = self.n_emulators, testing.shape[0]
+        Hs = design_matrix(self._mean_spec, testing)
+        M = Hs.shape[1]
+        fit = self.get_indices_fit()
+        extra = {}
+        if unc and fit:
+            vecs = np.zeros((E, M, self.n))
+            for i in fit:
+                vecs[i] = self._meanfit[i].W.T
+            dots = self._handle.kstar_dot(testing, vecs)
+            extra = {i: self._meanfit[i].variance_term(Hs, dots[i], full_cov=full_cov) for i in fit}
+        if unc and full_cov:
+            mean = np.full((E, m), np.nan)
+            cov = np.full((E, m, m), np.nan)
+            for i in fit:
+                mean[i], cov[i] = self._handle.predict_cov(i, testing, include_nugget=include_nugget)
+                mean[i] += np.dot(Hs, self._meanfit[i].beta)
+                cov[i] += extra[i]
+            return PredictResult(mean=mean, unc=cov, deriv=dmean)
+        mean, var, _ = self._handle.predict(testing, want_var=2 if unc else 0, include_nugget=include_nugget)
+        for i in fit:
+            mean[i] += np.dot(Hs, self._meanfit[i].beta)
+            if unc:
+                var[i] = np.maximum(var[i] + extra[i], 0.0)
+        return PredictResult(mean=mean, unc=var if unc else None, deriv=dmean)
 
     def __call__(self, testing, processes=None):
         return self.predict(testing, unc=False, deriv=False, processes=processes)[0]

@@ -473,3 +473,37 @@ def test_constant_mean_gradient_and_map(mogp, kernel, nugget):
     gp = mogp.fit_GP_MAP(gp, n_tries=1, theta0=theta0)
     assert_allclose(gp.current_logpost, rr["fun"], rtol=1e-6)
     gp.close()
+
+
+def test_multi_output_constant_mean(mogp):
+    """MultiOutputGP_GPU(mean="1"): batched K^-1 H solves + host algebra per emulator; posterior, log-posterior, batched
+    gradients and the lock-step MAP fit against per-output oracles; an unfit emulator stays NaN."""
+    X, Y, Xs = orc.make_workload(180, 2, 4, 45, seed=44)
+    Y = Y + np.array([[1.0], [-2.0], [0.5], [3.0]])
+    thetas = np.array([[0.5, 0.8, 0.1], [0.9, 0.4, 0.3], [0.2, 0.2, -0.1], [1.1, 0.7, 0.0]])
+    mo = mogp.MultiOutputGP_GPU(X, Y, mean="1", nugget=1e-5)
+    for i in (0, 1, 3):
+        mo.fit_emulator(i, thetas[i])
+    r = mo.predict(Xs, allow_not_fit=True)
+    assert np.all(np.isnan(r.mean[2])) and np.all(np.isnan(r.unc[2]))
+    refs = [orc.OracleGP(X, Y[i], mean="1", nugget=1e-5).fit(thetas[i]) for i in range(4)]
+    for i in (0, 1, 3):
+        rm, rv = refs[i].predict(Xs)
+        assert_allclose(r.mean[i], rm, rtol=1e-6, atol=1e-8)
+        assert_allclose(r.unc[i], rv, rtol=1e-4, atol=1e-9)
+        assert_allclose(mo.thetas[i].mean, refs[i].theta_mean, rtol=1e-8)
+        assert_allclose(mo.logposterior(i), refs[i].current_logpost, rtol=_logpost_rtol(refs[i].get_K_matrix(), 1e-5))
+    mo.fit(thetas)
+    got = mo.logpost_and_deriv_batch([3, 0, 2], thetas[[3, 0, 2]])
+    for i in (3, 0, 2):
+        want = refs[i].logpost_deriv(thetas[i])
+        assert_allclose(got[i][1], want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
+    _, rcov = refs[1].predict(Xs, full_cov=True)
+    assert_allclose(mo.predict(Xs, deriv=False, full_cov=True).unc[1], rcov, rtol=1e-4, atol=1e-9)
+    mo.reset_fit_status()
+    mo = mogp.fit_GP_MAP(mo, n_tries=1, theta0=np.zeros(3))
+    assert mo.get_indices_not_fit() == []
+    from scipy.optimize import minimize
+    rr = minimize(refs[0].logposterior, np.zeros(3), method="L-BFGS-B", jac=refs[0].logpost_deriv)
+    assert_allclose(mo.logposterior(0), rr["fun"], rtol=1e-6)
+    mo.close()
