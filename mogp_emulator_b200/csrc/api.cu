@@ -269,9 +269,16 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
                   prop.major);
         return MOGP_ERR_CUDA;
     }
-    if (chol_init() || solve_init() || kmat_init() || predict_init() || grad_init()) {
-        set_error("kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return MOGP_ERR_CUDA;
+    {
+        // kernel attributes (opt-in shared memory, non-portable cluster size) are per device
+        static bool inited[64] = {false};
+        if (!inited[device & 63]) {
+            if (chol_init() || solve_init() || kmat_init() || predict_init() || grad_init()) {
+                set_error("kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MOGP_ERR_CUDA;
+            }
+            inited[device & 63] = true;
+        }
     }
     tc.mark("kernel attribute setup");
     mogp_handle* h = new mogp_handle();

@@ -644,13 +644,11 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     }
 }
 
+// kernel attributes are per device: called once per device by mogp_create (api.cu keeps the per-device flag)
 int chol_init() {
-    static bool done = false;
-    if (done) return 0;
     if (cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CholCfg::SMEM_BYTES) !=
         cudaSuccess)
         return 1;
-    done = true;
     return 0;
 }
 

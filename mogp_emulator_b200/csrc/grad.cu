@@ -283,13 +283,10 @@ __global__ void set_identity_kernel(double* __restrict__ W, int64_t n_pad) {
 }
 
 int grad_init() {
-    static bool done = false;
-    if (done) return 0;
     if (cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_SQEXP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_MATERN52, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_SQEXP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess)
         return 1;
-    done = true;
     return 0;
 }
 

@@ -169,7 +169,7 @@ __global__ void mean_reduce_kernel(const double* __restrict__ part, int n_tiles,
     mean[(int64_t)ol.outs[o] * mean_stride + c] = s;
 }
 
-int kmat_init() { return 0; }
+
 
 int kmat_dbox(int d) { return d < DCH ? d : DCH; }
 
@@ -302,18 +302,18 @@ __global__ void __launch_bounds__(128) kderiv_kernel(const DerivParams p) {
 
 int kderiv_max_dims() { return KD_MAXD; }
 
+int kmat_init() {
+    const int maxs = (int)(sizeof(double) * ((size_t)KD_MAXD * KD_TB + KD_TB + KD_MAXD));
+    if (cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess ||
+        cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess)
+        return 1;
+    return 0;
+}
+
 int kmat_deriv(int kernel, const double* XsT, int64_t xs_stride, const double* XT, int64_t n, int64_t n_pad, int64_t m,
                int d, const int* outs, int count, const double* hyper, const double* alpha, double* out, cudaStream_t st) {
     if (count < 1 || count > MAXG || d > KD_MAXD) return 1;
-    static bool attr_done = false;
     const size_t smem = sizeof(double) * ((size_t)d * KD_TB + KD_TB + d);
-    if (!attr_done) {
-        const int maxs = (int)(sizeof(double) * ((size_t)KD_MAXD * KD_TB + KD_TB + KD_MAXD));
-        if (cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess ||
-            cudaFuncSetAttribute(kderiv_kernel<MOGP_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs) != cudaSuccess)
-            return 1;
-        attr_done = true;
-    }
     DerivParams p{};
     p.XsT = XsT; p.xs_stride = xs_stride; p.XT = XT; p.alpha = alpha; p.hyper = hyper; p.out = out;
     p.n = n; p.n_pad = n_pad; p.m = m; p.d = d;

@@ -323,13 +323,6 @@ template <int NT>
 static int launch_pred(const TrsmPlan& plan, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                        const CUtensorMap& tmW, const PredParams& p, int n_sms, cudaStream_t st) {
     using Cfg = PredCfg<NT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(predict_trsm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-            cudaSuccess)
-            return 1;
-        attr_done = true;
-    }
     const int64_t tiles = (int64_t)p.T * plan.panels * count;
     const unsigned grid = (unsigned)(tiles < n_sms ? tiles : n_sms);
     if (cudaMemsetAsync(p.sync, 0, predict_sync_bytes(plan, count, p.T), st) != cudaSuccess) return 1;
@@ -337,7 +330,12 @@ static int launch_pred(const TrsmPlan& plan, int count, const CUtensorMap& tmL, 
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-int predict_init() { return 0; }
+int predict_init() {
+    if (cudaFuncSetAttribute(predict_trsm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PredCfg<2>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(predict_trsm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PredCfg<4>::SMEM_BYTES) != cudaSuccess)
+        return 1;
+    return 0;
+}
 
 size_t predict_sync_bytes(const TrsmPlan& plan, int count, int T) {
     return sizeof(int) * ((size_t)SYNC_HDR + (size_t)count * plan.panels * T);

@@ -222,8 +222,6 @@ solve_alpha_kernel(const SolveParams sp) {
 static int g_max_cluster = 0;
 
 int solve_init() {
-    static bool done = false;
-    if (done) return 0;
     if (cudaFuncSetAttribute(solve_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return 1;
     // clusters of 16 CTAs need the non-portable opt-in; fall back to the portable 8
@@ -244,7 +242,6 @@ int solve_init() {
         if (cudaOccupancyMaxActiveClusters(&ncl, solve_alpha_kernel, &cfg) == cudaSuccess && ncl >= 1) g_max_cluster = 16;
     }
     cudaGetLastError();
-    done = true;
     return 0;
 }
 

@@ -507,3 +507,21 @@ def test_multi_output_constant_mean(mogp):
     rr = minimize(refs[0].logposterior, np.zeros(3), method="L-BFGS-B", jac=refs[0].logpost_deriv)
     assert_allclose(mo.logposterior(0), rr["fun"], rtol=1e-6)
     mo.close()
+
+
+def test_two_devices_in_one_process(mogp):
+    """Handles on different GPUs of one process (kernel attributes and the buffer cache are per device)."""
+    from mogp_emulator_b200 import libmogp
+    if libmogp.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    X, Y, Xs = orc.make_workload(300, 3, 2, 50, seed=51)
+    theta = np.array([0.5, 0.7, 0.9, 0.1])
+    out = []
+    for dev in (1, 0, 1):
+        gp = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-6, device=dev)
+        gp.fit(theta)
+        out.append(gp.predict(Xs, deriv=False))
+        gp.close()
+    for r in out[1:]:
+        assert_allclose(r.mean, out[0].mean, rtol=0, atol=0)
+        assert_allclose(r.unc, out[0].unc, rtol=0, atol=0)
