@@ -51,7 +51,7 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
     const int r = lane & 15;
     double a[SB];
 #pragma unroll
-    for (int jj = 0; jj < SB; jj++) a[jj] = (jj <= r) ? sm.S[(j0 + r) * PS + j0 + jj] : 0.0;
+    for (int jj = 0; jj < SB; jj++) a[jj] = (jj <= r && lane < SB) ? sm.S[(j0 + r) * PS + j0 + jj] : 0.0;   // lanes 16..31 only relay
     int fail = 0;
 #pragma unroll
     for (int j = 0; j < SB; j++) {
@@ -523,6 +523,9 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         const int64_t rb = (int64_t)o * p.n_pad;
 
         if (id.kind == TK_D) {
+            // the factorisation borrows the ring and the staging buffer: every consumer warp must be done reading them
+            // for the previous tile (its last MMA stage, a DIAG tile's write-back) before the first store lands there
+            named_bar_sync(1, Cfg::NCW * 32);
             if (!skip) {
                 Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(base);
                 double* Ablk = p.A + (rb + (int64_t)j * NB) * p.n_pad + (int64_t)j * NB;
