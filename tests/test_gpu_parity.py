@@ -526,3 +526,24 @@ def test_two_devices_in_one_process(mogp):
     for r in out[1:]:
         assert_allclose(r.mean, out[0].mean, rtol=0, atol=0)
         assert_allclose(r.unc, out[0].unc, rtol=0, atol=0)
+
+
+def test_bitwise_reproducible(mogp):
+    """The dataflow kernels order every floating-point reduction (tile chains, rank-order cluster sums, per-tile mean
+    partials): two runs of the same job -- in two different emulator objects -- must agree bit for bit, whatever the
+    order in which CTAs happened to draw their tickets."""
+    X, Y, Xs = orc.make_workload(1500, 6, 5, 2100, seed=77)
+    thetas = np.zeros((5, 7))
+    thetas[:, :6] = 0.8 + 0.05 * np.arange(5)[:, None]
+    runs = []
+    for _ in range(3):
+        mo = mogp.MultiOutputGP_GPU(X, Y, kernel="Matern52", nugget=1e-6)
+        mo.fit(thetas)
+        r = mo.predict(Xs)
+        g = mo.logpost_and_deriv_batch([0, 3], thetas[[0, 3]])
+        runs.append((r.mean.copy(), r.unc.copy(), r.deriv.copy(), [mo.logposterior(i) for i in range(5)],
+                     g[0][1].copy(), g[3][1].copy(), mo._handle.get(2, 1)))
+        mo.close()
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert np.array_equal(np.asarray(a), np.asarray(b))

@@ -226,3 +226,32 @@ def test_gathered_rows_are_already_in_output_order():
     for E in (1, 2, 5, 8, 31, 32, 33, 256):
         for world in (1, 2, 3, 4, 8):
             assert sharding.gathered_rows(E, world) == list(range(E))
+
+
+def test_meanfit_algebra_matches_oracle():
+    """meanfunc.MeanFit (the host half of the analytic mean function) fed with numpy solves instead of device ones must
+    reproduce the oracle's coefficients, K^-1 (y - H beta), log-posterior data term and variance correction."""
+    import scipy.linalg
+    from mogp_emulator_b200.meanfunc import MeanFit, design_matrix, interpret_mean
+    assert interpret_mean(None) is None and interpret_mean("-1") is None and interpret_mean(" 1 ") == "1"
+    with pytest.raises(ValueError):
+        interpret_mean("x[0]")
+    X, Y, Xs = orc.make_workload(90, 2, 1, 12, seed=4)
+    y = Y[0] - 1.5
+    theta = np.array([0.4, 0.8, 0.2])
+    ref = orc.OracleGP(X, y, nugget=1e-4, mean="1", priors="weak").fit(theta)
+    K = ref.get_K_matrix() + 1e-4 * np.eye(90)
+    H = design_matrix("1", X)
+    cf = scipy.linalg.cho_factor(K, lower=True)
+    t, W = scipy.linalg.cho_solve(cf, y), scipy.linalg.cho_solve(cf, H)
+    mf = MeanFit(H, y, t, W, 90)
+    assert_allclose(mf.beta, ref.theta_mean, rtol=1e-10)
+    assert_allclose(mf.alpha_mean, ref.Kinv_t_mean, rtol=1e-8, atol=1e-10)
+    logdet = 2.0 * np.sum(np.log(np.diag(cf[0])))
+    assert_allclose(mf.data_logpost(float(y @ t), logdet, 90), ref.current_logpost, rtol=1e-11)
+    assert_allclose(mf.U @ mf.U.T, W @ np.linalg.solve(H.T @ W, W.T), rtol=1e-9, atol=1e-12)
+    Ks = ref.get_cov_matrix(Xs)
+    extra = mf.variance_term(design_matrix("1", Xs), W.T @ Ks)
+    _, var = ref.predict(Xs)
+    base = np.exp(theta[2]) + 1e-4 - np.sum(Ks * scipy.linalg.cho_solve(cf, Ks), axis=0)
+    assert_allclose(np.maximum(base + extra, 0.0), var, rtol=1e-7, atol=1e-12)
