@@ -127,7 +127,7 @@ int mogp_solve_list(mogp_handle* h, const int32_t* idx, int32_t count, const dou
 /* replace the stored K^-1 y of the listed outputs (used by the posterior mean, its derivative and the gradient) with
  * alpha[i] (count, n) -- Kinv_t_mean = K^-1 (y - H beta) */
 int mogp_set_alpha_list(mogp_handle* h, const int32_t* idx, int32_t count, const double* alpha);
-/* vectors u_q (count, n_vec, n), n_vec <= 4, with K^-1 H A^-1 H^T K^-1 = sum_q u_q u_q^T: mogp_logpost_grad_list then
+/* vectors u_q (count, n_vec, n), n_vec <= 32, with K^-1 H A^-1 H^T K^-1 = sum_q u_q u_q^T: mogp_logpost_grad_list then
  * differentiates the mean-integrated likelihood.  Every mogp_fit of an output clears its vectors. */
 int mogp_set_mean_vectors_list(mogp_handle* h, const int32_t* idx, int32_t count, int32_t n_vec, const double* U);
 /* out[o][q][c] = sum_i k_o(x*_c, x_i) vecs[o][q][i] for every fitted output o (vecs: (n_out, n_vec, n); out: (n_out, n_vec,

@@ -3,14 +3,17 @@
 
 Values follow the reference's CPU ``GaussianProcess`` (GaussianProcess.py:629-927): adaptive jitter
 schedule of linalg/cholesky.py:234-281, variance clipped at zero, priors added to the log-posterior on the
-host.  Zero mean function only (every other mean is out of scope and raises).
+host.  Mean functions: zero, constant and formula means (``formula.py``), coefficients integrated out analytically as in
+the CPU reference.
 """
+import warnings
+
 import numpy as np
 
 from . import libmogp
 from .hyper import GPParams, GPPriors, make_priors
 from .kernels import SquaredExponential, Matern52, interpret_kernel
-from .meanfunc import interpret_mean, design_matrix, MeanFit
+from .meanfunc import interpret_mean, design_matrix, design_matrix_inputderiv, MeanFit
 
 
 class GPUUnavailableError(RuntimeError):
@@ -70,7 +73,7 @@ def interpret_nugget(nugget):
 
 
 def _check_mean(mean):
-    """-> canonical mean spec (None or "1"); ValueError for formula means (see meanfunc.py)."""
+    """-> None (zero mean) or a MeanFormula; ValueError for anything that is not a valid formula (see meanfunc.py)."""
     return interpret_mean(mean)
 
 
@@ -98,7 +101,10 @@ class GaussianProcessGPU(object):
         self._meanfit = None
         self._max_batch_size = max_batch_size    # kept for signature compatibility; predict is chunked natively
         self._device = int(device)
-        self.mean = self._mean_spec
+        self.mean = None if self._mean_spec is None else str(self._mean_spec)
+        if inputdict:
+            warnings.warn("The inputdict interface for mean functions has been deprecated. You must input your mean "
+                          "formulae using the x[0] format directly in the formula.", DeprecationWarning)
         self.kernel_type, self.kernel = interpret_kernel(kernel)
         self._nugget_type, self._init_nugget_size = interpret_nugget(nugget)
         self._priors_arg = priors
@@ -304,6 +310,9 @@ class GaussianProcessGPU(object):
         assert testing.shape[1] == self.D
         dmean = self._handle.predict_deriv(testing)[0][0] if deriv else None
         mf = self._meanfit
+        if deriv and mf is not None and self._mean_spec.terms:
+            # the mean function's share: d(H* beta)/dx* (densegp_gpu.hpp:411-448 adds mean_inputderiv the same way)
+            dmean = dmean + np.dot(design_matrix_inputderiv(self._mean_spec, testing), mf.beta)
         mshift = 0.0 if mf is None else np.dot(self.get_design_matrix(testing), mf.beta)
         extra = None
         if mf is not None and unc:

@@ -13,7 +13,7 @@ from . import libmogp
 from .GaussianProcessGPU import PredictResult, GPUUnavailableError, _check_mean
 from .hyper import GPParams, GPPriors, make_priors
 from .kernels import interpret_kernel
-from .meanfunc import design_matrix, MeanFit
+from .meanfunc import design_matrix, design_matrix_inputderiv, MeanFit
 from .sharding import shard_bounds
 
 
@@ -51,7 +51,7 @@ class MultiOutputGP_GPU(object):
             nugtype, nugsize = libmogp.nugget_type.fixed, float(nugget)
         else:
             raise TypeError("nugget parameter must be a string or a non-negative float")
-        self._mean_spec = _check_mean(mean)      # one mean function shared by all emulators: None or the constant "1"
+        self._mean_spec = _check_mean(mean)      # one mean function shared by all emulators: None or a MeanFormula
         self._inputs = np.ascontiguousarray(inputs)
         self._targets = np.ascontiguousarray(targets)
         self._dm = design_matrix(self._mean_spec, self._inputs)
@@ -337,6 +337,10 @@ class MultiOutputGP_GPU(object):
         Hs = design_matrix(self._mean_spec, testing)
         M = Hs.shape[1]
         fit = self.get_indices_fit()
+        if dmean is not None and self._mean_spec.terms:
+            dHs = design_matrix_inputderiv(self._mean_spec, testing)          # (m, D, M)
+            for i in fit:
+                dmean[i] += np.dot(dHs, self._meanfit[i].beta)
         extra = {}
         if unc and fit:
             vecs = np.zeros((E, M, self.n))

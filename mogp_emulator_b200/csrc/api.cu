@@ -97,7 +97,7 @@ struct TraceClock {
 
 using namespace mogp;
 
-constexpr int MAXM = 4;   // mean-function vectors per output (grad_max_mean())
+constexpr int MAXM = 32;  // mean-function vectors per output (grad_max_mean())
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H, T_COUNT };
 
 struct mogp_handle {

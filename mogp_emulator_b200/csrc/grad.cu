@@ -23,7 +23,8 @@ namespace mogp {
 constexpr int G_BM = 128, G_BN = 64, G_NS = 4, G_NCW = 4;
 constexpr int G_A_BYTES = G_BM * KC * 8, G_B_BYTES = G_BN * KC * 8, G_STAGE = G_A_BYTES + G_B_BYTES;
 constexpr int G_MAXD = 64;  // X tiles of all dims are parked in the (idle) ring during the epilogue
-constexpr int G_MAXM = 4;   // mean-function vectors u_q (G -= sum_q u_q u_q^T), see mogp_set_mean_vectors
+constexpr int G_MAXM = 4;   // mean-function vectors u_q (G -= sum_q u_q u_q^T) staged in shared memory, see mogp_set_mean_vectors
+constexpr int G_MAXM_TOTAL = 32;   // vectors per output in all: those beyond G_MAXM are read through L1 in the epilogue
 constexpr int G_SMEM = G_NS * G_STAGE + 2 * G_NS * 8 + 128 + (G_BM + G_BN) * 8 * (1 + G_MAXM) + 32 * 8 * G_NCW + G_MAXD * 8;
 constexpr int G_DCH = 8;    // parameters reduced per epilogue pass
 
@@ -93,7 +94,8 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (MODE == 0) {
         for (int i = threadIdx.x; i < G_BM + G_BN; i += blockDim.x)
             al_r[i] = (i < G_BM) ? p.alpha[row0 + i] : p.alpha[col0 + i - G_BM];
-        for (int i = threadIdx.x; i < p.n_u * (G_BM + G_BN); i += blockDim.x) {
+        const int n_u_sm = p.n_u < G_MAXM ? p.n_u : G_MAXM;
+        for (int i = threadIdx.x; i < n_u_sm * (G_BM + G_BN); i += blockDim.x) {
             const int q = i / (G_BM + G_BN), k = i - q * (G_BM + G_BN);
             u_rc[i] = p.U[(int64_t)q * p.u_stride + ((k < G_BM) ? row0 + k : col0 + k - G_BM)];
         }
@@ -189,8 +191,10 @@ grad_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 kval_and_deriv<KT>(r2, kv, dk);
                 const double kinv = acc[mt][nt][e];
                 double G = kinv - al_r[rl] * al_c[cl];
-                for (int q = 0; q < p.n_u; q++)    // analytic mean function: K^-1 -> K^-1 - K^-1 H A^-1 H^T K^-1
+                for (int q = 0; q < p.n_u && q < G_MAXM; q++)    // analytic mean function: K^-1 -> K^-1 - K^-1 H A^-1 H^T K^-1
                     G = fma(-u_rc[q * (G_BM + G_BN) + rl], u_rc[q * (G_BM + G_BN) + G_BM + cl], G);
+                for (int q = G_MAXM; q < p.n_u; q++)             // wide design matrices: the rest straight from global memory
+                    G = fma(-__ldg(p.U + (int64_t)q * p.u_stride + j), __ldg(p.U + (int64_t)q * p.u_stride + k), G);
                 s_cov = fma(w * G, sigma2 * kv, s_cov);
                 if (k == j && j < p.n) s_tr += kinv;
                 acc[mt][nt][e] = w * G * sigma2 * dk;
@@ -291,7 +295,7 @@ int grad_init() {
 }
 
 int grad_max_dims() { return G_MAXD; }
-int grad_max_mean() { return G_MAXM; }
+int grad_max_mean() { return G_MAXM_TOTAL; }
 
 int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st) {
     const int64_t total = n_pad * n_pad;
@@ -303,7 +307,7 @@ int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st) {
 int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int kernel, const double* XT, int64_t n,
                       int64_t n_pad, int d, const double* alpha, const double* hyper, int fit_nugget, double* partial,
                       double* grad, const double* U, int n_u, int64_t u_stride, cudaStream_t st) {
-    if (n_u > G_MAXM) return 1;
+    if (n_u > G_MAXM_TOTAL) return 1;
     GradParams p{};
     p.U = U; p.n_u = n_u; p.u_stride = u_stride;
     p.XT = XT; p.alpha = alpha; p.hyper = hyper; p.partial = partial; p.n = n; p.n_pad = n_pad; p.d = d; p.kernel = kernel;

@@ -1,35 +1,53 @@
 """Host side of the analytic mean function (CPU semantics: GaussianProcess.get_design_matrix, GaussianProcess.py:485-514;
 fit / predict algebra GaussianProcess.py:657-685, 887-920; linalg_utils.py:5-168 calc_Ainv / calc_mean_params / calc_R).
 
-The mean parameters are integrated out analytically with the reference's default (weak) mean priors.  Without ``patsy``
-(not available offline) the expressible mean functions are the zero mean (``None``, ``"0"``, ``"-1"``) and the constant
-mean (``"1"``, ``"-0"``); the algebra below is written for a general design matrix with up to 4 columns (the device
-keeps that many rank-1 vectors per output).  The n x n work -- the solves K^-1 H, the products H^T K^-1 K* -- runs on the
-GPU (mogp_solve_list, mogp_kstar_dot); only n_mean x n_mean matrices are handled here.
+The mean parameters are integrated out analytically with the reference's default (weak) mean priors.  The design
+matrix comes from ``formula.MeanFormula`` (a patsy-free evaluator of the formula subset that makes sense for numeric
+inputs: ``"x[0]"``, ``"x[0] + x[1]:x[2]"``, ``"I(x[0]**2)"``, ``"np.sin(x[1])"``, ``"y ~ x[0]"``, ``"-1 + x[0]"`` ...); the zero
+mean is ``None``, ``"0"`` or ``"-1"``, the constant mean ``"1"`` or ``"-0"``.  The algebra below is written for a general
+design matrix with up to ``MAX_MEAN`` columns (the device keeps that many rank-1 vectors per output for the gradient).
+The n x n work -- the solves K^-1 H, the products H^T K^-1 K* -- runs on the GPU (mogp_solve_list, mogp_kstar_dot); only
+n_mean x n_mean matrices are handled here.
 """
 import numpy as np
 import scipy.linalg
 
+from .formula import MeanFormula
+
+MAX_MEAN = 32     # mogp_set_mean_vectors_list: vectors per output (csrc/api.cu MAXM)
+
 
 def interpret_mean(mean):
-    """-> canonical spec ``None`` (zero mean) or ``"1"`` (constant mean); ValueError for anything else."""
+    """-> ``None`` (zero mean) or a ``MeanFormula``; ValueError("Provided mean function is invalid") otherwise
+    (GaussianProcess.py:499-512)."""
     if mean is None:
         return None
-    if isinstance(mean, str):
-        spec = mean.replace(" ", "")
-        if spec in ("0", "-1"):
-            return None
-        if spec in ("1", "-0"):
-            return "1"
-    raise ValueError("the B200 GPU emulator supports the zero mean (None, '0', '-1') and the constant mean ('1', '-0'); "
-                     "formula mean functions need patsy")
+    if isinstance(mean, MeanFormula):
+        spec = mean
+    elif isinstance(mean, str):
+        spec = MeanFormula(mean)
+    else:
+        raise ValueError("Provided mean function is invalid")
+    if spec.n_mean == 0:
+        return None
+    if spec.n_mean > MAX_MEAN:
+        raise ValueError("Provided mean function is invalid: at most %d design-matrix columns are supported" % MAX_MEAN)
+    return spec
 
 
 def design_matrix(spec, inputs):
     inputs = np.atleast_2d(np.asarray(inputs, dtype=np.float64))
     if spec is None:
         return np.zeros((inputs.shape[0], 0))
-    return np.ones((inputs.shape[0], 1))
+    return spec.design_matrix(inputs)
+
+
+def design_matrix_inputderiv(spec, inputs):
+    """dH/dx (m, D, n_mean) -- the mean function's share of the predictive derivatives."""
+    inputs = np.atleast_2d(np.asarray(inputs, dtype=np.float64))
+    if spec is None:
+        return np.zeros(inputs.shape + (0,))
+    return spec.input_deriv(inputs)
 
 
 class MeanFit(object):

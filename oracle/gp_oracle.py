@@ -271,6 +271,24 @@ def priors_dlogpdtheta(priors, theta_corr_raw, nugget, n_params):
 # single-output GP
 # ------------------------------------------------------------------------------------------------
 
+# Design matrices of the formula mean functions used by the fixtures and tests, written out column by column the way
+# patsy.dmatrix(formula, data={"x": inputs.T}) builds them (GaussianProcess.py:503-512): intercept first unless removed,
+# then the terms by interaction order; a left-hand side ("y ~") is ignored.  Hand-written on purpose: this table is the
+# independent statement the product's formula evaluator (mogp_emulator_b200/formula.py) is checked against.
+DESIGN_FUNCTIONS = {
+    "x[0]": lambda X: [np.ones(len(X)), X[:, 0]],
+    "y ~ x[0] + x[1]": lambda X: [np.ones(len(X)), X[:, 0], X[:, 1]],
+    "x[0] + x[1]:x[2] + I(x[0]**2) + np.sin(x[1]) + x[2]": lambda X: [np.ones(len(X)), X[:, 0], X[:, 0] ** 2, np.sin(X[:, 1]),
+                                                                       X[:, 2], X[:, 1] * X[:, 2]],
+    "-1 + x[0]*x[1]": lambda X: [X[:, 0], X[:, 1], X[:, 0] * X[:, 1]],
+}
+
+
+def design_from_table(formula, inputs):
+    inputs = np.atleast_2d(np.asarray(inputs, dtype=np.float64))
+    return np.column_stack(DESIGN_FUNCTIONS[formula](inputs))
+
+
 class OracleGP(object):
     """Zero-mean GaussianProcess restatement (GaussianProcess.py:86-927 with mean=None).
 
@@ -308,15 +326,20 @@ class OracleGP(object):
         self.Kinv_t = None
         self.current_logpost = None
 
-    # -- GaussianProcess.get_design_matrix, GaussianProcess.py:485-514: zero mean (no columns) or the constant mean;
-    #    formula means need patsy and are out of scope.  Mean priors are the reference's default (weak) ones.
+    # -- GaussianProcess.get_design_matrix, GaussianProcess.py:485-514: zero mean (no columns), the constant mean, a
+    #    callable inputs -> design matrix, or one of the formulas of DESIGN_FUNCTIONS (what patsy's dmatrix returns for
+    #    them, written out by hand -- patsy itself is not installed).  Mean priors are the reference's default (weak) ones.
     def get_design_matrix(self, inputs):
         inputs = np.atleast_2d(np.asarray(inputs, dtype=np.float64))
-        if self.mean is None or self.mean in ("0", "-1"):
+        if self.mean is None or (isinstance(self.mean, str) and self.mean in ("0", "-1")):
             return np.zeros((inputs.shape[0], 0))
+        if callable(self.mean):
+            return np.asarray(self.mean(inputs), dtype=np.float64)
         if self.mean in ("1", "-0"):
             return np.ones((inputs.shape[0], 1))
-        raise ValueError("only the zero and the constant mean function are restated here")
+        if self.mean in DESIGN_FUNCTIONS:
+            return design_from_table(self.mean, inputs)
+        raise ValueError("mean function %r is not restated here (zero, constant, callable or DESIGN_FUNCTIONS)" % (self.mean,))
 
     @property
     def n_mean(self):
@@ -454,8 +477,17 @@ class OracleGP(object):
         for c, x in enumerate(testing):                      # small cases only
             diff = x[np.newaxis, :] - self.inputs            # (n, D)
             r2 = np.sum(w * diff ** 2, axis=1)
-            coef = cov * calc_dKdr2(r2, self.kernel) * self.Kinv_t
+            coef = cov * calc_dKdr2(r2, self.kernel) * self.Kinv_t_mean
             out[c] = 2.0 * w * np.dot(coef, diff)
+        if self.LA is not None:
+            # the mean function's share d(H* beta)/dx* (meanfunc.hpp mean_inputderiv in the GPU reference), by central
+            # differences of the design matrix (exact for the constant mean)
+            h = 1.0e-6
+            for q in range(self.D):
+                step = np.zeros(self.D)
+                step[q] = h
+                dH = (self.get_design_matrix(testing + step) - self.get_design_matrix(testing - step)) / (2.0 * h)
+                out[:, q] += np.dot(dH, self.theta_mean)
         return out
 
 

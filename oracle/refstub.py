@@ -3,8 +3,9 @@
 The reference tree at /root/reference is read-only and lacks two things needed to
 `import mogp_emulator` in this container:
   * mogp_emulator/version.py  (written by the reference's setup.py at install time)
-  * the third-party `patsy` package (only used for formula mean functions, which are
-    out of scope here: every config uses mean=None)
+  * the third-party `patsy` package (only used for formula mean functions; the stand-in
+    returns the hand-written design matrices of gp_oracle.DESIGN_FUNCTIONS for the few
+    formulas the fixtures use and raises PatsyError for everything else)
 This module registers in-memory stand-ins for both and puts /root/reference on sys.path.
 It only exists so that tests/golden/make_golden.py can generate fixtures from the real
 reference and so that the restatement in oracle/gp_oracle.py can be validated against it
@@ -40,8 +41,24 @@ def import_reference():
         patsy.ModelDesc = type("ModelDesc", (), {})
         patsy.Term = type("Term", (), {})
         patsy.EvalFactor = type("EvalFactor", (), {})
-        patsy.dmatrix = _unavailable
-        patsy.dmatrices = _unavailable
+        def _dmatrix(formula, data=None, **kwargs):
+            # formula mean functions of the fixtures: the design matrices patsy would build, from the oracle's hand-written
+            # table (gp_oracle.DESIGN_FUNCTIONS); the reference's GP algebra then runs unmodified on top of them
+            import numpy as np
+            import gp_oracle
+            if formula not in gp_oracle.DESIGN_FUNCTIONS or "~" in formula:
+                raise PatsyError("formula %r is not in gp_oracle.DESIGN_FUNCTIONS (patsy is stubbed)" % (formula,))
+            return gp_oracle.design_from_table(formula, np.asarray(data["x"]).T)
+
+        def _dmatrices(formula, data=None, **kwargs):
+            import numpy as np
+            import gp_oracle
+            if formula not in gp_oracle.DESIGN_FUNCTIONS:
+                raise PatsyError("formula %r is not in gp_oracle.DESIGN_FUNCTIONS (patsy is stubbed)" % (formula,))
+            return np.asarray(data["y"]), gp_oracle.design_from_table(formula, np.asarray(data["x"]).T)
+
+        patsy.dmatrix = _dmatrix
+        patsy.dmatrices = _dmatrices
         sys.modules["patsy"] = patsy
     if "mogp_emulator.version" not in sys.modules:
         ver = types.ModuleType("mogp_emulator.version")

@@ -42,7 +42,16 @@ def prior_params(gp):
     return np.array(corr, dtype=np.float64), np.array(nug, dtype=np.float64)
 
 
+ONLY = sys.argv[1:]      # optional name filters: `make_golden.py fmean` regenerates only the matching fixtures
+
+
+def wanted(name):
+    return not ONLY or any(k in name for k in ONLY)
+
+
 def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with_deriv=True, mean_fn=None):
+    if not wanted(name):
+        return
     X, Y, Xs = workload(n, d, 1, m, seed)
     y = Y[0]
     if dup_rows:
@@ -73,6 +82,8 @@ def single_case(name, n, d, m, seed, kernel, nugget, theta, dup_rows=False, with
 
 
 def multi_case(name, n, d, n_out, m, seed, kernel, nugget, theta_scale):
+    if not wanted(name):
+        return
     X, Y, Xs = workload(n, d, n_out, m, seed)
     rng = np.random.default_rng(seed + 1000)
     n_params = d + 1 + (1 if nugget == "fit" else 0)
@@ -111,5 +122,13 @@ if __name__ == "__main__":
                 with_deriv=False, mean_fn="1")
     single_case("cmean_mat52_adaptive_n140_d2", 140, 2, 25, 42, "Matern52", "adaptive", [0.7, 0.3, -0.2],
                 with_deriv=False, mean_fn="1")
+    # formula mean functions: the reference's GP algebra on the design matrices patsy would build
+    # (oracle/refstub.py feeds them from gp_oracle.DESIGN_FUNCTIONS; patsy is not installed)
+    single_case("fmean_sqexp_fixed_n160_d3", 160, 3, 30, 43, "SquaredExponential", 1e-5, [0.5, 0.8, 0.3, 0.1],
+                with_deriv=False, mean_fn="x[0]")
+    single_case("fmean_mat52_adaptive_n150_d3", 150, 3, 28, 44, "Matern52", "adaptive", [0.6, 0.2, 0.4, -0.1],
+                with_deriv=False, mean_fn="x[0] + x[1]:x[2] + I(x[0]**2) + np.sin(x[1]) + x[2]")
+    single_case("fmean_sqexp_fit_n120_d2", 120, 2, 22, 45, "SquaredExponential", "fit", [0.9, 0.7, 0.2, -8.0],
+                with_deriv=False, mean_fn="y ~ x[0] + x[1]")
     multi_case("multi_sqexp_fixed_e4_n120_d3", 120, 3, 4, 30, 20, "SquaredExponential", 1e-6, 0.5)
     multi_case("multi_mat52_adaptive_e3_n90_d2", 90, 2, 3, 17, 21, "Matern52", "adaptive", 0.5)

@@ -194,7 +194,7 @@ def test_multi_output_not_fit_semantics(mogp):
         gp.fit(np.zeros((4, 7)))
 
 
-@pytest.mark.parametrize("name", [s for s in SINGLE if "n1_" not in s and "n2_" not in s and not s.startswith("cmean_")])
+@pytest.mark.parametrize("name", [s for s in SINGLE if "n1_" not in s and "n2_" not in s and not s.startswith(("cmean_", "fmean_"))])
 def test_logpost_deriv_matches_reference_golden(mogp, name):
     g = _load(name)
     gp = mogp.GaussianProcessGPU(g["X"], g["y"], kernel=str(g["kernel"]), nugget=_nugget_arg(g))
@@ -474,6 +474,73 @@ def test_constant_mean_gradient_and_map(mogp, kernel, nugget):
     gp = mogp.fit_GP_MAP(gp, n_tries=1, theta0=theta0)
     assert_allclose(gp.current_logpost, rr["fun"], rtol=1e-6)
     gp.close()
+
+
+@pytest.mark.parametrize("formula,kernel,nugget", [
+    ("x[0]", "SquaredExponential", 1e-4),
+    ("x[0] + x[1]:x[2] + I(x[0]**2) + np.sin(x[1]) + x[2]", "Matern52", "fit"),       # 6 columns: > 4 device vectors
+    ("-1 + x[0]*x[1]", "SquaredExponential", "adaptive"),
+])
+def test_formula_mean_function(mogp, formula, kernel, nugget):
+    """Formula mean functions (design matrix by formula.MeanFormula, coefficients integrated out analytically): fit,
+    log-posterior, gradient (rank-n_mean corrected K^-1 on the device; the vectors beyond the four staged in shared memory
+    come from global memory), predictions with variance / full covariance and the predictive derivative including the
+    mean function's share, against the oracle with its hand-written design matrices (values pinned by the fmean_* goldens,
+    gradient by finite differences in test_oracle.py)."""
+    X, Y, Xs = orc.make_workload(230, 3, 1, 50, seed=51)
+    y = Y[0] + 1.5 - 2.0 * X[:, 0] + 0.8 * X[:, 1] * X[:, 2]
+    theta = np.array([0.5, 0.8, 0.3, 0.1] + ([-7.5] if nugget == "fit" else []))
+    gp = mogp.GaussianProcessGPU(X, y, mean=formula, kernel=kernel, nugget=nugget)
+    ref = orc.OracleGP(X, y, mean=formula, kernel=kernel, nugget=nugget)
+    assert gp.n_mean == ref.n_mean and gp.mean == formula
+    assert_allclose(gp.get_design_matrix(Xs), ref.get_design_matrix(Xs), rtol=0, atol=0)
+    want_lp = ref.logposterior(theta)
+    assert_allclose(gp.logposterior(theta), want_lp, rtol=_logpost_rtol(ref.get_K_matrix(), ref.nugget))
+    assert_allclose(gp.theta.mean, ref.theta_mean, rtol=1e-6, atol=1e-8 * np.abs(ref.theta_mean).max())
+    want = ref.logpost_deriv(theta)
+    assert_allclose(gp.logpost_deriv(theta), want, rtol=1e-6, atol=1e-7 * np.abs(want).max())
+    res = gp.predict(Xs)
+    rmean, rvar = ref.predict(Xs)
+    assert_allclose(res.mean, rmean, rtol=1e-6, atol=1e-8)
+    assert_allclose(res.unc, rvar, rtol=1e-4, atol=1e-4 * max(ref.nugget, 1e-8))
+    _, rcov = ref.predict(Xs, full_cov=True)
+    assert_allclose(gp.predict(Xs, deriv=False, full_cov=True).unc, rcov, rtol=1e-4, atol=1e-4 * max(ref.nugget, 1e-8))
+    assert res.deriv.shape == (50, 3)
+    rderiv = ref.predict_deriv(Xs)
+    assert_allclose(res.deriv, rderiv, rtol=1e-6, atol=1e-6 * np.abs(rderiv).max())
+    h = 1e-5
+    for q in range(3):
+        e = np.zeros(3)
+        e[q] = h
+        fd = (gp.predict(Xs + e, unc=False, deriv=False).mean - gp.predict(Xs - e, unc=False, deriv=False).mean) / (2 * h)
+        assert_allclose(res.deriv[:, q], fd, rtol=2e-4, atol=2e-4 * np.abs(fd).max())
+    gp.close()
+
+
+def test_multi_output_formula_mean(mogp):
+    """MultiOutputGP_GPU with a formula mean shared by the emulators: batched K^-1 H solves for every design-matrix
+    column, per-emulator coefficients, batched gradients, predictive derivatives with the mean function's share."""
+    formula = "x[0] + x[1]:x[2] + I(x[0]**2) + np.sin(x[1]) + x[2]"
+    X, Y, Xs = orc.make_workload(200, 3, 3, 40, seed=52)
+    Y = Y + np.array([[1.0], [-2.0], [0.5]]) * (1.0 + X[:, 0])
+    thetas = np.array([[0.5, 0.8, 0.4, 0.1], [0.9, 0.4, 0.6, 0.3], [0.2, 0.3, 0.5, -0.1]])
+    mo = mogp.MultiOutputGP_GPU(X, Y, mean=formula, nugget=1e-5)
+    mo.fit(thetas)
+    r = mo.predict(Xs)
+    refs = [orc.OracleGP(X, Y[i], mean=formula, nugget=1e-5).fit(thetas[i]) for i in range(3)]
+    for i in range(3):
+        rm, rv = refs[i].predict(Xs)
+        assert_allclose(r.mean[i], rm, rtol=1e-6, atol=1e-8)
+        assert_allclose(r.unc[i], rv, rtol=1e-4, atol=1e-9)
+        assert_allclose(mo.thetas[i].mean, refs[i].theta_mean, rtol=1e-6, atol=1e-8 * np.abs(refs[i].theta_mean).max())
+        assert_allclose(mo.logposterior(i), refs[i].current_logpost, rtol=_logpost_rtol(refs[i].get_K_matrix(), 1e-5))
+        rd = refs[i].predict_deriv(Xs)
+        assert_allclose(r.deriv[i], rd, rtol=1e-6, atol=1e-6 * np.abs(rd).max())
+    got = mo.logpost_and_deriv_batch([2, 0], thetas[[2, 0]])
+    for i in (2, 0):
+        want = refs[i].logpost_deriv(thetas[i])
+        assert_allclose(got[i][1], want, rtol=1e-6, atol=1e-7 * np.abs(want).max())
+    mo.close()
 
 
 def test_multi_output_constant_mean(mogp):

@@ -228,30 +228,87 @@ def test_gathered_rows_are_already_in_output_order():
             assert sharding.gathered_rows(E, world) == list(range(E))
 
 
-def test_meanfit_algebra_matches_oracle():
+@pytest.mark.parametrize("formula", ["1", "x[0]", "-1 + x[0]*x[1]"])
+def test_meanfit_algebra_matches_oracle(formula):
     """meanfunc.MeanFit (the host half of the analytic mean function) fed with numpy solves instead of device ones must
     reproduce the oracle's coefficients, K^-1 (y - H beta), log-posterior data term and variance correction."""
     import scipy.linalg
     from mogp_emulator_b200.meanfunc import MeanFit, design_matrix, interpret_mean
-    assert interpret_mean(None) is None and interpret_mean("-1") is None and interpret_mean(" 1 ") == "1"
-    with pytest.raises(ValueError):
-        interpret_mean("x[0]")
+    assert interpret_mean(None) is None and interpret_mean("-1") is None and interpret_mean("0") is None
+    assert interpret_mean(" 1 ").n_mean == 1 and interpret_mean("-0").n_mean == 1
+    for bad in (1.0, "x[6]+", "(x[0]+x[1]):x[0]", "x[0]/x[1]"):
+        with pytest.raises(ValueError):
+            interpret_mean(bad)
+    spec = interpret_mean(formula)
     X, Y, Xs = orc.make_workload(90, 2, 1, 12, seed=4)
-    y = Y[0] - 1.5
+    y = Y[0] - 1.5 + 0.7 * X[:, 0]
     theta = np.array([0.4, 0.8, 0.2])
-    ref = orc.OracleGP(X, y, nugget=1e-4, mean="1", priors="weak").fit(theta)
+    ref = orc.OracleGP(X, y, nugget=1e-4, mean=formula, priors="weak").fit(theta)
     K = ref.get_K_matrix() + 1e-4 * np.eye(90)
-    H = design_matrix("1", X)
+    H = design_matrix(spec, X)
+    assert_allclose(H, ref.get_design_matrix(X), rtol=0, atol=0)
     cf = scipy.linalg.cho_factor(K, lower=True)
     t, W = scipy.linalg.cho_solve(cf, y), scipy.linalg.cho_solve(cf, H)
     mf = MeanFit(H, y, t, W, 90)
-    assert_allclose(mf.beta, ref.theta_mean, rtol=1e-10)
-    assert_allclose(mf.alpha_mean, ref.Kinv_t_mean, rtol=1e-8, atol=1e-10)
+    assert_allclose(mf.beta, ref.theta_mean, rtol=1e-9)
+    assert_allclose(mf.alpha_mean, ref.Kinv_t_mean, rtol=1e-7, atol=1e-9)
     logdet = 2.0 * np.sum(np.log(np.diag(cf[0])))
     assert_allclose(mf.data_logpost(float(y @ t), logdet, 90), ref.current_logpost, rtol=1e-11)
-    assert_allclose(mf.U @ mf.U.T, W @ np.linalg.solve(H.T @ W, W.T), rtol=1e-9, atol=1e-12)
+    assert_allclose(mf.U @ mf.U.T, W @ np.linalg.solve(H.T @ W, W.T), rtol=1e-8, atol=1e-11)
     Ks = ref.get_cov_matrix(Xs)
-    extra = mf.variance_term(design_matrix("1", Xs), W.T @ Ks)
+    extra = mf.variance_term(design_matrix(spec, Xs), W.T @ Ks)
     _, var = ref.predict(Xs)
     base = np.exp(theta[2]) + 1e-4 - np.sum(Ks * scipy.linalg.cho_solve(cf, Ks), axis=0)
-    assert_allclose(np.maximum(base + extra, 0.0), var, rtol=1e-7, atol=1e-12)
+    assert_allclose(np.maximum(base + extra, 0.0), var, rtol=1e-7, atol=1e-11)
+
+
+def test_formula_design_matrices_follow_patsy_conventions():
+    """formula.MeanFormula against the oracle's hand-written design matrices (what patsy.dmatrix returns for the same
+    formulas: intercept first, main effects before interactions, left-hand side ignored) and against explicit columns."""
+    from mogp_emulator_b200.formula import MeanFormula
+    rng = np.random.default_rng(3)
+    X = rng.random((17, 3))
+    for formula in orc.DESIGN_FUNCTIONS:
+        assert_allclose(MeanFormula(formula).design_matrix(X), orc.design_from_table(formula, X), rtol=0, atol=0)
+    one = np.ones(17)
+    cases = {
+        "x[1]": [one, X[:, 1]],
+        "1 + x[1]": [one, X[:, 1]],
+        "x[1] + 0": [X[:, 1]],
+        "0 + x[1]": [X[:, 1]],
+        "x[1] - 1": [X[:, 1]],
+        "x[0]:x[1] + x[2]": [one, X[:, 2], X[:, 0] * X[:, 1]],                      # interactions after main effects
+        "x[0]*x[1]": [one, X[:, 0], X[:, 1], X[:, 0] * X[:, 1]],
+        "x[0]*x[1] - x[0]:x[1]": [one, X[:, 0], X[:, 1]],
+        "x[0] + x[0]": [one, X[:, 0]],
+        "x[1]:x[0] + x[0]:x[1]": [one, X[:, 0] * X[:, 1]],
+        "I(x[0] + x[1])": [one, X[:, 0] + X[:, 1]],
+        "np.exp(-x[2]) + I(x[0]*x[1]**2)": [one, np.exp(-X[:, 2]), X[:, 0] * X[:, 1] ** 2],
+        "y ~ x[2]": [one, X[:, 2]],
+    }
+    for formula, cols in cases.items():
+        f = MeanFormula(formula)
+        assert f.n_mean == len(cols), formula
+        assert_allclose(f.design_matrix(X), np.column_stack(cols), rtol=0, atol=0, err_msg=formula)
+    assert MeanFormula("x[0] + x[1]") == MeanFormula("x[0]+x[1]") and str(MeanFormula("y ~ x[0]")) == "y ~ x[0]"
+    for bad in ("x[3]", "x[0] +", "x[0]**2", "a ~ b ~ c", "nosuch(x[0])", "x[0] + (x[1]", "x"):
+        with pytest.raises(ValueError):
+            MeanFormula(bad).design_matrix(X)
+
+
+def test_formula_input_derivatives():
+    from mogp_emulator_b200.formula import MeanFormula
+    rng = np.random.default_rng(5)
+    X = rng.random((11, 3)) + 0.1
+    f = MeanFormula("x[0] + x[1]:x[2] + I(x[0]**3) + np.log(x[1]) + abs(x[2] - 0.5)")
+    d = f.input_deriv(X)
+    want = np.zeros((11, 3, 6))
+    want[:, 0, 1] = 1.0
+    want[:, 0, 2] = 3.0 * X[:, 0] ** 2
+    want[:, 1, 3] = 1.0 / X[:, 1]
+    want[:, 2, 4] = np.sign(X[:, 2] - 0.5)        # not complex-analytic: the central-difference path
+    want[:, 1, 5] = X[:, 2]
+    want[:, 2, 5] = X[:, 1]
+    assert_allclose(d[:, :2], want[:, :2], rtol=1e-13, atol=1e-13)          # complex step: exact to rounding
+    assert_allclose(d[:, 2], want[:, 2], rtol=1e-8, atol=1e-8)
+    assert MeanFormula("1").input_deriv(X).shape == (11, 3, 1) and not MeanFormula("1").input_deriv(X).any()

@@ -203,9 +203,10 @@ def test_constant_mean_logpost_deriv_vs_finite_differences():
     """With a mean function the reference's own logpost_deriv cannot run here (calc_A_deriv under scipy >= 1.15), so the
     oracle's collected form of GaussianProcess.py:743-778 is pinned by central differences of its log-posterior (whose
     values ARE pinned by the cmean_* goldens)."""
-    for kernel, nugget in ((orc.SQEXP, 1e-3), (orc.MAT52, "fit")):
+    for kernel, nugget, mean in ((orc.SQEXP, 1e-3, "1"), (orc.MAT52, "fit", "1"), (orc.SQEXP, "fit", "x[0]"),
+                                 (orc.MAT52, 1e-3, "-1 + x[0]*x[1]")):
         X, Y, _ = orc.make_workload(70, 2, 1, 5, seed=12)
-        gp = orc.OracleGP(X, Y[0] + 3.0, kernel=kernel, nugget=nugget, mean="1")
+        gp = orc.OracleGP(X, Y[0] + 3.0 - X[:, 0], kernel=kernel, nugget=nugget, mean=mean)
         theta = np.array([0.6, 0.9, 0.1] + ([-6.0] if nugget == "fit" else []))
         got = gp.logpost_deriv(theta)
         for i in range(theta.size):
@@ -213,3 +214,17 @@ def test_constant_mean_logpost_deriv_vs_finite_differences():
             e[i] = 1e-4
             fd = (gp.logposterior(theta + e) - gp.logposterior(theta - e)) / 2e-4
             assert_allclose(got[i], fd, rtol=1e-6, atol=1e-8)
+
+
+def test_formula_mean_predict_deriv_vs_finite_differences():
+    """Predictive derivative with a formula mean: kernel share on K^-1 (y - H beta) plus d(H* beta)/dx*."""
+    X, Y, Xs = orc.make_workload(60, 3, 1, 9, seed=6)
+    gp = orc.OracleGP(X, Y[0] + 2.0 * X[:, 0], nugget=1e-4,
+                      mean="x[0] + x[1]:x[2] + I(x[0]**2) + np.sin(x[1]) + x[2]").fit(np.array([0.7, 1.1, 0.9, 0.3]))
+    got = gp.predict_deriv(Xs)
+    h = 1e-6
+    for q in range(3):
+        e = np.zeros(3)
+        e[q] = h
+        fd = (gp.predict(Xs + e, unc=False)[0] - gp.predict(Xs - e, unc=False)[0]) / (2 * h)
+        assert_allclose(got[:, q], fd, rtol=1e-5, atol=1e-6)
