@@ -6,7 +6,8 @@ from .hyper import GPParams, GPPriors, InvGammaPrior, GammaPrior, LogNormalPrior
 from .GaussianProcessGPU import GaussianProcessGPU, PredictResult, GPUUnavailableError
 from .MultiOutputGP_GPU import MultiOutputGP_GPU
 from .fitting import fit_GP_MAP
+from . import validation
 
 __all__ = ["gpu_usable", "HAVE_LIBMOGP", "SquaredExponential", "Matern52", "GPParams", "GPPriors", "InvGammaPrior",
            "GammaPrior", "LogNormalPrior", "WeakPrior", "GaussianProcessGPU", "MultiOutputGP_GPU", "PredictResult",
-           "GPUUnavailableError", "fit_GP_MAP"]
+           "GPUUnavailableError", "fit_GP_MAP", "validation"]

@@ -545,6 +545,49 @@ class OracleMultiOutputGP(object):
 # synthetic workloads shared by tests and bench
 # ------------------------------------------------------------------------------------------------
 
+# ------------------------------------------------------------------------------------------------
+# validation diagnostics (mogp_emulator/validation.py) on a given prediction
+# ------------------------------------------------------------------------------------------------
+
+def pivot_cholesky(A):
+    """linalg/cholesky.py:284-330: dpstrf; rows beyond the numerical rank get a decreasing fake diagonal."""
+    A = np.ascontiguousarray(_check_cholesky_inputs(A))
+    L, P, rank, info = lapack.dpstrf(A, lower=1)
+    L = np.tril(L)
+    if info < 0:
+        raise scipy.linalg.LinAlgError("Illegal value in covariance matrix")
+    n = A.shape[0]
+    idx = np.arange(rank, n)
+    L[idx, idx] = L[rank - 1, rank - 1] / np.cumprod(np.arange(rank + 1, n + 1, dtype=np.float64))
+    return L, P - 1
+
+
+def standard_errors(target, mean, var):
+    """StandardErrors.__call__, validation.py:376-400."""
+    P = np.argsort(var)[::-1]
+    return ((mean - target) / np.sqrt(var))[P], P
+
+
+def pivoted_errors(target, mean, cov):
+    """PivotErrors.__call__, validation.py:416-441 (ChoInvPivot.solve_L, linalg/cholesky.py:130-166)."""
+    L, P = pivot_cholesky(cov)
+    if L.shape == (1, 1):
+        return (mean - target) / L[0, 0], P
+    return scipy.linalg.solve_triangular(L, (mean - target)[P], lower=True), P
+
+
+def mahalanobis(target, mean, cov, n_train, n_mean=0, scaled=False):
+    """validation.py:8-95 for one emulator: sum of squared pivoted errors, optionally standardised with the
+    Fisher-Snedecor distribution F(n_valid, n - n_mean - 2) scaled by n_valid (validation.py:98-135)."""
+    import scipy.stats
+    M = np.sum(pivoted_errors(target, mean, cov)[0] ** 2)
+    if scaled:
+        n_valid = len(target)
+        mu, var = scipy.stats.f(dfn=n_valid, dfd=n_train - n_mean - 2, scale=n_valid).stats()
+        M = (M - mu) / np.sqrt(var)
+    return M
+
+
 def make_workload(n, d, n_out, m, seed):
     """X~U[0,1)^d, Y[k] = sin(2*sum(x)+k) + 0.01*N(0,1), Xs~U[0,1)^d, all from default_rng(seed)."""
     rng = np.random.default_rng(seed)

@@ -50,3 +50,12 @@ VAR_STABILITY = dict(
 def matern52_closed_form(r2):
     r = np.sqrt(r2)
     return (1.0 + np.sqrt(5.0) * r + 5.0 / 3.0 * r2) * np.exp(-np.sqrt(5.0) * r)
+
+
+# ---- validation diagnostics: the mocked predictions of mogp_emulator/tests/test_validation.py:8-15, 67-70, 105-110, 145 ----
+VALID_TARGETS1 = np.array([0.5, 2.1, 2.8])
+VALID_TARGETS2 = np.array([2.5, 2.9, 3.5])
+VALID_MEAN1 = np.array([1.0, 2.0, 3.0])
+VALID_MEAN2 = np.array([2.0, 3.0, 4.0])
+VALID_COV = np.array([[0.1, 0.05, 0.02], [0.05, 0.2, 0.01], [0.02, 0.01, 0.15]])
+VALID_ORDER = np.array([1, 2, 0])          # decreasing variance, and the pivoting order of VALID_COV

@@ -102,7 +102,46 @@ def multi_case(name, n, d, n_out, m, seed, kernel, nugget, theta_scale):
     print(name, "logposts", logposts)
 
 
+def validation_case(name, n, d, m, seed, kernel, nugget, theta, n_out=1, mean_fn=None):
+    """validation.py of the reference on a fitted GP / MultiOutputGP: standard errors, pivoted errors, Mahalanobis."""
+    if not wanted(name):
+        return
+    from mogp_emulator.validation import standard_errors, pivoted_errors, mahalanobis
+    X, Y, Xv = workload(n, d, n_out, m, seed)
+    rng = np.random.default_rng(seed + 500)
+    Yv = np.stack([np.sin(2.0 * Xv.sum(axis=1) + k) + 0.05 * rng.standard_normal(m) for k in range(n_out)])
+    kern = SquaredExponential() if kernel == "SquaredExponential" else Matern52()
+    if n_out == 1:
+        gp = mogp.GaussianProcess(X, Y[0], mean=mean_fn, kernel=kern, nugget=nugget)
+        gp.fit(theta)
+        yv = Yv[0]
+        se, sp = standard_errors(gp, Xv, yv)
+        pe, pp = pivoted_errors(gp, Xv, yv)
+        out = dict(std_err=se, std_idx=sp, piv_err=pe, piv_idx=pp, mahal=np.array(mahalanobis(gp, Xv, yv)),
+                   mahal_scaled=np.array(mahalanobis(gp, Xv, yv, scaled=True)), y=Y[0], yv=yv)
+    else:
+        gp = mogp.MultiOutputGP(X, Y, mean=mean_fn, kernel=kernel, nugget=nugget)
+        gp.fit(np.tile(theta, (n_out, 1)) + 0.1 * np.arange(n_out)[:, None])
+        se = standard_errors(gp, Xv, Yv)
+        pe = pivoted_errors(gp, Xv, Yv)
+        out = dict(std_err=np.array([e[0] for e in se]), std_idx=np.array([e[1] for e in se]),
+                   piv_err=np.array([e[0] for e in pe]), piv_idx=np.array([e[1] for e in pe]),
+                   mahal=np.array(mahalanobis(gp, Xv, Yv)), mahal_scaled=np.array(mahalanobis(gp, Xv, Yv, scaled=True)),
+                   y=Y, yv=Yv)
+    out.update(X=X, Xv=Xv, theta=np.array(theta), kernel=kernel, n_out=np.array(n_out),
+               nugget_in=np.array(nugget if not isinstance(nugget, str) else np.nan),
+               nugget_type="fixed" if not isinstance(nugget, str) else nugget)
+    if mean_fn is not None:
+        out["mean_spec"] = mean_fn
+    np.savez_compressed(os.path.join(HERE, "validation", name + ".npz"), **out)
+    print(name, "mahalanobis", out["mahal"], out["mahal_scaled"])
+
+
 if __name__ == "__main__":
+    os.makedirs(os.path.join(HERE, "validation"), exist_ok=True)
+    validation_case("valid_sqexp_fixed_n90_d2", 90, 2, 24, 61, "SquaredExponential", 1e-4, [0.8, 0.5, 0.1])
+    validation_case("valid_mat52_adaptive_n80_d3_x0", 80, 3, 20, 62, "Matern52", "adaptive", [0.4, 0.6, 0.2, 0.0], mean_fn="x[0]")
+    validation_case("valid_multi_sqexp_e3_n70_d2", 70, 2, 18, 63, "SquaredExponential", 1e-4, [0.7, 0.9, 0.0], n_out=3)
     # C1-shaped (BASELINE.json configs[0]) but n=200 to keep the stored L small
     single_case("sqexp_fixed_n200_d4", 200, 4, 64, 0, "SquaredExponential", 1e-6, [1.0, 1.0, 1.0, 1.0, 0.0])
     # spans two 128-blocks with ragged edge, non-trivial theta
