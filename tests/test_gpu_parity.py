@@ -479,7 +479,7 @@ def test_constant_mean_gradient_and_map(mogp, kernel, nugget):
 @pytest.mark.parametrize("formula,kernel,nugget", [
     ("x[0]", "SquaredExponential", 1e-4),
     ("x[0] + x[1]:x[2] + I(x[0]**2) + np.sin(x[1]) + x[2]", "Matern52", "fit"),       # 6 columns: > 4 device vectors
-    ("-1 + x[0]*x[1]", "SquaredExponential", "adaptive"),
+    ("-1 + x[0]*x[1]", "Matern52", "adaptive"),      # (SqExp without a nugget: cond(K) ~ 1e13, coefficients not comparable)
 ])
 def test_formula_mean_function(mogp, formula, kernel, nugget):
     """Formula mean functions (design matrix by formula.MeanFormula, coefficients integrated out analytically): fit,
