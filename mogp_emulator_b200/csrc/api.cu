@@ -98,6 +98,7 @@ struct TraceClock {
 using namespace mogp;
 
 constexpr int MAXM = 32;  // mean-function vectors per output (grad_max_mean())
+constexpr int I8_DEFAULT_PLANES = 0;   // default of MOGP_TRSM_I8 (see mogp_create)
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H, T_COUNT };
 
 struct mogp_handle {
@@ -121,6 +122,14 @@ struct mogp_handle {
     double *XsT = nullptr, *W = nullptr, *part = nullptr, *res = nullptr, *h_res = nullptr, *h_XsT = nullptr;
     double *sync = nullptr, *normacc = nullptr;   // TRSM ticket/flag words (used as int) and running column norms
     double* csync = nullptr;                       // Cholesky ticket/progress words (used as int)
+    // int8 (tcgen05) predict TRSM: planes of L~ per output (valid until the output is fitted again), planes of V per call
+    int8_t* Lq = nullptr;
+    int* eL = nullptr;
+    unsigned long long* rowmax = nullptr;
+    double* Vq = nullptr;                          // (bytes; typed double for grow())
+    size_t Vq_cap = 0;
+    std::vector<char> lq_valid;
+    int use_i8 = 0;                                // planes per operand of the tcgen05 path (6 or 7), 0 = FP64 DMMA path only
     size_t csync_cap = 0;
     // analytic mean function (set by the host front-end after a fit, cleared by every fit of that output)
     double* U = nullptr;                           // [E][MAXM][n_pad]: u_q with K^-1 H A^-1 H^T K^-1 = sum_q u_q u_q^T
@@ -228,7 +237,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->sync, h->normacc, h->csync, h->U, h->aux, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
+                    h->sync, h->normacc, h->csync, h->U, h->aux, h->Lq, h->eL, h->rowmax, h->Vq, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -269,7 +278,7 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         // kernel attributes (opt-in shared memory, non-portable cluster size) are per device
         static bool inited[64] = {false};
         if (!inited[device & 63]) {
-            if (chol_init() || solve_init() || kmat_init() || predict_init() || grad_init()) {
+            if (chol_init() || solve_init() || kmat_init() || predict_init() || grad_init() || i8_init()) {
                 set_error("kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return MOGP_ERR_CUDA;
             }
@@ -289,6 +298,15 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     h->nug_fixed = nugget;
     h->fitted.assign(n_out, 0);
     h->n_u.assign(n_out, 0);
+    h->lq_valid.assign(n_out, 0);
+    {
+        // MOGP_TRSM_I8 = 0: FP64 DMMA path only; 6 / 7: planes per operand of the int8 tcgen05 path
+        const char* e = getenv("MOGP_TRSM_I8");
+        h->use_i8 = I8_DEFAULT_PLANES;
+        if (e && e[0] == '0') h->use_i8 = 0;
+        else if (e && e[0] == '6') h->use_i8 = 6;
+        else if (e && (e[0] == '7' || e[0] == '1')) h->use_i8 = 7;
+    }
     const int64_t np = h->n_pad;
     (void)n_streams;   // kept in the ABI: every phase is one batched launch on the handle's stream, there is nothing to tune
     int rc = MOGP_OK;
@@ -468,6 +486,7 @@ int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const doubl
         hy[d + 1] = nug[i];
         h->fitted[o] = 0;
         h->n_u[o] = 0;
+        h->lq_valid[o] = 0;
         todo[i] = o;
         pos[o] = i;
     }
@@ -596,6 +615,10 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 return MOGP_ERR_CUDA;
             }
             API_CUDA(cudaEventRecord(h->ev_b, h->main));
+            // many right-hand sides (every block row keeps >= 2 tiles per SM busy): the int8 / tcgen05 path
+            const bool i8 = want_var && h->use_i8 && n_tiles >= 2 &&
+                            (int64_t)cnt * ((mc + i8_panel_width() - 1) / i8_panel_width()) >= 2 * (int64_t)h->n_sms;
+            if (i8) plan = TrsmPlan{i8_panel_width(), (int)((mc + i8_panel_width() - 1) / i8_panel_width())};
             if (want_var) {
                 if (make_kblocked_tmap(&tmW, h->W, (int64_t)cnt * w_stride, np, plan.nw)) {
                     set_error("tensor map (W) failed");
@@ -603,7 +626,41 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 }
                 if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, cnt, n_tiles), h->device))) return rc;
                 if ((rc = grow(&h->normacc, &h->normacc_cap, sizeof(double) * (size_t)cnt * w_stride, h->device))) return rc;
-                if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
+                if (i8) {
+                    const int S8 = h->use_i8;
+                    const size_t lq_stride = i8_lq_bytes(n_tiles, S8);
+                    if (!h->Lq) {
+                        h->Lq = (int8_t*)pool_alloc(lq_stride * (size_t)h->E, h->device);
+                        h->eL = (int*)pool_alloc(sizeof(int) * (size_t)h->E * np, h->device);
+                        h->rowmax = (unsigned long long*)pool_alloc(sizeof(unsigned long long) * (size_t)MAXG * np, h->device);
+                        if (!h->Lq || !h->eL || !h->rowmax) {
+                            set_error("allocation of the int8 planes of L failed");
+                            return MOGP_ERR_NOMEM;
+                        }
+                    }
+                    std::vector<int> stale;
+                    for (int k = 0; k < cnt; k++)
+                        if (!h->lq_valid[outs[k]]) stale.push_back(outs[k]);
+                    if (!stale.empty()) {
+                        if (i8_prepare_L(S8, h->A, h->Dinv, np, stale.data(), (int)stale.size(), h->Lq, (int64_t)lq_stride, h->eL,
+                                         h->rowmax, h->main)) {
+                            set_error("i8_prepare_L launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                            return MOGP_ERR_CUDA;
+                        }
+                        for (int o : stale) h->lq_valid[o] = 1;
+                    }
+                    if ((rc = grow(&h->Vq, &h->Vq_cap, i8_vq_bytes(cnt, plan.panels, n_tiles, S8), h->device))) return rc;
+                    // K~* = blockdiag(L_ii)^-1 K* in place (FP64 DMMA, empty history), then the integer forward substitution
+                    if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
+                                     include_nugget, np, mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms,
+                                     h->main, 0, 0, 1) ||
+                        i8_trsm(S8, outs, cnt, plan.panels, h->Lq, (int64_t)lq_stride, h->eL, (int8_t*)h->Vq, h->W, w_stride,
+                                h->hyper, h->h_hyper, d, include_nugget, want_var == 2 ? 1 : 0, np, mc, h->res + m + m0, 2 * m,
+                                h->normacc, h->n_sms, h->main)) {
+                        set_error("i8 predict launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                        return MOGP_ERR_CUDA;
+                    }
+                } else if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
                                  include_nugget, np, mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms,
                                  h->main, 0, want_var == 2 ? 1 : 0)) {
                     set_error("predict_trsm launch failed: %s", cudaGetErrorString(cudaGetLastError()));

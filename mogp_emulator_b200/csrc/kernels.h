@@ -60,7 +60,22 @@ size_t predict_sync_bytes(const TrsmPlan& plan, int count, int T);
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
                  int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, int* sync, double* normacc,
-                 int n_sms, cudaStream_t st, int keep_v = 0, int no_clip = 0);
+                 int n_sms, cudaStream_t st, int keep_v = 0, int no_clip = 0, int diag_only = 0);
+
+// ---- trsm_i8.cu: the predict TRSM from int8 slices on tcgen05 (many right-hand sides) ----
+int i8_init();
+// S = planes per operand: 6 (21 MMAs per K step) or 7 (28 MMAs, 128 x finer)
+size_t i8_lq_bytes(int T, int S);                           // planes of L~ per output (strictly lower blocks)
+size_t i8_vq_bytes(int count, int panels, int T, int S);    // planes of V for one batched call
+int i8_panel_width();
+// L~ = blockdiag(L_ii)^-1 L of the listed outputs -> planes + per-row scale exponents (rowmax: scratch [min(count,MAXG)][n_pad])
+int i8_prepare_L(int S, const double* A_slab, const double* Dinv_slab, int64_t n_pad, const int* outs, int count, int8_t* Lq,
+                 int64_t lq_stride, int* eL, unsigned long long* rowmax, cudaStream_t st);
+// forward substitution, one launch per block row; W holds K~* = blockdiag(L_ii)^-1 K* on entry
+int i8_trsm(int S, const int* outs, int count, int panels, const int8_t* Lq, int64_t lq_stride, const int* eL, int8_t* Vq,
+            const double* W, int64_t w_stride, const double* hyper, const double* h_hyper, int d, int include_nugget,
+            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int n_sms,
+            cudaStream_t st);
 
 // ---- grad.cu ----
 int grad_init();

@@ -52,6 +52,7 @@ struct PredParams {
     int tri_rhs;            // right-hand side is the identity: panel c0 starts its walk at block row c0/128
     int no_clip;            // write sigma2 [+ nugget] - ||V_c||^2 without the max(., 0) (the caller adds the mean-function term first)
     int keep_v;             // also store the last block row of V (full predictive covariance needs all of V)
+    int diag_only;          // empty history: W_i <- inv(L_ii) W_i for every block row (the K~* of trsm_i8.cu); no norms, no variance
     double* var;            // result rows: var of output o at var + o*var_stride
     int64_t var_stride;
     int* sync;              // [SYNC_HDR + count*panels*T]: ticket counter, then one ready-flag per tile (zeroed per launch)
@@ -130,7 +131,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
                     i = t / per_row;
                     q = t - i * per_row;
                     pnl = q % p.panels;
-                    i0 = p.tri_rhs ? (pnl * BN) / NB : 0;
+                    i0 = p.diag_only ? i : (p.tri_rhs ? (pnl * BN) / NB : 0);
                     if (i >= i0) break;   // identity right-hand side: block rows above the panel's own are exactly zero
                 }
                 tq[slot] = (t < total) ? t : -1;
@@ -210,7 +211,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
         const int pnl = q % p.panels;
         const int o_local = q / p.panels;
         const int c0 = pnl * BN;
-        const int i0 = p.tri_rhs ? c0 / NB : 0;
+        const int i0 = p.diag_only ? i : (p.tri_rhs ? c0 / NB : 0);
         const int wrow = (int)(o_local * p.w_stride) + c0;
 
         double acc[2][NT][4];
@@ -261,7 +262,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
         seq++;
 
         const bool last = (i + 1 == T);
-        if (!p.tri_rhs) {
+        if (!p.tri_rhs && !p.diag_only) {
             // column norms of this tile -> running accumulator of the panel (the chain of tiles of one panel is
             // strictly ordered by the ready flags, so this read-modify-write is race-free and deterministic)
 #pragma unroll
@@ -295,7 +296,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
                 }
             }
         }
-        if (!last || p.tri_rhs || p.keep_v) {   // the last block row is only needed when V itself is the result
+        if (!last || p.tri_rhs || p.keep_v || p.diag_only) {   // the last block row is only needed when V itself is the result
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
@@ -374,8 +375,9 @@ TrsmPlan predict_plan_square(int64_t n_pad, int n_sms) {
 int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtensorMap& tmL, const CUtensorMap& tmD,
                  const CUtensorMap& tmW, double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
                  int64_t n_pad, int64_t m, double* var, int64_t var_stride, int tri_rhs, int* sync, double* normacc,
-                 int n_sms, cudaStream_t st, int keep_v, int no_clip) {
+                 int n_sms, cudaStream_t st, int keep_v, int no_clip, int diag_only) {
     PredParams p{};
+    p.diag_only = diag_only;
     p.keep_v = keep_v;
     p.no_clip = no_clip;
     p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m; p.T = (int)(n_pad / NB);
