@@ -336,6 +336,40 @@ def run_b200(args, wl):
     units_per_launch = tm["n_trsm"] and (e_loc * args.steps / tm["n_trsm"])
     peak = libmogp.peak_dmma_tflops(device)
     achieved = trsm_flops * args.steps / tm["n_trsm"] / (trsm_ms * 1e-3) * 1e-12 if tm["n_trsm"] else None
+    roofline = {"bound": "tensor", "kernel": "predict_trsm_kernel (V = L^-1 K*, DMMA)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, world),
+                "peak_source": "DMMA issue peak measured in this run (mogp_peak_dmma); MEASURED_PEAKS.json has "
+                               "no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 36.1 TFLOP/s",
+                "flops_per_launch": trsm_flops * args.steps / tm["n_trsm"] if tm["n_trsm"] else None,
+                "ms_per_launch": trsm_ms, "outputs_per_launch": units_per_launch}
+    if tm.get("i8_row_launches", 0) > 0:
+        # the predict TRSM ran on the int8 tcgen05 path (csrc/trsm_i8.cu): the dominant kernel is i8_row_kernel, one launch
+        # per block row.  Algorithmic work of a launch = its kind::i8 MMAs: tiles x (4 K-steps per 128-block of history) x
+        # plane pairs x 2*128*64*32 integer ops; DESIGN.md section 3 states the count.
+        planes = int(os.environ.get("MOGP_TRSM_I8", "7")[0:1] or 7)
+        planes = 7 if planes not in (6, 7) else planes
+        pairs = planes * (planes + 1) // 2
+        T = (n + 127) // 128
+        panels = (m + 63) // 64
+        ops_step = float(e_loc) * panels * (T * (T - 1) // 2) * 4 * pairs * 2.0 * 128 * 64 * 32
+        rows_ms = tm["i8_rows_ms"] / args.steps
+        launches = tm["i8_row_launches"] / args.steps
+        peak256, peak64 = libmogp.peak_i8_tops(device)
+        ach = ops_step / (rows_ms * 1e-3) * 1e-12
+        roofline = {"bound": "tensor", "kernel": "i8_row_kernel<%d> (V_i = K~*_i - sum_j L~_ij V_j, tcgen05.mma kind::i8, "
+                                                 "%d plane pairs per K step)" % (planes, pairs),
+                    "achieved": ach, "peak": peak256, "unit": "TOP/s", "frac": ach / peak256,
+                    "traffic": ncu_traffic(args.workload + "-i8", world),
+                    "peak_source": "int8 tcgen05 issue peak (M128 N256 K32 MMAs from resident operands) measured in this run "
+                                   "(mogp_peak_i8); the M128 N64 K32 shape the kernel is confined to by TMEM capacity issues at "
+                                   "%.0f TOP/s (frac of that: %.3f)" % (peak64, ach / peak64),
+                    "ops_per_launch": ops_step / launches, "ms_per_launch": rows_ms / launches,
+                    "launches_per_step": launches, "outputs_per_launch": float(e_loc),
+                    "fp64_equivalent_tflops": trsm_flops * (1.0 - 1.0 / T) / (rows_ms * 1e-3) * 1e-12,
+                    "fp64_dmma_peak_tflops": peak,
+                    "whole_trsm_phase": {"ms": tm["trsm_ms"] / args.steps, "fp64_equivalent_tflops": achieved,
+                                         "vs_dmma_peak": achieved / peak if achieved else None}}
     line = {
         "metric": "gp_fit_predict_seconds", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
@@ -347,17 +381,14 @@ def run_b200(args, wl):
                 "d2h_bytes_per_step": int(8 * 2 * m * (E if world > 1 else e_loc) + 8 * 4 * e_loc)},
         "e2e_iterations_ms": {"construct, fit+predict, destroy": e2e_iters},
         "gpu_launches": int(tm["n_launches"]),
-        "roofline": {"bound": "tensor", "kernel": "predict_trsm_kernel (V = L^-1 K*, DMMA)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, world),
-                     "peak_source": "DMMA issue peak measured in this run (mogp_peak_dmma); MEASURED_PEAKS.json has "
-                                    "no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 36.1 TFLOP/s",
-                     "flops_per_launch": trsm_flops * args.steps / tm["n_trsm"] if tm["n_trsm"] else None,
-                     "ms_per_launch": trsm_ms, "outputs_per_launch": units_per_launch},
+        "roofline": roofline,
         "phases_ms_per_step": {"fit_all_outputs": tm["fit_ms"] / args.steps, "kmat": tm["kmat_ms"] / args.steps,
                                "cholesky": tm["chol_ms"] / args.steps, "fit_solves": tm["solve_ms"] / args.steps,
                                "kstar_and_mean": tm["kstar_ms"] / args.steps,
-                               "predict_trsm": tm["trsm_ms"] / args.steps},
+                               "predict_trsm": tm["trsm_ms"] / args.steps,
+                               "trsm_i8_planes_of_L": tm.get("i8_prep_ms", 0.0) / args.steps,
+                               "trsm_i8_ktilde": tm.get("i8_ktilde_ms", 0.0) / args.steps,
+                               "trsm_i8_block_rows": tm.get("i8_rows_ms", 0.0) / args.steps},
         "phases_ms_per_step_max_over_ranks": phase_max,
         "host_wall_ms_per_step": dict(wall_ms, predict_device_part=tm["predict_device_wall_ms"] / args.steps,
                                       predict_copy_out=tm["predict_d2h_wall_ms"] / args.steps),

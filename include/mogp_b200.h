@@ -136,7 +136,8 @@ int mogp_kstar_dot(mogp_handle* h, const double* Xs, int64_t m, const double* ve
 
 /* accumulated device time per phase in ms since the last call with reset != 0:
  * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),
- *              predict host wall up to the last kernel's completion, predict result copy-out host wall */
+ *              predict host wall up to the last kernel's completion, predict result copy-out host wall;
+ * out[11..14] = int8 path of the predict TRSM (inside predict_trsm): L~ planes, K~* pass, block-row launches (ms), #row launches */
 int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset);
 
 /* NCCL plumbing (no reference equivalent: the reference is single-device, multioutputgp_gpu.hpp:183). */
@@ -149,6 +150,9 @@ int mogp_comm_allreduce_max(mogp_comm* c, double* value);
 /* measured FP64 tensor-pipe (DMMA) issue peak of `device` in TFLOP/s: the roofline denominator bench.py uses
  * (MEASURED_PEAKS.json has no FP64 entry). */
 int mogp_peak_dmma(int32_t device, int32_t iters, double* tflops);
+/* int8 tcgen05 (kind::i8) issue peaks in TOP/s: tops[0] = M128 N256 K32 MMAs (the chip's int8 tensor peak), tops[1] = the
+ * M128 N64 K32 shape of the predict kernel (csrc/trsm_i8.cu) */
+int mogp_peak_i8(int32_t device, int32_t iters, double* tops);
 
 int mogp_version(int32_t* major, int32_t* minor);
 

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mogp_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mogp_comm_allreduce_max": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "mogp_peak_dmma": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_double_p]),
+    "mogp_peak_i8": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_double_p]),
 }
 
 _lib = None
@@ -158,6 +159,14 @@ def peak_dmma_tflops(device=0, iters=20000):
     v = ctypes.c_double(0.0)
     check(_lib.mogp_peak_dmma(int(device), int(iters), ctypes.byref(v)), "mogp_peak_dmma")
     return float(v.value)
+
+
+def peak_i8_tops(device=0, iters=20000):
+    """Measured int8 tcgen05 issue peaks, TOP/s: (N = 256 MMAs -- the chip's int8 tensor peak, the N = 64 shape of the
+    predict kernel)."""
+    v = (ctypes.c_double * 2)()
+    check(_lib.mogp_peak_i8(int(device), int(iters), v), "mogp_peak_i8")
+    return float(v[0]), float(v[1])
 
 
 class Handle(object):
@@ -302,10 +311,10 @@ class Handle(object):
         return out
 
     def timings(self, reset=False):
-        out = np.zeros(11)
-        check(_lib.mogp_timings(self._h, dptr(out), 11, int(reset)))
+        out = np.zeros(15)
+        check(_lib.mogp_timings(self._h, dptr(out), 15, int(reset)))
         keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms",
-                "predict_device_wall_ms", "predict_d2h_wall_ms"]
+                "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_ktilde_ms", "i8_rows_ms", "i8_row_launches"]
         return dict(zip(keys, out.tolist()))
 
 

@@ -614,3 +614,95 @@ def test_bitwise_reproducible(mogp):
     for other in runs[1:]:
         for a, b in zip(runs[0], other):
             assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+# ---- predict TRSM on the int8 tcgen05 path (csrc/trsm_i8.cu) -------------------------------------------------------------
+def _with_planes(monkeypatch, planes):
+    monkeypatch.setenv("MOGP_TRSM_I8", str(planes))     # read by mogp_create
+
+
+@pytest.mark.parametrize("planes", [6, 7])
+@pytest.mark.parametrize("kernel,nugget,n,d,E,m,theta_corr", [
+    ("SquaredExponential", 1e-6, 300, 3, 40, 600, 1.0),        # three block rows, ragged last panel
+    ("SquaredExponential", 1e-6, 1000, 5, 8, 5000, 1.0),
+    ("Matern52", 1e-8, 1153, 4, 6, 4000, -1.0),                # cond(K) ~ 1e10, variances down to 2e-7
+])
+def test_i8_trsm_matches_oracle_and_dmma(mogp, monkeypatch, planes, kernel, nugget, n, d, E, m, theta_corr):
+    """Many right-hand sides take the int8 path: variances against the oracle (outputs 0 and E-1) and against the FP64 DMMA
+    path (all outputs) at the parity tolerance (rtol 1e-4, atol 1e-4 nugget); means are untouched by the TRSM.  Seven
+    planes (the default) must sit far inside the tolerance; six planes (opt-in) land at the order of the tolerance on
+    these deliberately ill-conditioned cases, which is why they are not the default."""
+    X, Y, Xs = orc.make_workload(n, d, E, m, seed=2)
+    thetas = np.tile(np.array([theta_corr] * d + [0.0]), (E, 1)) + 0.05 * np.arange(E)[:, None]
+    _with_planes(monkeypatch, 0)
+    gp = mogp.MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget)
+    gp.fit(thetas)
+    ref = gp.predict(Xs, deriv=False)
+    assert gp.timings()["i8_row_launches"] == 0
+    gp.close()
+    _with_planes(monkeypatch, planes)
+    gp = mogp.MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget)
+    gp.fit(thetas)
+    gp.timings(reset=True)
+    res = gp.predict(Xs, deriv=False)
+    assert gp.timings()["i8_row_launches"] == (n + 127) // 128
+    res_nn = gp.predict(Xs, deriv=False, include_nugget=False)
+    gp.close()
+    assert np.array_equal(res.mean, ref.mean)
+    tol = 1e-4 * np.abs(ref.unc) + 1e-4 * nugget
+    worst = (np.abs(res.unc - ref.unc) / tol).max()
+    assert worst < (0.05 if planes == 7 else 2.0), worst
+    if planes == 7:
+        assert_allclose(res_nn.unc, np.maximum(ref.unc - nugget, 0.0), rtol=1e-4, atol=1e-4 * nugget)
+        for o in (0, E - 1):
+            _, rv = orc.OracleGP(X, Y[o], kernel=kernel, nugget=nugget, priors="weak").fit(thetas[o]).predict(Xs)
+            assert_allclose(res.unc[o], rv, rtol=1e-4, atol=1e-4 * nugget)
+
+
+def test_i8_trsm_gating_and_refit(mogp, monkeypatch):
+    """The int8 path is taken only for many right-hand sides and a nugget of at least 1e-9 sigma^2; the planes of L~ are
+    rebuilt after every fit of an output and reused otherwise."""
+    X, Y, Xs = orc.make_workload(300, 3, 40, 600, seed=5)
+    thetas = np.tile(np.array([1.0, 1.0, 1.0, 0.0]), (40, 1))
+    _with_planes(monkeypatch, 7)
+    gp = mogp.MultiOutputGP_GPU(X, Y, nugget=1e-6)
+    gp.fit(thetas)
+    gp.timings(reset=True)
+    v1 = gp.predict(Xs, deriv=False).unc
+    t1 = gp.timings(reset=True)
+    v2 = gp.predict(Xs, deriv=False).unc
+    t2 = gp.timings(reset=True)
+    assert t1["i8_row_launches"] == 3 and t2["i8_row_launches"] == 3
+    assert np.array_equal(v1, v2)                                  # deterministic, planes reused
+    gp.predict(Xs[:100], deriv=False)                              # few right-hand sides: FP64 DMMA path
+    assert gp.timings(reset=True)["i8_row_launches"] == 0
+    thetas2 = thetas + 0.3
+    gp.fit(thetas2)                                                # new factors: stale planes must not be used
+    v3 = gp.predict(Xs, deriv=False).unc
+    _, rv = orc.OracleGP(X, Y[7], nugget=1e-6, priors="weak").fit(thetas2[7]).predict(Xs)
+    assert_allclose(v3[7], rv, rtol=1e-4, atol=1e-10)
+    gp.close()
+    gp = mogp.MultiOutputGP_GPU(X, Y, kernel="Matern52", nugget="adaptive")   # nugget 0: FP64 path
+    gp.fit(thetas)
+    gp.timings(reset=True)
+    gp.predict(Xs, deriv=False)
+    assert gp.timings()["i8_row_launches"] == 0
+    gp.close()
+
+
+def test_i8_trsm_with_mean_function(mogp, monkeypatch):
+    """Un-clipped variances (the mean-function term is added on the host before the clip) through the int8 path."""
+    X, Y, Xs = orc.make_workload(280, 3, 40, 640, seed=9)
+    Y = Y + 2.0 - X[:, 0]
+    thetas = np.tile(np.array([0.8, 0.9, 1.0, 0.1]), (40, 1))
+    _with_planes(monkeypatch, 7)
+    gp = mogp.MultiOutputGP_GPU(X, Y, mean="x[0]", nugget=1e-5)
+    gp.fit(thetas)
+    gp.timings(reset=True)
+    res = gp.predict(Xs, deriv=False)
+    assert gp.timings()["i8_row_launches"] == 3
+    gp.close()
+    for o in (3, 39):
+        rm, rv = orc.OracleGP(X, Y[o], mean="x[0]", nugget=1e-5, priors="weak").fit(thetas[o]).predict(Xs)
+        assert_allclose(res.mean[o], rm, rtol=1e-6, atol=1e-8)
+        assert_allclose(res.unc[o], rv, rtol=1e-4, atol=1e-9)
