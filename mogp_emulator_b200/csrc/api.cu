@@ -628,7 +628,27 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 const double* hy = h->h_hyper + (size_t)outs[k] * (d + 2);
                 if (!(hy[d + 1] >= 1.0e-9 * hy[d])) i8 = false;
             }
-            if (i8) plan = TrsmPlan{i8_panel_width(), (int)((mc + i8_panel_width() - 1) / i8_panel_width())};
+            if (i8) {
+                // planes of L~ (all outputs of the handle, allocated once) and of V (this call); if the device cannot hold them the
+                // call stays on the FP64 path
+                const int panels8 = (int)((mc + i8_panel_width() - 1) / i8_panel_width());
+                if (!h->Lq) {
+                    h->Lq = (int8_t*)pool_alloc(i8_lq_bytes(n_tiles, h->use_i8) * (size_t)h->E, h->device);
+                    h->eL = (int*)pool_alloc(sizeof(int) * (size_t)h->E * np, h->device);
+                    h->rowmax = (unsigned long long*)pool_alloc(sizeof(unsigned long long) * (size_t)MAXG * np, h->device);
+                }
+                if (!h->Lq || !h->eL || !h->rowmax ||
+                    grow(&h->Vq, &h->Vq_cap, i8_vq_bytes(cnt, panels8, n_tiles, h->use_i8), h->device) != MOGP_OK) {
+                    pool_free(h->Lq); pool_free(h->eL); pool_free(h->rowmax);
+                    h->Lq = nullptr; h->eL = nullptr; h->rowmax = nullptr;
+                    std::fill(h->lq_valid.begin(), h->lq_valid.end(), 0);
+                    cudaGetLastError();
+                    h->use_i8 = 0;
+                    i8 = false;
+                } else {
+                    plan = TrsmPlan{i8_panel_width(), panels8};
+                }
+            }
             if (want_var) {
                 if (make_kblocked_tmap(&tmW, h->W, (int64_t)cnt * w_stride, np, plan.nw)) {
                     set_error("tensor map (W) failed");
@@ -639,15 +659,6 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 if (i8) {
                     const int S8 = h->use_i8;
                     const size_t lq_stride = i8_lq_bytes(n_tiles, S8);
-                    if (!h->Lq) {
-                        h->Lq = (int8_t*)pool_alloc(lq_stride * (size_t)h->E, h->device);
-                        h->eL = (int*)pool_alloc(sizeof(int) * (size_t)h->E * np, h->device);
-                        h->rowmax = (unsigned long long*)pool_alloc(sizeof(unsigned long long) * (size_t)MAXG * np, h->device);
-                        if (!h->Lq || !h->eL || !h->rowmax) {
-                            set_error("allocation of the int8 planes of L failed");
-                            return MOGP_ERR_NOMEM;
-                        }
-                    }
                     API_CUDA(cudaEventRecord(h->ev_d, h->main));
                     std::vector<int> stale;
                     for (int k = 0; k < cnt; k++)
@@ -661,7 +672,6 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                         for (int o : stale) h->lq_valid[o] = 1;
                         i8_prep_launches = 2;
                     }
-                    if ((rc = grow(&h->Vq, &h->Vq_cap, i8_vq_bytes(cnt, plan.panels, n_tiles, S8), h->device))) return rc;
                     API_CUDA(cudaEventRecord(h->ev_e, h->main));
                     // K~* = blockdiag(L_ii)^-1 K* in place (FP64 DMMA, empty history), then the integer forward substitution
                     if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,

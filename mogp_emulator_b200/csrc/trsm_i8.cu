@@ -38,13 +38,13 @@ constexpr int I8_THREADS = 320;               // 8 consumer warps + MMA warp + l
 // output scales), S = 7 the pairs t + u <= 8 (28 MMAs, 2^-56): the accurate default, see the error table in DESIGN.md
 template <int S>
 struct I8Cfg {
-    static constexpr int NS = (S == 6) ? 4 : 3;             // ring stages (shared memory: ring + digit image of V_i)
+    static constexpr int NS = (S == 6) ? 6 : 5;             // ring stages: the feed is latency-bound, all shared memory goes to the ring
     static constexpr int ASTAGE = S * I8_APLANE;
     static constexpr int BSTAGE = S * I8_BPLANE;
     static constexpr int STAGE = ASTAGE + BSTAGE;
     static constexpr int LBLOCK = 4 * ASTAGE;               // one 128 x 128 block of L~: 4 K steps
     static constexpr int VBLOCK = 4 * BSTAGE;               // one 128-row block of V for one panel
-    static constexpr int SMEM = NS * STAGE + VBLOCK + 4 * I8_BN * 8 + 256 + 128;
+    static constexpr int SMEM = NS * STAGE + 4 * I8_BN * 8 + 256 + 128;
     static_assert(S * I8_BN <= 512, "one s32 accumulator group per weight must fit TMEM");
 };
 
@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
     constexpr int I8_LBLOCK = Cfg::LBLOCK, I8_VBLOCK = Cfg::VBLOCK, I8_S = S;
     extern __shared__ __align__(128) unsigned char i8_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 127) & ~uintptr_t(127));
-    unsigned char* img = base + I8_NS * I8_STAGE;                                   // digits of V_i of the current tile
-    double* nred = reinterpret_cast<double*>(img + I8_VBLOCK);                      // [4][64]
+    double* nred = reinterpret_cast<double*>(base + I8_NS * I8_STAGE);              // [4][64]
     uint64_t* full = reinterpret_cast<uint64_t*>(nred + 4 * I8_BN);                 // [NS]
     uint64_t* empty = full + I8_NS;                                                 // [NS]
     uint64_t* acc_full = empty + I8_NS;
@@ -337,16 +336,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
             const double scale = (nst > 0) ? ldexp(1.0, p.eL[(size_t)p.outs[o] * p.n_pad + (size_t)i * NB + r] + ev) : 0.0;
             const double vinv = ldexp(1.0, -ev);
             const double* wsrc = p.W + ((size_t)o * p.w_stride + (size_t)pnl * I8_BN + h * 32) * p.n_pad + (size_t)i * NB + r;
-            unsigned char* dimg = img + q4 * I8_BSTAGE;       // K step of the later products = r / 32
+            // digits of V_i go straight to the planes in global memory (K step of the later products = r / 32); a warp's
+            // store of one (column, plane) is two 16-byte runs
+            int8_t* dimg = p.Vq + ((size_t)tile * p.T + i) * I8_VBLOCK + q4 * I8_BSTAGE;
 #pragma unroll
             for (int c = 0; c < 32; c++) {
                 const double v = __ldcs(wsrc + (size_t)c * p.n_pad) - acc[c] * scale;
                 if (!last) {
                     int8_t dig[I8_S];
                     i8_digits<I8_S>(v * vinv, dig);
-                    unsigned char* dst = dimg + i8_plane_off(h * 32 + c, lane);
+                    int8_t* dst = dimg + i8_plane_off(h * 32 + c, lane);
 #pragma unroll
-                    for (int t = 0; t < I8_S; t++) dst[t * I8_BPLANE] = (unsigned char)dig[t];
+                    for (int t = 0; t < I8_S; t++) dst[t * I8_BPLANE] = dig[t];
                 }
                 double s = v * v;
                 s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -371,13 +372,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
                     p.var[(int64_t)og * p.var_stride + cg] = p.no_clip ? (top - nrm) : fmax(top - nrm, 0.0);
                 }
             }
-            if (!last) {
-                uint4* dstg = reinterpret_cast<uint4*>(p.Vq + ((size_t)tile * p.T + i) * I8_VBLOCK);
-                const uint4* srcs = reinterpret_cast<const uint4*>(img);
-#pragma unroll
-                for (int q = 0; q < I8_VBLOCK / 16 / 256; q++) dstg[tid + q * 256] = srcs[tid + q * 256];
-            }
-            named_bar_sync(1, 256);      // img / nred are reused by the next tile
+            named_bar_sync(1, 256);      // nred is reused by the next tile
         }
     }
     i8_fence_before();

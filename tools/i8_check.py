@@ -90,4 +90,7 @@ if __name__ == "__main__":
         ok &= compare("ill-conditioned", 1153, 4, 6, 4000, "Matern52", 1e-8, -1.0)
     if what in ("c3", "all"):
         ok &= compare("C3", 4096, 10, 32, 10000, "SquaredExponential", 1e-6, 1.0, check_oracle=False, reps=3)
+    if what == "c5rank":       # one rank's share of C5: 32 outputs x n=8192 x d=15, m=10000
+        PLANES = (7,)
+        ok &= compare("C5/rank", 8192, 15, 32, 10000, "SquaredExponential", 1e-6, 1.0, check_oracle=False, reps=2)
     sys.exit(0 if ok else 1)
