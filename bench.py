@@ -338,7 +338,7 @@ def run_b200(args, wl):
     achieved = trsm_flops * args.steps / tm["n_trsm"] / (trsm_ms * 1e-3) * 1e-12 if tm["n_trsm"] else None
     roofline = {"bound": "tensor", "kernel": "predict_trsm_kernel (V = L^-1 K*, DMMA)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, world),
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload + "-dmma", world),
                 "peak_source": "DMMA issue peak measured in this run (mogp_peak_dmma); MEASURED_PEAKS.json has "
                                "no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 36.1 TFLOP/s",
                 "flops_per_launch": trsm_flops * args.steps / tm["n_trsm"] if tm["n_trsm"] else None,
