@@ -674,9 +674,13 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     }
                     API_CUDA(cudaEventRecord(h->ev_e, h->main));
                     // K~* = blockdiag(L_ii)^-1 K* in place (FP64 DMMA, empty history), then the integer forward substitution
-                    if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
-                                     include_nugget, np, mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms,
-                                     h->main, 0, 0, 1) ||
+                    CUtensorMap tmW32;
+                    if (make_kblocked_tmap(&tmW32, h->W, (int64_t)cnt * w_stride, np, 32)) {
+                        set_error("tensor map (W, 32 rows) failed");
+                        return MOGP_ERR_CUDA;
+                    }
+                    if (i8_ktilde(outs, cnt, h->maps.d128, tmW32, h->W, w_stride, np, (int64_t)plan.panels * plan.nw, h->n_sms,
+                                  h->main) ||
                         cudaEventRecord(h->ev_f, h->main) != cudaSuccess ||
                         i8_trsm(S8, outs, cnt, plan.panels, h->Lq, (int64_t)lq_stride, h->eL, (int8_t*)h->Vq, h->W, w_stride,
                                 h->hyper, h->h_hyper, d, include_nugget, want_var == 2 ? 1 : 0, np, mc, h->res + m + m0, 2 * m,

@@ -71,6 +71,9 @@ int i8_panel_width();
 // L~ = blockdiag(L_ii)^-1 L of the listed outputs -> planes + per-row scale exponents (rowmax: scratch [min(count,MAXG)][n_pad])
 int i8_prepare_L(int S, const double* A_slab, const double* Dinv_slab, int64_t n_pad, const int* outs, int count, int8_t* Lq,
                  int64_t lq_stride, int* eL, unsigned long long* rowmax, cudaStream_t st);
+// W <- blockdiag(L_ii)^-1 W for the first m_rows test points of every listed output (tmW32: K-blocked map over W, box 32 rows)
+int i8_ktilde(const int* outs, int count, const CUtensorMap& tmD, const CUtensorMap& tmW32, double* W, int64_t w_stride,
+              int64_t n_pad, int64_t m_rows, int n_sms, cudaStream_t st);
 // forward substitution, one launch per block row; W holds K~* = blockdiag(L_ii)^-1 K* on entry
 int i8_trsm(int S, const int* outs, int count, int panels, const int8_t* Lq, int64_t lq_stride, const int* eL, int8_t* Vq,
             const double* W, int64_t w_stride, const double* hyper, const double* h_hyper, int d, int include_nugget,

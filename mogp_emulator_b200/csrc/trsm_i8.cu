@@ -200,6 +200,104 @@ __global__ void __launch_bounds__(256) i8_lprep_kernel(const I8PrepParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K~* = blockdiag(L_ii)^-1 K*, in place in the test-major workspace (FP64 DMMA)
+//
+// Unit of work = (output, block row i): inv(L_ii) is loaded ONCE into shared memory as the A operand (128 KB, K-blocked) and
+// every 32-test-point tile of K*_i streams through a two-slot TMA ring as the B operand -- 32 KB in, one
+// mma_stage<1,4,128> per consumer warp (16 rows each), 32 KB out.  (The dataflow kernel of predict.cu, run with an empty
+// history, reloads inv(L_ii) for every tile and serialises the right-hand-side load with the product: 16 ms at C3.)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KT_BN = 32;
+constexpr int KT_A_BYTES = NB * NB * 8, KT_B_BYTES = KT_BN * NB * 8;
+constexpr int KT_SMEM = KT_A_BYTES + 2 * KT_B_BYTES + 128 + 128;
+
+struct KtParams {
+    double* W;
+    int64_t w_stride, n_pad;
+    int T, tiles, count;        // tiles of KT_BN test points per output
+    int outs[MAXG];
+};
+
+__global__ void __launch_bounds__(288, 1)
+i8_ktilde_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW, const KtParams p) {
+    extern __shared__ __align__(128) unsigned char kt_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(kt_smem_raw) + 127) & ~uintptr_t(127));
+    double* As = reinterpret_cast<double*>(base);                                  // [16][128][8]
+    unsigned char* Bring = base + KT_A_BYTES;                                      // 2 x [16][32][8]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(Bring + 2 * KT_B_BYTES);
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* b_full = a_empty + 1;   // [2]
+    uint64_t* b_empty = b_full + 2;   // [2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int units = p.count * p.T;
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 8);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 8);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        if (lane == 0) {
+            prefetch_tmap(&tmD);
+            prefetch_tmap(&tmW);
+            int it = 0, k = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, k++) {
+                const int o = u / p.T, i = u - o * p.T;
+                if (k > 0) i8_wait(a_empty, (uint32_t)((k - 1) & 1));       // consumers are done with the previous inv(L_ii)
+                mbar_arrive_expect_tx(a_full, KT_A_BYTES);
+                for (int ch = 0; ch < NB / KC; ch++)
+                    tma_load_3d(reinterpret_cast<unsigned char*>(As) + ch * (KC / 8) * NB * 64, &tmD, 0,
+                                (int)(p.outs[o] * p.n_pad) + i * NB, ch * (KC / 8), a_full);
+                for (int tl = 0; tl < p.tiles; tl++, it++) {
+                    const int slot = it & 1;
+                    if (it >= 2) i8_wait(&b_empty[slot], (uint32_t)(((it >> 1) - 1) & 1));
+                    mbar_arrive_expect_tx(&b_full[slot], KT_B_BYTES);
+                    for (int ch = 0; ch < NB / KC; ch++)
+                        tma_load_3d(Bring + slot * KT_B_BYTES + ch * (KC / 8) * KT_BN * 64, &tmW, 0,
+                                    (int)(o * p.w_stride) + tl * KT_BN, i * (NB / 8) + ch * (KC / 8), &b_full[slot]);
+                }
+            }
+        }
+        return;
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+    const int arow0 = warp * 16;
+    int it = 0, k = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, k++) {
+        const int o = u / p.T, i = u - o * p.T;
+        i8_wait(a_full, (uint32_t)(k & 1));
+        for (int tl = 0; tl < p.tiles; tl++, it++) {
+            const int slot = it & 1;
+            i8_wait(&b_full[slot], (uint32_t)((it >> 1) & 1));
+            double acc[1][4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[0][nt][e] = 0.0;
+            mma_stage<1, 4, NB>(acc, As, NB, arow0, reinterpret_cast<const double*>(Bring + slot * KT_B_BYTES), KT_BN, 0, g, t4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_empty[slot]);
+            // W[test point c][i*128 + row] <- acc (row = arow0 + g (+8), c = 8 nt + 2 t4 (+1))
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int e1 = 0; e1 < 2; e1++) {
+                    const int c = nt * 8 + 2 * t4 + e1;
+                    double* wr = p.W + ((int64_t)o * p.w_stride + (int64_t)tl * KT_BN + c) * p.n_pad + (int64_t)i * NB + arow0 + g;
+                    wr[0] = acc[0][nt][e1];
+                    wr[8] = acc[0][nt][2 + e1];
+                }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // one block row of the forward substitution
 // ------------------------------------------------------------------------------------------------------------------
 struct I8RowParams {
@@ -386,7 +484,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
+int i8_ktilde(const int* outs, int count, const CUtensorMap& tmD, const CUtensorMap& tmW32, double* W, int64_t w_stride,
+              int64_t n_pad, int64_t m_rows, int n_sms, cudaStream_t st) {
+    KtParams p{};
+    p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.T = (int)(n_pad / NB); p.count = count;
+    p.tiles = (int)((m_rows + KT_BN - 1) / KT_BN);
+    for (int k = 0; k < count; k++) p.outs[k] = outs[k];
+    const int units = count * p.T;
+    i8_ktilde_kernel<<<(unsigned)(units < n_sms ? units : n_sms), 288, KT_SMEM, st>>>(tmD, tmW32, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int i8_init() {
+    if (cudaFuncSetAttribute(i8_ktilde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM) != cudaSuccess) return 1;
     if (cudaFuncSetAttribute(i8_row_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6>::SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(i8_row_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<7>::SMEM) != cudaSuccess)
         return 1;
