@@ -664,8 +664,10 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     for (int k = 0; k < cnt; k++)
                         if (!h->lq_valid[outs[k]]) stale.push_back(outs[k]);
                     if (!stale.empty()) {
+                        // the planes of V (not yet written by this call) double as the FP64 scratch of the two passes when they are big enough
+                        double* scratch = h->Vq_cap >= i8_scratch_bytes((int)stale.size(), n_tiles) ? h->Vq : nullptr;
                         if (i8_prepare_L(S8, h->A, h->Dinv, np, stale.data(), (int)stale.size(), h->Lq, (int64_t)lq_stride, h->eL,
-                                         h->rowmax, h->main)) {
+                                         h->rowmax, scratch, h->main)) {
                             set_error("i8_prepare_L launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                             return MOGP_ERR_CUDA;
                         }

@@ -69,8 +69,10 @@ size_t i8_lq_bytes(int T, int S);                           // planes of L~ per 
 size_t i8_vq_bytes(int count, int panels, int T, int S);    // planes of V for one batched call
 int i8_panel_width();
 // L~ = blockdiag(L_ii)^-1 L of the listed outputs -> planes + per-row scale exponents (rowmax: scratch [min(count,MAXG)][n_pad])
+// scratch (optional, i8_scratch_bytes(count, T) bytes of FP64): L~ is parked there between the two passes instead of being formed twice
+size_t i8_scratch_bytes(int count, int T);
 int i8_prepare_L(int S, const double* A_slab, const double* Dinv_slab, int64_t n_pad, const int* outs, int count, int8_t* Lq,
-                 int64_t lq_stride, int* eL, unsigned long long* rowmax, cudaStream_t st);
+                 int64_t lq_stride, int* eL, unsigned long long* rowmax, double* scratch, cudaStream_t st);
 // W <- blockdiag(L_ii)^-1 W for the first m_rows test points of every listed output (tmW32: K-blocked map over W, box 32 rows)
 int i8_ktilde(const int* outs, int count, const CUtensorMap& tmD, const CUtensorMap& tmW32, double* W, int64_t w_stride,
               int64_t n_pad, int64_t m_rows, int n_sms, cudaStream_t st);

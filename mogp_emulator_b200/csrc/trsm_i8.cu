@@ -118,6 +118,7 @@ struct I8PrepParams {
     int8_t* Lq;            // [E][lq_stride]
     int64_t lq_stride;
     int* eL;               // [E][n_pad]
+    double* scratch;       // optional [count][blocks][256 threads][64]: pass 0 parks L~ here, pass 1 only slices it
 };
 
 template <int PASS, int S>
@@ -139,7 +140,18 @@ __global__ void __launch_bounds__(256) i8_lprep_kernel(const I8PrepParams p) {
     for (int u = 0; u < 8; u++)
 #pragma unroll
         for (int v = 0; v < 8; v++) acc[u][v] = 0.0;
-    for (int k0 = 0; k0 < NB; k0 += 16) {
+    double* park = p.scratch ? p.scratch + (((size_t)blockIdx.y * gridDim.x + b) * 256 + tid) * 64 : nullptr;
+    if (PASS == 1 && park) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int v = 0; v < 8; v += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(park + u * 8 + v);
+                acc[u][v] = t2.x;
+                acc[u][v + 1] = t2.y;
+            }
+    }
+    for (int k0 = 0; k0 < ((PASS == 1 && park) ? 0 : NB); k0 += 16) {
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int idx = tid + q * 256;
@@ -164,6 +176,12 @@ __global__ void __launch_bounds__(256) i8_lprep_kernel(const I8PrepParams p) {
     }
     unsigned long long* rm = p.rowmax + (size_t)blockIdx.y * p.n_pad + (size_t)i * NB;
     if (PASS == 0) {
+        if (park) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int v = 0; v < 8; v += 2) *reinterpret_cast<double2*>(park + u * 8 + v) = make_double2(acc[u][v], acc[u][v + 1]);
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             double mx = 0.0;
@@ -509,14 +527,17 @@ size_t i8_lq_bytes(int T, int S) { return (size_t)T * (T - 1) / 2 * lblock(S); }
 size_t i8_vq_bytes(int count, int panels, int T, int S) { return (size_t)count * panels * T * vblock(S); }
 int i8_panel_width() { return I8_BN; }
 
+size_t i8_scratch_bytes(int count, int T) { return (size_t)(count < MAXG ? count : MAXG) * (T * (T - 1) / 2) * NB * NB * 8; }
+
 int i8_prepare_L(int S, const double* A_slab, const double* Dinv_slab, int64_t n_pad, const int* outs, int count, int8_t* Lq,
-                 int64_t lq_stride, int* eL, unsigned long long* rowmax, cudaStream_t st) {
+                 int64_t lq_stride, int* eL, unsigned long long* rowmax, double* scratch, cudaStream_t st) {
     const int T = (int)(n_pad / NB);
     if (T < 2 || count < 1) return 0;
     for (int g0 = 0; g0 < count; g0 += MAXG) {
         const int cnt = count - g0 < MAXG ? count - g0 : MAXG;
         I8PrepParams p{};
         p.A = A_slab; p.Dinv = Dinv_slab; p.n_pad = n_pad; p.rowmax = rowmax; p.Lq = Lq; p.lq_stride = lq_stride; p.eL = eL;
+        p.scratch = scratch;
         for (int k = 0; k < cnt; k++) p.outs[k] = outs[g0 + k];
         if (cudaMemsetAsync(rowmax, 0, sizeof(unsigned long long) * (size_t)cnt * n_pad, st) != cudaSuccess) return 1;
         const dim3 grid((unsigned)(T * (T - 1) / 2), (unsigned)cnt);
