@@ -1,4 +1,4 @@
-"""CPU study for a possible round-2 kernel: the predict TRSM's GEMM part on INT8 tensor cores (Ozaki-style slicing).
+"""CPU study behind csrc/trsm_i8.cu: the predict TRSM's GEMM part on INT8 tensor cores (Ozaki-style slicing).
 
 V_i = inv(L_ii) (K*_i - sum_{j<i} L_ij V_j) with the sum evaluated from s signed 7-bit slices of fixed-point L rows
 (one exponent per row of L) and V columns (one global exponent, |V| <= sqrt(sigma2 + nugget) because the predictive
@@ -59,6 +59,22 @@ def trsm_var(L, Ks, sigma2, nugget, s=None, nb=128):
     return sigma2 + nugget - np.sum(V * V, axis=0), n_mma
 
 
+def trsm_var_ltilde(L, Ks, sigma2, nugget, s, nb=128):
+    """The formulation csrc/trsm_i8.cu runs: V_i = inv(L_ii) K*_i - sum_j (inv(L_ii) L_ij) V_j with the rows of
+    L~ = blockdiag(L_ii)^-1 L and the solved V sliced (no FP64 diagonal solve inside the integer kernel)."""
+    n, m = Ks.shape
+    V = np.zeros_like(Ks)
+    b_exp = int(np.frexp(np.sqrt(sigma2 + nugget))[1])
+    for i0 in range(0, n, nb):
+        i1 = min(n, i0 + nb)
+        Dinv = np.linalg.inv(L[i0:i1, i0:i1])
+        V[i0:i1] = Dinv @ Ks[i0:i1]
+        if i0 > 0:
+            upd, _ = sliced_gemm(Dinv @ L[i0:i1, :i0], V[:i0], s, b_exp)
+            V[i0:i1] -= upd
+    return sigma2 + nugget - np.sum(V * V, axis=0)
+
+
 def main():
     n, d, m = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024), 10, 256
     for theta_corr, label in ((1.0, "theta_corr=+1 (benchmark setting)"), (-1.0, "theta_corr=-1 (ill-conditioned)")):
@@ -77,6 +93,10 @@ def main():
             ok = np.all(err <= 1e-4 * np.abs(ref) + 1e-4 * 1e-6)
             print("   %d slices (%2d int8 MMAs per block): max abs var error %.2e, max rel %.2e -> parity %s"
                   % (s, n_mma, err.max(), (err / np.maximum(np.abs(ref), 1e-300)).max(), "OK" if ok else "BROKEN"))
+            err2 = np.abs(trsm_var_ltilde(gp.L, Ks, 1.0, 1e-6, s) - ref)
+            tol = 1e-4 * np.abs(ref) + 1e-4 * 1e-6
+            print("      L~ formulation (what the kernel runs): max abs %.2e, worst error / tolerance %.3f (rows-of-L form: %.3f)"
+                  % (err2.max(), (err2 / tol).max(), (err / tol).max()))
 
 
 if __name__ == "__main__":
