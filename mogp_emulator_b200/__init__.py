@@ -7,7 +7,8 @@ from .GaussianProcessGPU import GaussianProcessGPU, PredictResult, GPUUnavailabl
 from .MultiOutputGP_GPU import MultiOutputGP_GPU
 from .fitting import fit_GP_MAP
 from . import validation
+from .HistoryMatching import HistoryMatching
 
 __all__ = ["gpu_usable", "HAVE_LIBMOGP", "SquaredExponential", "Matern52", "GPParams", "GPPriors", "InvGammaPrior",
            "GammaPrior", "LogNormalPrior", "WeakPrior", "GaussianProcessGPU", "MultiOutputGP_GPU", "PredictResult",
-           "GPUUnavailableError", "fit_GP_MAP", "validation"]
+           "GPUUnavailableError", "fit_GP_MAP", "validation", "HistoryMatching"]

@@ -595,3 +595,20 @@ def make_workload(n, d, n_out, m, seed):
     Y = np.stack([np.sin(2.0 * X.sum(axis=1) + k) + 0.01 * rng.standard_normal(n) for k in range(n_out)])
     Xs = rng.random((m, d))
     return X, Y, Xs
+
+
+# ------------------------------------------------------------------------------------------------
+# history matching (mogp_emulator/HistoryMatching.py) on a given prediction
+# ------------------------------------------------------------------------------------------------
+
+def implausibility(mean, var, obs_val, obs_var, discrepancy=0.0, rank=1):
+    """HistoryMatching.get_implausibility, HistoryMatching.py:255-289: mean / var (n_obs, m) (or (m,) for one output);
+    the (rank+1)-th largest of |z - mean| / sqrt(var + discrepancy + obs_var) over the outputs, rank forced to 0 for one."""
+    mean, var = np.atleast_2d(mean), np.atleast_2d(var)
+    obs_val, obs_var = np.atleast_1d(obs_val), np.atleast_1d(obs_var)
+    n_obs = len(obs_val)
+    if n_obs == 1:
+        rank = 0
+    Vs = var + np.atleast_1d(discrepancy)[:, np.newaxis] + obs_var[:, np.newaxis]
+    I = np.abs(obs_val[:, np.newaxis] - mean) / np.sqrt(Vs)
+    return np.partition(I, n_obs - rank - 1, axis=0)[n_obs - rank - 1]

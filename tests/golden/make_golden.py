@@ -137,7 +137,47 @@ def validation_case(name, n, d, m, seed, kernel, nugget, theta, n_out=1, mean_fn
     print(name, "mahalanobis", out["mahal"], out["mahal_scaled"])
 
 
+def history_case(name, n, d, m, seed, kernel, nugget, theta, n_out):
+    """HistoryMatching of the reference on a fitted GP / MultiOutputGP: implausibility for several ranks / discrepancies,
+    NROY and RO index sets."""
+    if not wanted(name):
+        return
+    from mogp_emulator.HistoryMatching import HistoryMatching
+    X, Y, Xq = workload(n, d, n_out, m, seed)
+    rng = np.random.default_rng(seed + 700)
+    kern = SquaredExponential() if kernel == "SquaredExponential" else Matern52()
+    if n_out == 1:
+        gp = mogp.GaussianProcess(X, Y[0], kernel=kern, nugget=nugget)
+        gp.fit(theta)
+        obs = [0.3, 0.02]
+        thetas = np.array(theta)
+    else:
+        gp = mogp.MultiOutputGP(X, Y, kernel=kernel, nugget=nugget)
+        thetas = np.tile(theta, (n_out, 1)) + 0.1 * np.arange(n_out)[:, None]
+        gp.fit(thetas)
+        obs = [0.5 * rng.standard_normal(n_out), 0.01 + 0.05 * rng.random(n_out)]
+    out = dict(X=X, Y=Y, Xq=Xq, thetas=thetas, kernel=kernel, n_out=np.array(n_out), nugget_in=np.array(nugget),
+               obs_val=np.atleast_1d(obs[0]), obs_var=np.atleast_1d(obs[1]))
+    ranks = [0] if n_out == 1 else [0, 1, n_out - 1]
+    for r in ranks:
+        hm = HistoryMatching(gp=gp, obs=obs, coords=Xq, threshold=2.0)
+        out["I_rank%d" % r] = hm.get_implausibility(rank=r)
+        out["NROY_rank%d" % r] = np.array(hm.get_NROY(rank=r), dtype=np.int64)
+        out["RO_rank%d" % r] = np.array(hm.get_RO(rank=r), dtype=np.int64)
+    hm = HistoryMatching(gp=gp, obs=obs, coords=Xq)
+    out["I_disc"] = hm.get_implausibility(discrepancy=0.3, rank=0)
+    if n_out > 1:
+        disc = 0.1 * (1.0 + np.arange(n_out))
+        out["disc_vec"] = disc
+        out["I_disc_vec"] = HistoryMatching(gp=gp, obs=obs, coords=Xq).get_implausibility(discrepancy=disc, rank=1)
+    np.savez_compressed(os.path.join(HERE, "history", name + ".npz"), **out)
+    print(name, "I range", out["I_rank0"].min(), out["I_rank0"].max(), "NROY", len(out["NROY_rank0"]))
+
+
 if __name__ == "__main__":
+    os.makedirs(os.path.join(HERE, "history"), exist_ok=True)
+    history_case("hist_sqexp_single_n80_d2", 80, 2, 60, 71, "SquaredExponential", 1e-4, [0.8, 0.5, 0.1], 1)
+    history_case("hist_mat52_multi_e4_n70_d3", 70, 3, 50, 72, "Matern52", 1e-4, [0.4, 0.6, 0.2, 0.0], 4)
     os.makedirs(os.path.join(HERE, "validation"), exist_ok=True)
     validation_case("valid_sqexp_fixed_n90_d2", 90, 2, 24, 61, "SquaredExponential", 1e-4, [0.8, 0.5, 0.1])
     validation_case("valid_mat52_adaptive_n80_d3_x0", 80, 3, 20, 62, "Matern52", "adaptive", [0.4, 0.6, 0.2, 0.0], mean_fn="x[0]")
