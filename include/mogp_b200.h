@@ -119,6 +119,11 @@ int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_param
  * from one dataflow launch. */
 int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, double* grad, int32_t n_params);
 
+/* out[c] (n values) = leave-one-out predictive variance of training point c of a fitted output, 1 / (K^-1)_cc with
+ * K = sigma2 k(X,X) + nugget I: the quantity MICEFastGP.fast_predict(index) evaluates one index (and one O(n^3) inverse) at a
+ * time (SequentialDesign.py:705-748); here one L^-1 for all n points. */
+int mogp_loo_variance(mogp_handle* h, int32_t idx, double* out);
+
 /* ---- analytic mean function (the CPU GaussianProcess with a design matrix H, GaussianProcess.py:657-685, 887-920;
  * linalg_utils.py:5-168 calc_Ainv / calc_mean_params / calc_R).  The host front-end keeps H and the n_mean x n_mean
  * algebra; these are the device primitives it needs.  All index lists are distinct handle-local outputs. ---- */

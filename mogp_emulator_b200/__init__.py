@@ -8,7 +8,8 @@ from .MultiOutputGP_GPU import MultiOutputGP_GPU
 from .fitting import fit_GP_MAP
 from . import validation
 from .HistoryMatching import HistoryMatching
+from .SequentialDesign import MICEFastGP
 
 __all__ = ["gpu_usable", "HAVE_LIBMOGP", "SquaredExponential", "Matern52", "GPParams", "GPPriors", "InvGammaPrior",
            "GammaPrior", "LogNormalPrior", "WeakPrior", "GaussianProcessGPU", "MultiOutputGP_GPU", "PredictResult",
-           "GPUUnavailableError", "fit_GP_MAP", "validation", "HistoryMatching"]
+           "GPUUnavailableError", "fit_GP_MAP", "validation", "HistoryMatching", "MICEFastGP"]

@@ -1120,6 +1120,41 @@ int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, do
     return MOGP_OK;
 }
 
+int mogp_loo_variance(mogp_handle* h, int32_t idx, double* out) {
+    if (!h || idx < 0 || idx >= h->E || !out) return MOGP_ERR_ARG;
+    if (!h->fitted[idx]) {
+        set_error("mogp_loo_variance: output %d has not been fit", idx);
+        return MOGP_ERR_NOT_FIT;
+    }
+    API_CUDA(cudaSetDevice(h->device));
+    const int64_t np = h->n_pad;
+    const int T = (int)(np / NB);
+    int rc;
+    // Wt = (L^-1)^T by the dataflow TRSM on an identity right-hand side (as for the gradient), then 1 / squared row norms
+    if ((rc = grow(&h->G, &h->G_cap, sizeof(double) * ((size_t)np * np + np), h->device))) return rc;
+    TrsmPlan plan = predict_plan_square(np, h->n_sms);
+    if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, 1, T), h->device))) return rc;
+    double* Wt = h->G;
+    double* res = h->G + (size_t)np * np;
+    CUtensorMap tmW;
+    if (make_kblocked_tmap(&tmW, Wt, np, np, plan.nw)) {
+        set_error("tensor map (loo workspace) failed");
+        return MOGP_ERR_CUDA;
+    }
+    const int one[1] = {idx};
+    if (grad_set_identity(Wt, np, h->main) ||
+        predict_trsm(plan, one, 1, h->maps.a128, h->maps.d128, tmW, Wt, np, h->hyper, h->d, 0, np, np, nullptr, 0, 1,
+                     (int*)h->sync, nullptr, h->n_sms, h->main) ||
+        grad_row_inv_sumsq(Wt, np, h->n, res, h->main)) {
+        set_error("loo variance launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MOGP_ERR_CUDA;
+    }
+    API_CUDA(cudaMemcpyAsync(out, res, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->main));
+    API_CUDA(cudaStreamSynchronize(h->main));
+    h->timings[T_NLAUNCH] += 3;
+    return MOGP_OK;
+}
+
 int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_params) {
     return mogp_logpost_grad_list(h, &idx, 1, grad, n_params);
 }

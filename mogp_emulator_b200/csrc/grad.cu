@@ -286,6 +286,25 @@ __global__ void set_identity_kernel(double* __restrict__ W, int64_t n_pad) {
     if (idx < n_pad * n_pad) W[idx] = ((idx / n_pad) == (idx % n_pad)) ? 1.0 : 0.0;
 }
 
+// out[c] = 1 / sum_r W[c][r]^2 for the first n rows of a row-major n_pad x n_pad matrix: with W = (L^-1)^T (row c = column c of
+// L^-1) that is 1 / (K^-1)_cc, the leave-one-out predictive variance at training point c
+__global__ void row_inv_sumsq_kernel(const double* __restrict__ W, int64_t n_pad, int64_t n, double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (c >= n) return;
+    const double* row = W + c * n_pad;
+    double s = 0.0;
+    for (int64_t r = lane; r < n_pad; r += 32) s = fma(row[r], row[r], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = 1.0 / s;
+}
+
+int grad_row_inv_sumsq(const double* W, int64_t n_pad, int64_t n, double* out, cudaStream_t st) {
+    row_inv_sumsq_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(W, n_pad, n, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int grad_init() {
     if (cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_SQEXP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(grad_tile_kernel<MOGP_KERNEL_MATERN52, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM) != cudaSuccess ||

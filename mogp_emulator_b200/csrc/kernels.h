@@ -86,6 +86,7 @@ int i8_trsm(int S, const int* outs, int count, int panels, const int8_t* Lq, int
 int grad_init();
 int grad_max_dims();
 int grad_set_identity(double* W, int64_t n_pad, cudaStream_t st);
+int grad_row_inv_sumsq(const double* W, int64_t n_pad, int64_t n, double* out, cudaStream_t st);
 int grad_reduce_tiles(const CUtensorMap& tmW128, const CUtensorMap& tmW64, int kernel, const double* XT, int64_t n,
                       int64_t n_pad, int d, const double* alpha, const double* hyper, int fit_nugget, double* partial,
                       double* grad, const double* U, int n_u, int64_t u_stride, cudaStream_t st);

@@ -64,6 +64,7 @@ SIGNATURES = {
                                               ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, _c_int_p]),
     "mogp_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_double_p]),
     "mogp_logpost_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int32]),
+    "mogp_loo_variance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_double_p]),
     "mogp_timings": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int32]),
     "mogp_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "mogp_comm_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
@@ -308,6 +309,12 @@ class Handle(object):
     def logpost_grad(self, idx, n_params):
         out = np.zeros(n_params)
         check(_lib.mogp_logpost_grad(self._h, int(idx), dptr(out), int(n_params)), "mogp_logpost_grad")
+        return out
+
+    def loo_variance(self, idx):
+        """Leave-one-out predictive variances of all n training points of a fitted output."""
+        out = np.zeros(self.n)
+        check(_lib.mogp_loo_variance(self._h, int(idx), dptr(out)), "mogp_loo_variance")
         return out
 
     def timings(self, reset=False):

@@ -612,3 +612,19 @@ def implausibility(mean, var, obs_val, obs_var, discrepancy=0.0, rank=1):
     Vs = var + np.atleast_1d(discrepancy)[:, np.newaxis] + obs_var[:, np.newaxis]
     I = np.abs(obs_val[:, np.newaxis] - mean) / np.sqrt(Vs)
     return np.partition(I, n_obs - rank - 1, axis=0)[n_obs - rank - 1]
+
+
+# ------------------------------------------------------------------------------------------------
+# MICEFastGP.fast_predict (mogp_emulator/SequentialDesign.py:705-748)
+# ------------------------------------------------------------------------------------------------
+
+def mice_fast_predict(gp, index):
+    """Variance at training point ``index`` of the fitted OracleGP ``gp`` after removing that point, by the reference's
+    route: explicit (L L^T)^-1, Woodbury down-date, sigma2 + nugget - k^T Q k, clipped at zero."""
+    n = gp.n
+    keep = np.arange(n) != index
+    cov = np.exp(gp.theta[gp.D])
+    Ktest = cov * kernel_f(gp.inputs[keep], gp.inputs[index:index + 1], gp.theta[:gp.D], gp.kernel)
+    invQ = np.linalg.solve(gp.L.T, np.linalg.solve(gp.L, np.eye(n)))
+    invQ_mod = invQ[keep][:, keep] - np.outer(invQ[keep, index], invQ[keep, index]) / invQ[index, index]
+    return np.maximum(cov + gp.nugget - np.sum(Ktest * np.dot(invQ_mod, Ktest), axis=0), 0.0)

@@ -182,6 +182,10 @@ class FakeHandle(object):
     def logpost_grad_list(self, indices, n_params):
         return np.array([self.logpost_grad(int(o), n_params) for o in indices])
 
+    def loo_variance(self, idx):
+        s = self._need(int(idx))
+        return 1.0 / np.diag(orc.cho_solve(s["L"], np.eye(self.n)))
+
     def timings(self, reset=False):
         return {}
 
