@@ -11,7 +11,7 @@ from numpy.testing import assert_allclose, assert_equal
 import gp_oracle as orc
 from fake_device import FakeHandle
 
-HIST = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "history", "*.npz")))
+HIST = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "history", "hist_*.npz")))
 
 
 @pytest.fixture()
