@@ -1,5 +1,7 @@
-"""GPU check of the int8 / tcgen05 predict TRSM (MOGP_TRSM_I8=1) against the FP64 DMMA path and the oracle.
-    python tools/i8_check.py [small|c3]"""
+"""GPU check of the int8 / tcgen05 predict TRSM (MOGP_TRSM_I8 = 6 and 7 planes) against the FP64 DMMA path (MOGP_TRSM_I8=0) on
+the same inputs, all outputs, and against the oracle on output 0; prints the error relative to the parity tolerance and the
+device time of the TRSM phase.  Results of round 1: profiles/r01_i8_check.txt.
+    python tools/i8_check.py [small|c3|all|c5rank|diag]"""
 import os
 import sys
 import time
