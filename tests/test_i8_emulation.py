@@ -1,0 +1,50 @@
+"""The exact CPU emulation of csrc/trsm_i8.cu's integer arithmetic (oracle/i8_emulation.py) against the oracle: the designed
+scheme keeps the predictive variance inside the parity tolerance with six planes and far inside it with seven -- the same
+figures the GPU path shows against the FP64 path (profiles/r01_i8_check.txt)."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+import gp_oracle as orc
+import i8_emulation as emu
+
+
+def _case(n, d, m, kernel, nugget, theta):
+    X, Y, Xs = orc.make_workload(n, d, 1, m, seed=2)
+    s2 = np.exp(theta[d])
+    K = s2 * orc.kernel_f(X, X, theta[:d], kernel) + nugget * np.eye(n)
+    L = np.linalg.cholesky(K)
+    Ks = s2 * orc.kernel_f(X, Xs, theta[:d], kernel)
+    V = scipy.linalg.solve_triangular(L, Ks, lower=True)
+    ref = s2 + nugget - np.sum(V * V, axis=0)
+    return L, Ks, s2, ref
+
+
+@pytest.mark.parametrize("n,d,m,kernel,nugget,theta_corr,shift", [
+    (300, 3, 300, orc.SQEXP, 1e-6, 1.0, 0.0),
+    (300, 3, 300, orc.SQEXP, 1e-6, 1.0, 1.95),          # the worst output of the "small" GPU case (theta + 0.05 * 39)
+    (640, 4, 400, orc.MAT52, 1e-8, -1.0, 0.0),          # cond(K) ~ 1e10
+])
+def test_emulated_scheme_error_against_tolerance(n, d, m, kernel, nugget, theta_corr, shift):
+    theta = np.array([theta_corr] * d + [0.0]) + shift
+    L, Ks, s2, ref = _case(n, d, m, kernel, nugget, theta)
+    tol = 1e-4 * np.abs(ref) + 1e-4 * nugget
+    e6 = np.abs(emu.trsm_variance(L, Ks, s2, nugget, 6) - ref) / tol
+    e7 = np.abs(emu.trsm_variance(L, Ks, s2, nugget, 7) - ref) / tol
+    assert e6.max() < 1.0, e6.max()
+    assert e7.max() < 0.05, e7.max()
+    assert e7.max() < e6.max() / 20.0               # one more plane buys about two orders of magnitude (2^-7)
+    v_nn = emu.trsm_variance(L, Ks, s2, nugget, 7, include_nugget=False)
+    np.testing.assert_allclose(v_nn, ref - nugget, rtol=1e-4, atol=1e-4 * nugget)
+
+
+def test_digits_are_exact_and_bounded():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.5, 0.5, size=4000)
+    for S in (6, 7):
+        dig = emu.digits(x, S)
+        assert all(np.all(np.abs(dg) <= 64) and np.all(dg == np.rint(dg)) for dg in dig)
+        back = sum(dg * 2.0 ** (-7 * (t + 1)) for t, dg in enumerate(dig))
+        assert np.max(np.abs(back - x)) <= 2.0 ** (-7 * S - 1) * (1 + 1e-12)
+    edge = emu.digits(np.array([0.4999999, -0.4999999, 0.75]), 6)          # |x| < 0.5 in range; 0.75 degrades, never wraps int8
+    assert np.all(np.abs(edge[0]) <= 127)
