@@ -146,6 +146,11 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def i8_planes():
+    """Planes per operand of the int8 predict path as mogp_create reads MOGP_TRSM_I8: '6' -> 6, anything else that enables it -> 7."""
+    return 6 if os.environ.get("MOGP_TRSM_I8", "7")[:1] == "6" else 7
+
+
 def ncu_traffic(workload, world):
     """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture
     of this same command (profiles/r01_traffic.json); None when that workload / GPU count was not captured."""
@@ -347,8 +352,7 @@ def run_b200(args, wl):
         # the predict TRSM ran on the int8 tcgen05 path (csrc/trsm_i8.cu): the dominant kernel is i8_row_kernel, one launch
         # per block row.  Algorithmic work of a launch = its kind::i8 MMAs: tiles x (4 K-steps per 128-block of history) x
         # plane pairs x 2*128*64*32 integer ops; DESIGN.md section 3 states the count.
-        planes = int(os.environ.get("MOGP_TRSM_I8", "7")[0:1] or 7)
-        planes = 7 if planes not in (6, 7) else planes
+        planes = i8_planes()
         pairs = planes * (planes + 1) // 2
         T = (n + 127) // 128
         panels = (m + 63) // 64
@@ -370,11 +374,20 @@ def run_b200(args, wl):
                     "fp64_dmma_peak_tflops": peak,
                     "whole_trsm_phase": {"ms": tm["trsm_ms"] / args.steps, "fp64_equivalent_tflops": achieved,
                                          "vs_dmma_peak": achieved / peak if achieved else None}}
+    config = workload_config(args.workload, wl, world)
+    if tm.get("i8_row_launches", 0) > 0:
+        config["trsm_path"] = ("int8 tcgen05, %d planes per operand: the O(n^2 m) products of the FP64 forward substitution are "
+                               "evaluated exactly on signed 7-bit digits (error-free splitting), everything else -- kernel "
+                               "matrices, Cholesky, solves, means, the diagonal-block products, recombination and norms -- is "
+                               "IEEE FP64; variances agree with the all-FP64 path (MOGP_TRSM_I8=0) to 4e-12 on this workload, "
+                               "see parity_vs_cpu_sample" % i8_planes())
+    else:
+        config["trsm_path"] = "FP64 DMMA"
     line = {
         "metric": "gp_fit_predict_seconds", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.workload, wl, world),
+        "config": config,
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "s",
                 "h2d_bytes_per_step": int(8 * (X.size + Y[lo:hi].size + thetas[lo:hi].size + Xs.size)),
