@@ -52,7 +52,8 @@ struct PredParams {
     int tri_rhs;            // right-hand side is the identity: panel c0 starts its walk at block row c0/128
     int no_clip;            // write sigma2 [+ nugget] - ||V_c||^2 without the max(., 0) (the caller adds the mean-function term first)
     int keep_v;             // also store the last block row of V (full predictive covariance needs all of V)
-    int diag_only;          // empty history: W_i <- inv(L_ii) W_i for every block row (the K~* of trsm_i8.cu); no norms, no variance
+    int diag_only;          // empty history: W_i <- inv(L_ii) W_i for every block row; no norms, no variance.  (The first K~* pass of
+                            // trsm_i8.cu, 16.1 ms at C3; superseded by i8_ktilde_kernel at 10.1 ms and kept for that comparison.)
     double* var;            // result rows: var of output o at var + o*var_stride
     int64_t var_stride;
     int* sync;              // [SYNC_HDR + count*panels*T]: ticket counter, then one ready-flag per tile (zeroed per launch)

@@ -6,23 +6,27 @@
 //
 //     V_i = inv(L_ii) K*_i - sum_{j<i} (inv(L_ii) L_ij) V_j  =  K~*_i - sum_{j<i} L~_ij V_j
 //
-//   * L~ = blockdiag(L_ii)^-1 L is formed once per fit in FP64 (i8_lprep_kernel) and stored as S = 6 signed 7-bit planes
-//     per element with one power-of-two scale per row (the row of L~ is a fixed-point number with 42 fractional bits);
-//   * K~* = blockdiag(L_ii)^-1 K* comes from the FP64 DMMA kernel of predict.cu run with an empty history (diag_only);
-//   * every solved block row V_i is kept only as 6 int8 planes with one scale per output (||V_c||^2 <= sigma2, so
-//     |V| <= sqrt(sigma2 + nugget)): 6 bytes per element instead of 8, never re-read in FP64;
-//   * the products L~_ij V_j are tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) into s32 accumulators in TMEM: the 21
-//     plane pairs (t, u) with t + u <= 7 of a K step go to 6 accumulators, one per weight 2^-7(t+u); pairs of weight
-//     beyond 2^-49 are dropped (below the FP64 rounding of the products they would correct).  Integer accumulation is
-//     exact: |digit| <= 64, so a column of n = 16384 terms stays below 2^29;
-//   * recombination (TMEM -> FP64, 6 weights, row and output scales), the subtraction from K~*_i, the column norms and the
+//   * L~ = blockdiag(L_ii)^-1 L is formed once per fit in FP64 (i8_lprep_kernel) and stored as S signed 7-bit planes per
+//     element with one power-of-two scale per row (a row of L~ is a fixed-point number with 7 S fractional bits);
+//   * K~* = blockdiag(L_ii)^-1 K* is formed in place in FP64 (i8_ktilde_kernel, DMMA);
+//   * every solved block row V_i is kept only as S int8 planes with one scale per output (||V_c||^2 <= sigma2, so
+//     |V| <= sqrt(sigma2 + nugget)): S bytes per element instead of 8, never re-read in FP64;
+//   * the products L~_ij V_j are tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) into s32 accumulators in TMEM: the
+//     S (S + 1) / 2 plane pairs (t, u) with t + u <= S + 1 of a K step go to S accumulators, one per weight 2^-7(t+u);
+//     pairs of smaller weight are dropped.  Integer accumulation is exact: |digit| <= 64, so a column of n = 16384 terms
+//     times 7 pairs stays below 2^30;
+//   * recombination (TMEM -> FP64, S weights, row and output scales), the subtraction from K~*_i, the column norms and the
 //     slicing of V_i are the epilogue of the consumer warps; the MMA warp already works on the next tile meanwhile.
 //
+// S = 7 is the library default (>= 100 x inside the variance tolerance on every case measured), S = 6 is opt-in
+// (MOGP_TRSM_I8=6; at the edge of the tolerance on small ill-conditioned problems) -- DESIGN.md section 3 has the table.
+//
 // One launch per block row i (all panels of all outputs of the call are independent inside a launch): a persistent grid,
-// per CTA a loader warp (cp.async.bulk of contiguous plane blocks into a 4-stage mbarrier ring), an MMA warp (one elected
-// thread issues, tcgen05.commit frees ring slots / publishes the accumulators) and 8 consumer warps.
-// tools/ozaki_study.py (profiles/r01_ozaki_study.txt) is the error study behind S = 6; tools/probe_i8*.cu measured the
-// instruction (exact s32 results, 89 cycles per M128 N64 K32 MMA).
+// per CTA a loader warp (cp.async.bulk of contiguous plane blocks into a 5- or 6-stage mbarrier ring that takes all the
+// shared memory), an MMA warp (one elected thread issues, tcgen05.commit frees ring slots / publishes the accumulators)
+// and 8 consumer warps.  The kernel is bound by the operand feed out of L2 (5.4 - 5.9 TB/s, profiles/r01_c3_i8_row*.txt).
+// tools/ozaki_study.py (profiles/r01_ozaki_study.txt) is the error study, oracle/i8_emulation.py the exact CPU emulation of
+// this arithmetic, tools/probe_i8*.cu measured the instruction (exact s32 results; the M128 N64 K32 shape issues at 3.0 POP/s).
 #include "common.cuh"
 #include "kernels.h"
 
