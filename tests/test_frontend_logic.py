@@ -175,3 +175,52 @@ def test_fit_GP_MAP_over_the_front_end(fake_gpu, mean):
     assert_allclose(mo.logposterior(0), rr["fun"], rtol=1e-6)
     with pytest.raises(NotImplementedError):
         mogp.fit_GP_MAP(gp, method="Nelder-Mead")
+
+
+def test_nugget_setter_priors_forms_and_strings(fake_gpu):
+    """Less-travelled host paths: the nugget setter rebuilds the device object (and refits when the parameter vector keeps
+    its shape), priors given as a dict / GPPriors / per-emulator list, theta given as a GPParams, __str__."""
+    mogp = fake_gpu
+    X, Y, Xs = _workload(n=60, d=2, e=3, m=7, seed=13)
+    gp = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4)
+    assert gp.nugget_type == "fixed" and gp.nugget == 1e-4 and gp.n_params == 3
+    assert str(gp) == "Gaussian Process with 60 training examples and 2 input variables"
+    gp.fit(np.array([0.3, 0.6, 0.1]))
+    before = gp.predict(Xs, deriv=False).unc
+    gp.nugget = 1e-2                                   # same theta shape: refitted with the new nugget
+    assert gp.nugget == 1e-2 and gp.theta.data_has_been_set()
+    after = gp.predict(Xs, deriv=False).unc
+    assert np.all(after > before)
+    want = orc.OracleGP(X, Y[0], nugget=1e-2, priors="weak").fit(np.array([0.3, 0.6, 0.1])).predict(Xs)[1]
+    assert_allclose(after, want, rtol=1e-8, atol=1e-12)
+    gp.nugget = "fit"                                  # the parameter vector grows: fit status is dropped
+    assert gp.nugget_type == "fit" and gp.n_params == 4 and not gp.theta.data_has_been_set()
+    gp.nugget = "adaptive"
+    assert gp.nugget_type == "adaptive" and gp.n_params == 3 and gp.nugget == 0.0
+    with pytest.raises(ValueError):
+        gp.nugget = -1.0
+    # theta as a GPParams object
+    other = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4)
+    other.fit(np.array([0.3, 0.6, 0.1]))
+    gp2 = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4)
+    gp2.fit(other.theta)
+    assert_allclose(gp2.current_logpost, other.current_logpost, rtol=1e-12)
+    # priors: dict and GPPriors objects give the same log-posterior as the oracle with the same prior parameters
+    pri = dict(corr=[mogp.InvGammaPrior(2.0, 1.0), mogp.WeakPrior()], cov=mogp.WeakPrior(), nugget=None, n_corr=2,
+               nugget_type="fixed")
+    gp3 = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4, priors=pri)
+    gp4 = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4, priors=mogp.GPPriors(**pri))
+    th = np.array([0.2, -0.1, 0.4])
+    assert_allclose(gp3.logposterior(th), gp4.logposterior(th), rtol=1e-13)
+    weak = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4, priors=dict(n_corr=2, nugget_type="fixed"))
+    assert gp3.logposterior(th) != weak.logposterior(th)
+    assert_allclose(weak.logposterior(th), orc.OracleGP(X, Y[0], nugget=1e-4, priors="weak").logposterior(th), rtol=1e-10)
+    # multi-output: one priors object for all, or a list with one entry per emulator
+    mo = mogp.MultiOutputGP_GPU(X, Y, nugget=1e-4, priors=[None, pri, dict(n_corr=2, nugget_type="fixed")])
+    assert "3 emulators" in str(mo) and len(mo.priors) == 3
+    mo.fit(np.tile(th, (3, 1)))
+    assert_allclose(mo.logposterior(2), orc.OracleGP(X, Y[2], nugget=1e-4, priors="weak").logposterior(th), rtol=1e-10)
+    assert_allclose(mo.logposterior(0), orc.OracleGP(X, Y[0], nugget=1e-4).logposterior(th), rtol=1e-10)
+    with pytest.raises(AssertionError):
+        mogp.MultiOutputGP_GPU(X, Y, nugget=1e-4, priors=[None, None])
+    assert mo.nugget == 1e-4 and mo.nugget_type == "fixed" and mo.n_corr == [2, 2, 2]
