@@ -625,7 +625,7 @@ def _with_planes(monkeypatch, planes):
 @pytest.mark.parametrize("kernel,nugget,n,d,E,m,theta_corr", [
     ("SquaredExponential", 1e-6, 300, 3, 40, 600, 1.0),        # three block rows, ragged last panel
     ("SquaredExponential", 1e-6, 1000, 5, 8, 5000, 1.0),
-    ("Matern52", 1e-8, 1153, 4, 6, 4000, -1.0),                # cond(K) ~ 1e10, variances down to 2e-7
+    ("Matern52", 2e-7, 1153, 4, 6, 4000, -1.0),                # cond(K) ~ 2e9, variances down to 5e-7; just above the nugget gate
 ])
 def test_i8_trsm_matches_oracle_and_dmma(mogp, monkeypatch, planes, kernel, nugget, n, d, E, m, theta_corr):
     """Many right-hand sides take the int8 path: variances against the oracle (outputs 0 and E-1) and against the FP64 DMMA
@@ -660,7 +660,7 @@ def test_i8_trsm_matches_oracle_and_dmma(mogp, monkeypatch, planes, kernel, nugg
 
 
 def test_i8_trsm_gating_and_refit(mogp, monkeypatch):
-    """The int8 path is taken only for many right-hand sides and a nugget of at least 1e-9 sigma^2; the planes of L~ are
+    """The int8 path is taken only for many right-hand sides and a nugget of at least 1e-7 sigma^2; the planes of L~ are
     rebuilt after every fit of an output and reused otherwise."""
     X, Y, Xs = orc.make_workload(300, 3, 40, 600, seed=5)
     thetas = np.tile(np.array([1.0, 1.0, 1.0, 0.0]), (40, 1))
@@ -682,12 +682,13 @@ def test_i8_trsm_gating_and_refit(mogp, monkeypatch):
     _, rv = orc.OracleGP(X, Y[7], nugget=1e-6, priors="weak").fit(thetas2[7]).predict(Xs)
     assert_allclose(v3[7], rv, rtol=1e-4, atol=1e-10)
     gp.close()
-    gp = mogp.MultiOutputGP_GPU(X, Y, kernel="Matern52", nugget="adaptive")   # nugget 0: FP64 path
-    gp.fit(thetas)
-    gp.timings(reset=True)
-    gp.predict(Xs, deriv=False)
-    assert gp.timings()["i8_row_launches"] == 0
-    gp.close()
+    for small_nugget in ("adaptive", 1e-8):                                    # nugget 0 / below the gate: FP64 path
+        gp = mogp.MultiOutputGP_GPU(X, Y, kernel="Matern52", nugget=small_nugget)
+        gp.fit(thetas)
+        gp.timings(reset=True)
+        gp.predict(Xs, deriv=False)
+        assert gp.timings()["i8_row_launches"] == 0
+        gp.close()
 
 
 def test_i8_trsm_with_mean_function(mogp, monkeypatch):

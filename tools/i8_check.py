@@ -89,7 +89,7 @@ if __name__ == "__main__":
     if what in ("small", "all"):
         ok &= compare("small", 300, 3, 40, 600, "SquaredExponential", 1e-6, 1.0)
         ok &= compare("medium", 1000, 5, 8, 5000, "SquaredExponential", 1e-6, 1.0)
-        ok &= compare("ill-conditioned", 1153, 4, 6, 4000, "Matern52", 1e-8, -1.0)
+        ok &= compare("ill-conditioned", 1153, 4, 6, 4000, "Matern52", 2e-7, -1.0)     # just above the nugget gate (1e-7 sigma2)
     if what in ("c3", "all"):
         ok &= compare("C3", 4096, 10, 32, 10000, "SquaredExponential", 1e-6, 1.0, check_oracle=False, reps=3)
     if what == "c5rank":       # one rank's share of C5: 32 outputs x n=8192 x d=15, m=10000
