@@ -27,6 +27,8 @@
 // and 8 consumer warps.  The kernel is bound by the operand feed out of L2 (5.4 - 5.9 TB/s, profiles/r01_c3_i8_row*.txt).
 // tools/ozaki_study.py (profiles/r01_ozaki_study.txt) is the error study, oracle/i8_emulation.py the exact CPU emulation of
 // this arithmetic, tools/probe_i8*.cu measured the instruction (exact s32 results; the M128 N64 K32 shape issues at 3.0 POP/s).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -61,12 +63,14 @@ __device__ __forceinline__ int i8_plane_off(int r, int kk) {
 __device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
 }
-// D = s32, A = B = signed 8 bit, both K-major, N = 64, M = 128
-constexpr uint32_t I8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(NB >> 4) << 24);
+// D = s32, A = B = signed 8 bit, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t i8_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(NB >> 4) << 24);
+}
 
-__device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accumulate) : "memory");
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void i8_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -334,6 +338,7 @@ struct I8RowParams {
     int eV[MAXG];           // scale exponent of V per local output
     const double* hyper;
     int hyper_stride, d, include_nugget, no_clip;
+    int wide;               // wide-N MMA form (default); MOGP_I8_WIDE=0 keeps one MMA per plane pair
     double* var;
     int64_t var_stride;
     double* normacc;        // [count][w_stride]
@@ -409,6 +414,23 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
                     i8_wait(&full[slot], (uint32_t)((it / I8_NS) & 1));
                     i8_fence_after();
                     const uint32_t a0 = smem_u32(base + slot * I8_STAGE), b0 = a0 + I8_ASTAGE;
+                    if (p.wide) {
+                        // plane t of L~ against planes 1 .. S+1-t of V in one instruction chain: the planes of V are contiguous in N
+                        // (a plane is 8 row groups of 256 B) and the accumulators are contiguous in TMEM in weight order, so
+                        // D[:, 64 (t-1) ...] += A_t [B_1 | B_2 | ... | B_{S+1-t}] lands every pair (t, u) in the accumulator of weight
+                        // t + u.  10 MMAs of N <= 256 per K step instead of 28 of N = 64: the A plane is read from shared memory once
+                        // per t instead of once per pair (the N = 64 shape is bound by those reads: 6 KB per 32-cycle MMA).
+#pragma unroll
+                        for (int t = 1; t <= I8_S; t++) {
+                            const int ncols = I8_BN * (I8_S + 1 - t);
+                            const uint32_t accum = (st == 0 && t == 1) ? 0u : 1u;
+                            const uint32_t d0 = tmem + (uint32_t)(t - 1) * I8_BN;
+                            const uint64_t ad = i8_desc(a0 + (t - 1) * I8_APLANE);
+                            const int n1 = ncols > 256 ? 256 : ncols;
+                            i8_mma(d0, ad, i8_desc(b0), accum, i8_idesc(n1));
+                            if (ncols > 256) i8_mma(d0 + 256, ad, i8_desc(b0 + 4 * I8_BPLANE), accum, i8_idesc(ncols - 256));
+                        }
+                    } else {
 #pragma unroll
                     for (int w = 2; w <= I8_S + 1; w++) {
                         uint32_t accum = (st == 0) ? 0u : 1u;
@@ -417,9 +439,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
                             const int u = w - t;
                             if (t > I8_S || u > I8_S) continue;
                             i8_mma(tmem + (uint32_t)(w - 2) * I8_BN, i8_desc(a0 + (t - 1) * I8_APLANE),
-                                   i8_desc(b0 + (u - 1) * I8_BPLANE), accum);
+                                   i8_desc(b0 + (u - 1) * I8_BPLANE), accum, i8_idesc(I8_BN));
                             accum = 1u;
                         }
+                    }
                     }
                     i8_commit(&empty[slot]);      // the slot is free once these MMAs have read it
                 }
@@ -570,6 +593,10 @@ int i8_trsm(int S, const int* outs, int count, int panels, const int8_t* Lq, int
         int e = 0;
         frexp(bound > 0.0 ? bound : 1.0, &e);
         p.eV[k] = e + 1;
+    }
+    {
+        const char* e = getenv("MOGP_I8_WIDE");
+        p.wide = (e && e[0] == '0') ? 0 : 1;
     }
     const int ntiles = count * panels;
     const unsigned grid = (unsigned)(ntiles < n_sms ? ntiles : n_sms);

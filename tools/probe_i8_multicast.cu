@@ -8,7 +8,7 @@
 //   the next step for the kernel; if not, it is delivery and only a larger tile per operand byte helps.
 //   Operand values are irrelevant (timing only); A planes are shared by all clusters (L2-resident), B planes are per CTA.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probe_i8_multicast tools/probe_i8_multicast.cu
-// NOT YET RUN (written at the end of round 1 with the GPU budget spent): expect to debug the barrier protocol first.
+// mode bit 1 (value 2): the wide-N MMA form (10 instructions per K step instead of 28).
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -23,11 +23,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
 }
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-__device__ __forceinline__ void mma_i8(uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+__host__ __device__ constexpr uint32_t idesc_n(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
+constexpr uint32_t IDESC = idesc_n(64);
+__device__ __forceinline__ void mma_i8n(uint32_t d, uint64_t a, uint64_t b, uint32_t acc, uint32_t idesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d), "l"(a), "l"(b), "r"(IDESC), "r"(acc) : "memory");
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void mma_i8(uint32_t d, uint64_t a, uint64_t b, uint32_t acc) { mma_i8n(d, a, b, acc, IDESC); }
 __device__ __forceinline__ void commit_local(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const int8_t* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (CS > 1) ? cluster_rank() : 0u;
     const uint16_t mask = (uint16_t)((1u << CS) - 1u);
-    const bool mc = (mode == 1 && CS > 1);
+    const bool mc = ((mode & 1) && CS > 1);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -110,6 +112,20 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const int8_t* __restrict_
             mbar_wait(&full[slot], (uint32_t)((it / NS) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = smem_u32(smem + slot * STAGE), b0 = a0 + ABYTES;
+            if (mode & 2) {
+                // wide form: plane t of A against planes 1 .. S+1-t of V in ONE instruction chain (the planes of V are contiguous
+                // in N, the accumulators contiguous in TMEM in weight order): 10 MMAs of N <= 256 instead of 28 of N = 64
+#pragma unroll
+                for (int t = 1; t <= S; t++) {
+                    const int ncols = 64 * (S + 1 - t);
+                    const uint32_t acc = (it == 0 && t == 1) ? 0u : 1u;
+                    const uint32_t d0 = tmem + (uint32_t)(t - 1) * 64;
+                    const uint64_t ad = make_desc(a0 + (t - 1) * 128 * 32);
+                    const int n1 = ncols > 256 ? 256 : ncols;
+                    mma_i8n(d0, ad, make_desc(b0), acc, idesc_n(n1));
+                    if (ncols > 256) mma_i8n(d0 + 256, ad, make_desc(b0 + 4 * 64 * 32), acc, idesc_n(ncols - 256));
+                }
+            } else
 #pragma unroll
             for (int w = 2; w <= S + 1; w++) {
                 uint32_t acc = it == 0 ? 0u : 1u;
@@ -159,10 +175,10 @@ static void run(const int8_t* A, const int8_t* B, int nsm, int nstage, int mode)
     float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
     const double ctas = cfg.gridDim.x;
     const double delivered = ctas * nstage * (double)STAGE;
-    const double l2_reads = ctas * nstage * ((mode == 1 && CS > 1 ? (double)ABYTES / CS : (double)ABYTES) + BBYTES);
+    const double l2_reads = ctas * nstage * (((mode & 1) && CS > 1 ? (double)ABYTES / CS : (double)ABYTES) + BBYTES);
     const double ops = ctas * nstage * 28.0 * 2.0 * 128 * 64 * 32;
-    printf("cluster %d, %s: %.3f ms  delivered %.2f TB/s  L2 requests %.2f TB/s  %.0f TOP/s int8 (%.1f cycles per MMA at 1.965 GHz)\n",
-           CS, mode ? "A multicast" : "A unicast  ", ms, delivered / ms * 1e-9, l2_reads / ms * 1e-9, ops / ms * 1e-9,
+    printf("cluster %d, %s, %s: %.3f ms  delivered %.2f TB/s  L2 requests %.2f TB/s  %.0f TOP/s int8 (%.1f cycles per MMA at 1.965 GHz)\n",
+           CS, (mode & 1) ? "A multicast" : "A unicast  ", (mode & 2) ? "wide N (10 MMAs)  " : "narrow N (28 MMAs)", ms, delivered / ms * 1e-9, l2_reads / ms * 1e-9, ops / ms * 1e-9,
            ms * 1e-3 * 1.965e9 / (nstage * 28.0));
 }
 
@@ -175,11 +191,14 @@ int main() {
     CK(cudaMalloc(&B, (size_t)nsm * 64 * BBYTES));                   // 136 MB: per-CTA streams
     CK(cudaMemset(A, 1, (size_t)128 * ABYTES)); CK(cudaMemset(B, 1, (size_t)nsm * 64 * BBYTES));
     const int nstage = 4096;
-    run<1>(A, B, nsm, nstage, 0);
-    run<2>(A, B, nsm, nstage, 0);
-    run<2>(A, B, nsm, nstage, 1);
-    run<4>(A, B, nsm, nstage, 0);
-    run<4>(A, B, nsm, nstage, 1);
+    for (int wide = 0; wide <= 2; wide += 2) {
+        run<1>(A, B, nsm, nstage, wide);
+        run<2>(A, B, nsm, nstage, wide);
+        run<2>(A, B, nsm, nstage, wide | 1);
+        run<4>(A, B, nsm, nstage, wide);
+        run<4>(A, B, nsm, nstage, wide | 1);
+        run<8>(A, B, nsm, nstage, wide | 1);
+    }
     printf("probe done\n");
     return 0;
 }
