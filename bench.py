@@ -348,7 +348,7 @@ def run_b200(args, wl):
                                "no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 36.1 TFLOP/s",
                 "flops_per_launch": trsm_flops * args.steps / tm["n_trsm"] if tm["n_trsm"] else None,
                 "ms_per_launch": trsm_ms, "outputs_per_launch": units_per_launch}
-    if tm.get("i8_row_launches", 0) > 0:
+    if tm.get("i8_block_rows", 0) > 0:
         # the predict TRSM ran on the int8 tcgen05 path (csrc/trsm_i8.cu): the dominant kernel is i8_row_kernel, one launch
         # per block row.  Algorithmic work of a launch = its kind::i8 MMAs: tiles x (4 K-steps per 128-block of history) x
         # plane pairs x 2*128*64*32 integer ops; DESIGN.md section 3 states the count.
@@ -358,7 +358,7 @@ def run_b200(args, wl):
         panels = (m + 63) // 64
         ops_step = float(e_loc) * panels * (T * (T - 1) // 2) * 4 * pairs * 2.0 * 128 * 64 * 32
         rows_ms = tm["i8_rows_ms"] / args.steps
-        launches = tm["i8_row_launches"] / args.steps
+        launches = tm["i8_block_rows"] / args.steps
         peak256, peak64 = libmogp.peak_i8_tops(device)
         ach = ops_step / (rows_ms * 1e-3) * 1e-12
         roofline = {"bound": "tensor", "kernel": "i8_row_kernel<%d> (V_i = K~*_i - sum_j L~_ij V_j, tcgen05.mma kind::i8, "
@@ -375,7 +375,7 @@ def run_b200(args, wl):
                     "whole_trsm_phase": {"ms": tm["trsm_ms"] / args.steps, "fp64_equivalent_tflops": achieved,
                                          "vs_dmma_peak": achieved / peak if achieved else None}}
     config = workload_config(args.workload, wl, world)
-    if tm.get("i8_row_launches", 0) > 0:
+    if tm.get("i8_block_rows", 0) > 0:
         config["trsm_path"] = ("int8 tcgen05, %d planes per operand: the O(n^2 m) products of the FP64 forward substitution are "
                                "evaluated exactly on signed 7-bit digits (error-free splitting), everything else -- kernel "
                                "matrices, Cholesky, solves, means, the diagonal-block products, recombination and norms -- is "

@@ -125,8 +125,6 @@ struct mogp_handle {
     double* csync = nullptr;                       // Cholesky ticket/progress words (used as int)
     // int8 (tcgen05) predict TRSM: planes of L~ per output (valid until the output is fitted again), planes of V per call
     int8_t* Lq = nullptr;
-    int* eL = nullptr;
-    unsigned long long* rowmax = nullptr;
     double* Vq = nullptr;                          // (bytes; typed double for grow())
     size_t Vq_cap = 0;
     std::vector<char> lq_valid;
@@ -238,7 +236,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->sync, h->normacc, h->csync, h->U, h->aux, h->Lq, h->eL, h->rowmax, h->Vq, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
+                    h->sync, h->normacc, h->csync, h->U, h->aux, h->Lq, h->Vq, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -631,18 +629,13 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 if (!(hy[d + 1] >= 1.0e-7 * hy[d])) i8 = false;
             }
             if (i8) {
-                // planes of L~ (all outputs of the handle, allocated once) and of V (this call); if the device cannot hold them the
+                // planes of L (all outputs of the handle, allocated once) and of V (this call); if the device cannot hold them the
                 // call stays on the FP64 path
                 const int panels8 = (int)((mc + i8_panel_width() - 1) / i8_panel_width());
-                if (!h->Lq) {
-                    h->Lq = (int8_t*)pool_alloc(i8_lq_bytes(n_tiles, h->use_i8) * (size_t)h->E, h->device);
-                    h->eL = (int*)pool_alloc(sizeof(int) * (size_t)h->E * np, h->device);
-                    h->rowmax = (unsigned long long*)pool_alloc(sizeof(unsigned long long) * (size_t)MAXG * np, h->device);
-                }
-                if (!h->Lq || !h->eL || !h->rowmax ||
-                    grow(&h->Vq, &h->Vq_cap, i8_vq_bytes(cnt, panels8, n_tiles, h->use_i8), h->device) != MOGP_OK) {
-                    pool_free(h->Lq); pool_free(h->eL); pool_free(h->rowmax);
-                    h->Lq = nullptr; h->eL = nullptr; h->rowmax = nullptr;
+                if (!h->Lq) h->Lq = (int8_t*)pool_alloc(i8_lq_bytes(n_tiles, h->use_i8) * (size_t)h->E, h->device);
+                if (!h->Lq || grow(&h->Vq, &h->Vq_cap, i8_vq_bytes(cnt, panels8, n_tiles, h->use_i8), h->device) != MOGP_OK) {
+                    pool_free(h->Lq);
+                    h->Lq = nullptr;
                     std::fill(h->lq_valid.begin(), h->lq_valid.end(), 0);
                     cudaGetLastError();
                     h->use_i8 = 0;
@@ -661,34 +654,31 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 if (i8) {
                     const int S8 = h->use_i8;
                     const size_t lq_stride = i8_lq_bytes(n_tiles, S8);
+                    if ((rc = grow(&h->sync, &h->sync_cap, i8_sync_bytes(cnt, plan.panels), h->device))) return rc;
+                    std::vector<int> exps(cnt), stale, stale_exp;
+                    for (int k = 0; k < cnt; k++) {
+                        const double* hy = h->h_hyper + (size_t)outs[k] * (d + 2);
+                        exps[k] = i8_scale_exponent(hy[d], hy[d + 1]);
+                        if (!h->lq_valid[outs[k]]) {
+                            stale.push_back(outs[k]);
+                            stale_exp.push_back(exps[k]);
+                        }
+                    }
                     API_CUDA(cudaEventRecord(h->ev_d, h->main));
-                    std::vector<int> stale;
-                    for (int k = 0; k < cnt; k++)
-                        if (!h->lq_valid[outs[k]]) stale.push_back(outs[k]);
                     if (!stale.empty()) {
-                        // the planes of V (not yet written by this call) double as the FP64 scratch of the two passes when they are big enough
-                        double* scratch = h->Vq_cap >= i8_scratch_bytes((int)stale.size(), n_tiles) ? h->Vq : nullptr;
-                        if (i8_prepare_L(S8, h->A, h->Dinv, np, stale.data(), (int)stale.size(), h->Lq, (int64_t)lq_stride, h->eL,
-                                         h->rowmax, scratch, h->main)) {
-                            set_error("i8_prepare_L launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                        if (i8_slice_L(S8, h->A, np, stale.data(), stale_exp.data(), (int)stale.size(), h->Lq, (int64_t)lq_stride, h->main)) {
+                            set_error("i8_slice_L launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                             return MOGP_ERR_CUDA;
                         }
                         for (int o : stale) h->lq_valid[o] = 1;
-                        i8_prep_launches = 2;
+                        i8_prep_launches = 1;
                     }
                     API_CUDA(cudaEventRecord(h->ev_e, h->main));
-                    // K~* = blockdiag(L_ii)^-1 K* in place (FP64 DMMA, empty history), then the integer forward substitution
-                    CUtensorMap tmW32;
-                    if (make_kblocked_tmap(&tmW32, h->W, (int64_t)cnt * w_stride, np, 32)) {
-                        set_error("tensor map (W, 32 rows) failed");
-                        return MOGP_ERR_CUDA;
-                    }
-                    if (i8_ktilde(outs, cnt, h->maps.d128, tmW32, h->W, w_stride, np, (int64_t)plan.panels * plan.nw, h->n_sms,
-                                  h->main) ||
-                        cudaEventRecord(h->ev_f, h->main) != cudaSuccess ||
-                        i8_trsm(S8, outs, cnt, plan.panels, h->Lq, (int64_t)lq_stride, h->eL, (int8_t*)h->Vq, h->W, w_stride,
-                                h->hyper, h->h_hyper, d, include_nugget, want_var == 2 ? 1 : 0, np, mc, h->res + m + m0, 2 * m,
-                                h->normacc, h->n_sms, h->main)) {
+                    API_CUDA(cudaEventRecord(h->ev_f, h->main));
+                    // the integer forward substitution with its FP64 epilogue (K* in W is only read)
+                    if (i8_trsm(S8, outs, exps.data(), cnt, plan.panels, h->Lq, (int64_t)lq_stride, (int8_t*)h->Vq, h->maps.d128, h->W,
+                                w_stride, h->hyper, d, include_nugget, want_var == 2 ? 1 : 0, np, mc, h->res + m + m0, 2 * m,
+                                h->normacc, (int*)h->sync, h->n_sms, h->main)) {
                         set_error("i8 predict launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                         return MOGP_ERR_CUDA;
                     }
@@ -717,8 +707,8 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 h->timings[T_I8_PREP] += a;
                 h->timings[T_I8_KT] += b;
                 h->timings[T_I8_ROWS] += c;
-                h->timings[T_I8_NROWS] += n_tiles;
-                h->timings[T_NLAUNCH] += n_tiles + i8_prep_launches;
+                h->timings[T_I8_NROWS] += n_tiles;          // block rows solved by the (single) int8 launch
+                h->timings[T_NLAUNCH] += i8_prep_launches;
             }
         }
     }

@@ -64,22 +64,21 @@ int predict_trsm(const TrsmPlan& plan, const int* outs, int count, const CUtenso
 
 // ---- trsm_i8.cu: the predict TRSM from int8 slices on tcgen05 (many right-hand sides) ----
 int i8_init();
-// S = planes per operand: 6 (21 MMAs per K step) or 7 (28 MMAs, 128 x finer)
-size_t i8_lq_bytes(int T, int S);                           // planes of L~ per output (strictly lower blocks)
+// S = planes per operand: 6 (pairs t + u <= 7) or 7 (t + u <= 8, 128 x finer)
+size_t i8_lq_bytes(int T, int S);                           // planes of L per output (strictly lower blocks)
 size_t i8_vq_bytes(int count, int panels, int T, int S);    // planes of V for one batched call
+size_t i8_sync_bytes(int count, int panels);                // ticket counter + per-panel progress words
 int i8_panel_width();
-// L~ = blockdiag(L_ii)^-1 L of the listed outputs -> planes + per-row scale exponents (rowmax: scratch [min(count,MAXG)][n_pad])
-// scratch (optional, i8_scratch_bytes(count, T) bytes of FP64): L~ is parked there between the two passes instead of being formed twice
-size_t i8_scratch_bytes(int count, int T);
-int i8_prepare_L(int S, const double* A_slab, const double* Dinv_slab, int64_t n_pad, const int* outs, int count, int8_t* Lq,
-                 int64_t lq_stride, int* eL, unsigned long long* rowmax, double* scratch, cudaStream_t st);
-// W <- blockdiag(L_ii)^-1 W for the first m_rows test points of every listed output (tmW32: K-blocked map over W, box 32 rows)
-int i8_ktilde(const int* outs, int count, const CUtensorMap& tmD, const CUtensorMap& tmW32, double* W, int64_t w_stride,
-              int64_t n_pad, int64_t m_rows, int n_sms, cudaStream_t st);
-// forward substitution, one launch per block row; W holds K~* = blockdiag(L_ii)^-1 K* on entry
-int i8_trsm(int S, const int* outs, int count, int panels, const int8_t* Lq, int64_t lq_stride, const int* eL, int8_t* Vq,
-            const double* W, int64_t w_stride, const double* hyper, const double* h_hyper, int d, int include_nugget,
-            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int n_sms,
+// exponent e of the common power-of-two scale of L and V of one output: sqrt(sigma2 + nugget) <= 2^(e-1)
+int i8_scale_exponent(double sigma2, double nugget);
+// planes of the strictly lower 128 x 128 blocks of L of the listed outputs (exps[k] = i8_scale_exponent of outs[k])
+int i8_slice_L(int S, const double* A_slab, int64_t n_pad, const int* outs, const int* exps, int count, int8_t* Lq,
+               int64_t lq_stride, cudaStream_t st);
+// forward substitution + variances, one persistent launch; W holds K* (test-major) and is only read; tmD: K-blocked map
+// over the Dinv slab (box 128 rows); sync: i8_sync_bytes(count, panels) bytes (zeroed by the call)
+int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, const int8_t* Lq, int64_t lq_stride, int8_t* Vq,
+            const CUtensorMap& tmD, const double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
+            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync, int n_sms,
             cudaStream_t st);
 
 // ---- grad.cu ----

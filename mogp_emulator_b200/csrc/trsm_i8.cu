@@ -1,32 +1,37 @@
-// Predict TRSM on the tcgen05 tensor cores: FP64-equivalent blocked forward substitution from int8 slices
-// (Ozaki-style error-free splitting), for emulators with many right-hand sides (C3 / C5 shapes).
+// Predict TRSM on the tcgen05 tensor cores: FP64-equivalent blocked forward substitution whose O(n^2 m) part runs as
+// exact integer GEMM on int8 slices (Ozaki-style error-free splitting), for emulators with many right-hand sides
+// (C3 / C5 shapes).
 //
 // What it computes is what predict.cu computes -- V = L^-1 K* and var_c = sigma2 [+ nugget] - ||V_c||^2
-// (GaussianProcess.predict, GaussianProcess.py:896-920) -- reorganised so that the O(n^2 m) part is integer GEMM:
+// (GaussianProcess.predict, GaussianProcess.py:896-920):
 //
-//     V_i = inv(L_ii) K*_i - sum_{j<i} (inv(L_ii) L_ij) V_j  =  K~*_i - sum_{j<i} L~_ij V_j
+//     V_i = inv(L_ii) (K*_i - sum_{j<i} L_ij V_j)
 //
-//   * L~ = blockdiag(L_ii)^-1 L is formed once per fit in FP64 (i8_lprep_kernel) and stored as S signed 7-bit planes per
-//     element with one power-of-two scale per row (a row of L~ is a fixed-point number with 7 S fractional bits);
-//   * K~* = blockdiag(L_ii)^-1 K* is formed in place in FP64 (i8_ktilde_kernel, DMMA);
-//   * every solved block row V_i is kept only as S int8 planes with one scale per output (||V_c||^2 <= sigma2, so
-//     |V| <= sqrt(sigma2 + nugget)): S bytes per element instead of 8, never re-read in FP64;
-//   * the products L~_ij V_j are tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) into s32 accumulators in TMEM: the
-//     S (S + 1) / 2 plane pairs (t, u) with t + u <= S + 1 of a K step go to S accumulators, one per weight 2^-7(t+u);
-//     pairs of smaller weight are dropped.  Integer accumulation is exact: |digit| <= 64, so a column of n = 16384 terms
+//   * the strictly lower 128 x 128 blocks of L are stored once per fit as S signed 7-bit planes per element with ONE
+//     power-of-two scale per output (|L_rc| <= sqrt(K_rr) = sqrt(sigma2 + nugget)): a pure slicing pass (i8_slice_kernel);
+//   * every solved block row V_i is kept only as S int8 planes with the same kind of scale (||V_c||^2 <= sigma2): S bytes
+//     per element instead of 8, never stored or re-read in FP64;
+//   * the products L_ij V_j are tcgen05.mma.kind::i8 into s32 accumulators in TMEM, one accumulator of N = 64 columns
+//     per weight 2^-7(t+u), t + u <= S + 1 (pairs of smaller weight are dropped).  Plane t of L multiplies the planes
+//     1 .. S+1-t of V in ONE instruction chain: the planes of V are contiguous in N in shared memory and the accumulators
+//     contiguous in TMEM in weight order, so an MMA of N = 64 (S+1-t) columns drops every pair into the accumulator of its
+//     weight -- 10 MMAs of N <= 256 per K = 32 step instead of 28 of N = 64 (the N = 64 form is bound by its shared-memory
+//     operand reads: 6 KB per 32-cycle MMA).  Integer accumulation is exact: |digit| <= 64, a column of n = 16384 terms
 //     times 7 pairs stays below 2^30;
-//   * recombination (TMEM -> FP64, S weights, row and output scales), the subtraction from K~*_i, the column norms and the
-//     slicing of V_i are the epilogue of the consumer warps; the MMA warp already works on the next tile meanwhile.
+//   * the epilogue is FP64: T_i = K*_i - 2^(eL+eV) sum_w 2^-7w acc_w (TMEM -> registers -> shared memory, K-blocked), then
+//     V_i = inv(L_ii) T_i on the FP64 tensor pipe (DMMA, inv(L_ii) streamed by TMA in 16 KB chunks, the zero upper triangle
+//     skipped), column norms, and the S digits of V_i assembled as a plane image in shared memory that one cp.async.bulk
+//     stores.  The MMA warp works on the next tile meanwhile.
 //
-// S = 7 is the library default (>= 100 x inside the variance tolerance on every case measured), S = 6 is opt-in
-// (MOGP_TRSM_I8=6; at the edge of the tolerance on small ill-conditioned problems) -- DESIGN.md section 3 has the table.
+// ONE persistent launch for the whole solve: tiles (block row i, panel of 64 test points, output) are drawn from a global
+// ticket counter in block-row-major order; the only dependency of a tile is the same panel's previous block row, which
+// has a smaller ticket and is therefore held by a running CTA (a per-panel progress word, red.release / ld.acquire).  No
+// per-row launches, no static tile assignment (SMs differ by ~10 % in L2 distance), no wave quantisation.
 //
-// One launch per block row i (all panels of all outputs of the call are independent inside a launch): a persistent grid,
-// per CTA a loader warp (cp.async.bulk of contiguous plane blocks into a 5- or 6-stage mbarrier ring that takes all the
-// shared memory), an MMA warp (one elected thread issues, tcgen05.commit frees ring slots / publishes the accumulators)
-// and 8 consumer warps.  The kernel is bound by the operand feed out of L2 (5.4 - 5.9 TB/s, profiles/r01_c3_i8_row*.txt).
-// tools/ozaki_study.py (profiles/r01_ozaki_study.txt) is the error study, oracle/i8_emulation.py the exact CPU emulation of
-// this arithmetic, tools/probe_i8*.cu measured the instruction (exact s32 results; the M128 N64 K32 shape issues at 3.0 POP/s).
+// Per CTA (352 threads): warps 0-7 consumers (TMEM drain, FP64 epilogue), warp 8 MMA issuer (one elected thread),
+// warp 9 ticket + operand loader (cp.async.bulk of contiguous plane blocks into a 3-stage mbarrier ring), warp 10 loader
+// of the inv(L_ii) chunks.  S = 7 is the library default, S = 6 opt-in (MOGP_TRSM_I8=6); DESIGN.md section 3 has the
+// error table, oracle/i8_emulation.py the exact CPU emulation of this arithmetic, tools/probe_i8*.cu the instruction probes.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -35,28 +40,37 @@
 namespace mogp {
 
 constexpr int I8_BITS = 7;                    // bits per plane (signed digit in [-64, 64])
-constexpr int I8_BN = 64;                     // test points per tile (MMA N)
-constexpr int I8_APLANE = NB * 32;            // bytes of one plane of a K = 32 step of L~ (128 rows)
+constexpr int I8_BN = 64;                     // test points per tile (MMA N per accumulator)
+constexpr int I8_APLANE = NB * 32;            // bytes of one plane of a K = 32 step of L (128 rows)
 constexpr int I8_BPLANE = I8_BN * 32;         // ... of V (64 columns)
-constexpr int I8_THREADS = 320;               // 8 consumer warps + MMA warp + loader warp
+constexpr int I8_NCW = 8;                     // consumer warps
+constexpr int I8_THREADS = (I8_NCW + 3) * 32; // + MMA warp + loader warp + inv(L_ii) loader warp
+constexpr int I8_QN = 4;                      // ticket queue depth
+constexpr int I8_DCHUNK = NB * KC * 8;        // one K chunk (16 columns) of inv(L_ii): 16 KB, K-blocked
 
-// S planes per operand: S = 6 keeps the pairs t + u <= 7 (21 MMAs per K step, products resolved to 2^-49 of the row and
-// output scales), S = 7 the pairs t + u <= 8 (28 MMAs, 2^-56): the accurate default, see the error table in DESIGN.md
+// S planes per operand: S = 6 keeps the pairs t + u <= 7 (products resolved to 2^-49 of the two scales), S = 7 the pairs
+// t + u <= 8 (2^-56): the accurate default, see the error table in DESIGN.md
 template <int S>
 struct I8Cfg {
-    static constexpr int NS = (S == 6) ? 6 : 5;             // ring stages: the feed is latency-bound, all shared memory goes to the ring
+    static constexpr int NS = 3;                            // ring stages (a deeper ring changed nothing: profiles/r01)
     static constexpr int ASTAGE = S * I8_APLANE;
     static constexpr int BSTAGE = S * I8_BPLANE;
     static constexpr int STAGE = ASTAGE + BSTAGE;
-    static constexpr int LBLOCK = 4 * ASTAGE;               // one 128 x 128 block of L~: 4 K steps
+    static constexpr int LBLOCK = 4 * ASTAGE;               // one 128 x 128 block of L: 4 K steps
     static constexpr int VBLOCK = 4 * BSTAGE;               // one 128-row block of V for one panel
-    static constexpr int SMEM = NS * STAGE + 4 * I8_BN * 8 + 256 + 128;
+    static constexpr int OFF_T = NS * STAGE;                // T_i (FP64, K-blocked, 64 KB); later the plane image of V_i
+    static constexpr int OFF_D = OFF_T + NB * I8_BN * 8;    // two chunks of inv(L_ii)
+    static constexpr int OFF_NRED = OFF_D + 2 * I8_DCHUNK;  // [8 warps][64] column-norm partials
+    static constexpr int OFF_BAR = OFF_NRED + I8_NCW * I8_BN * 8;
+    static constexpr int SMEM = OFF_BAR + 256 + 128;
     static_assert(S * I8_BN <= 512, "one s32 accumulator group per weight must fit TMEM");
+    static_assert(SMEM <= 232448, "shared memory per CTA");
+    static_assert(VBLOCK <= NB * I8_BN * 8, "the plane image reuses the T buffer");
 };
 
 // byte offset of element (row r, k in [0, 32)) inside a plane of a K = 32 step: K-major, no swizzle, 8 x 16-byte core
 // matrices; leading (K half) byte offset 128, stride (8-row group) byte offset 256 (checked by tools/probe_i8.cu)
-__device__ __forceinline__ int i8_plane_off(int r, int kk) {
+__host__ __device__ __forceinline__ int i8_plane_off(int r, int kk) {
     return (r >> 3) * 256 + ((kk >> 4) & 1) * 128 + (r & 7) * 16 + (kk & 15);
 }
 
@@ -81,6 +95,12 @@ __device__ __forceinline__ void i8_bulk_load(void* dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void i8_bulk_store(void* dst_global, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void i8_bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // mbarrier wait that traps instead of hanging the GPU if the pipeline protocol is ever violated
 __device__ __forceinline__ void i8_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -103,7 +123,7 @@ __device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
 // S signed 7-bit digits of x in (-0.5, 0.5):  x = sum_t d_t 2^-7t + O(2^-(7S+1)).  Every step is exact in FP64.
 template <int S>
 __device__ __forceinline__ void i8_digits(double x, int8_t (&dig)[S]) {
-    x = fmin(fmax(x, -0.99), 0.99);        // in-range data has |x| < 0.5; out-of-range input degrades instead of wrapping int8
+    x = fmin(fmax(x, -0.99), 0.99);        // in-range data has |x| <= 0.5; out-of-range input degrades instead of wrapping int8
     double y = x;
 #pragma unroll
     for (int t = 0; t < S; t++) {
@@ -115,336 +135,220 @@ __device__ __forceinline__ void i8_digits(double x, int8_t (&dig)[S]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// L~ = blockdiag(L_ii)^-1 L, strictly lower blocks, FP64; PASS 0: row maxima, PASS 1: digits
+// planes of the strictly lower blocks of L (one pass, no arithmetic besides the slicing)
 // ------------------------------------------------------------------------------------------------------------------
-struct I8PrepParams {
+struct I8SliceParams {
     const double* A;       // L slab [E][n_pad][n_pad]
-    const double* Dinv;    // [E][n_pad][128]
     int64_t n_pad;
     int outs[MAXG];
-    unsigned long long* rowmax;   // [count][n_pad] bit patterns of non-negative doubles
+    int eL[MAXG];          // scale exponent per listed output: L 2^-eL in [-0.5, 0.5]
     int8_t* Lq;            // [E][lq_stride]
     int64_t lq_stride;
-    int* eL;               // [E][n_pad]
-    double* scratch;       // optional [count][blocks][256 threads][64]: pass 0 parks L~ here, pass 1 only slices it
 };
 
-template <int PASS, int S>
-__global__ void __launch_bounds__(256) i8_lprep_kernel(const I8PrepParams p) {
+// grid (T (T-1) / 2 blocks, outputs); thread = (row, run of 16 columns): reads 128 contiguous bytes, writes one 16-byte
+// run per plane in the K-major core-matrix order tcgen05.mma reads without swizzle
+template <int S>
+__global__ void __launch_bounds__(256) i8_slice_kernel(const I8SliceParams p) {
     using Cfg = I8Cfg<S>;
-    __shared__ double As[NB][17];
-    __shared__ double Bs[16][NB];
     const int b = blockIdx.x;
     int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)b)) * 0.5f);
     while (i * (i - 1) / 2 > b) i--;
     while ((i + 1) * i / 2 <= b) i++;
     const int j = b - i * (i - 1) / 2;
     const int o = p.outs[blockIdx.y];
-    const double* L = p.A + (size_t)o * p.n_pad * p.n_pad;
-    const double* D = p.Dinv + (size_t)o * p.n_pad * NB;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double acc[8][8];
+    const double sc = ldexp(1.0, -p.eL[blockIdx.y]);
+    const double* Lb = p.A + ((size_t)o * p.n_pad + (size_t)i * NB) * p.n_pad + (size_t)j * NB;
+    int8_t* blk = p.Lq + (size_t)o * p.lq_stride + (size_t)b * Cfg::LBLOCK;
+    const int tid = threadIdx.x, cg = tid & 7;
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+        const int r = (tid >> 3) + 32 * it;
+        const double2* src = reinterpret_cast<const double2*>(Lb + (size_t)r * p.n_pad + cg * 16);
+        uint32_t w[S][4];
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+        for (int t = 0; t < S; t++)
 #pragma unroll
-        for (int v = 0; v < 8; v++) acc[u][v] = 0.0;
-    double* park = p.scratch ? p.scratch + (((size_t)blockIdx.y * gridDim.x + b) * 256 + tid) * 64 : nullptr;
-    if (PASS == 1 && park) {
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-#pragma unroll
-            for (int v = 0; v < 8; v += 2) {
-                const double2 t2 = *reinterpret_cast<const double2*>(park + u * 8 + v);
-                acc[u][v] = t2.x;
-                acc[u][v + 1] = t2.y;
-            }
-    }
-    for (int k0 = 0; k0 < ((PASS == 1 && park) ? 0 : NB); k0 += 16) {
+            for (int q = 0; q < 4; q++) w[t][q] = 0u;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            const int idx = tid + q * 256;
-            // inv(L_ii) is lower triangular: entries above the diagonal are taken as exact zeros whatever the slab holds
-            As[idx >> 4][idx & 15] = (k0 + (idx & 15) <= (idx >> 4)) ? D[(size_t)(i * NB + (idx >> 4)) * NB + k0 + (idx & 15)] : 0.0;
-            Bs[idx >> 7][idx & 127] = L[(size_t)(i * NB + k0 + (idx >> 7)) * p.n_pad + (size_t)j * NB + (idx & 127)];
+            const double2 v = __ldcs(src + q);
+            int8_t d0[S], d1[S];
+            i8_digits<S>(v.x * sc, d0);
+            i8_digits<S>(v.y * sc, d1);
+#pragma unroll
+            for (int t = 0; t < S; t++)
+                w[t][q >> 1] |= ((uint32_t)(uint8_t)d0[t] | ((uint32_t)(uint8_t)d1[t] << 8)) << (16 * (q & 1));
         }
-        __syncthreads();
+        // columns cg*16 .. +15: K step cg >> 1, K half cg & 1
+        int8_t* dst = blk + (size_t)(cg >> 1) * Cfg::ASTAGE + (r >> 3) * 256 + (cg & 1) * 128 + (r & 7) * 16;
 #pragma unroll
-        for (int kk = 0; kk < 16; kk++) {
-            double a[8], bb[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) a[u] = As[ty * 8 + u][kk];
-#pragma unroll
-            for (int v = 0; v < 8; v++) bb[v] = Bs[kk][v * 16 + tx];      // columns strided by 16: conflict-free
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-#pragma unroll
-                for (int v = 0; v < 8; v++) acc[u][v] = fma(a[u], bb[v], acc[u][v]);
-        }
-        __syncthreads();
-    }
-    unsigned long long* rm = p.rowmax + (size_t)blockIdx.y * p.n_pad + (size_t)i * NB;
-    if (PASS == 0) {
-        if (park) {
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-#pragma unroll
-                for (int v = 0; v < 8; v += 2) *reinterpret_cast<double2*>(park + u * 8 + v) = make_double2(acc[u][v], acc[u][v + 1]);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            double mx = 0.0;
-#pragma unroll
-            for (int v = 0; v < 8; v++) mx = fmax(mx, fabs(acc[u][v]));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-            if (tx == 0 && mx > 0.0) atomicMax(rm + ty * 8 + u, (unsigned long long)__double_as_longlong(mx));
-        }
-        return;
-    }
-    int8_t* blk = p.Lq + (size_t)o * p.lq_stride + (size_t)b * Cfg::LBLOCK;
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const int r = ty * 8 + u;
-        const double mx = __longlong_as_double((long long)rm[r]);
-        int e = 0;
-        if (mx > 0.0) frexp(mx, &e);
-        e += 1;                                   // scaled row in (-0.5, 0.5)
-        if (j == 0 && tx == 0) p.eL[(size_t)o * p.n_pad + (size_t)i * NB + r] = e;
-        const double sc = ldexp(1.0, -e);
-#pragma unroll
-        for (int v = 0; v < 8; v++) {
-            const int c = v * 16 + tx;            // column of the block = K index of the MMA
-            int8_t dig[S];
-            i8_digits<S>(acc[u][v] * sc, dig);
-            int8_t* dst = blk + (size_t)(c >> 5) * Cfg::ASTAGE + i8_plane_off(r, c & 31);
-#pragma unroll
-            for (int t = 0; t < S; t++) dst[(size_t)t * I8_APLANE] = dig[t];
-        }
+        for (int t = 0; t < S; t++)
+            *reinterpret_cast<uint4*>(dst + (size_t)t * I8_APLANE) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K~* = blockdiag(L_ii)^-1 K*, in place in the test-major workspace (FP64 DMMA)
-//
-// Unit of work = (output, block row i): inv(L_ii) is loaded ONCE into shared memory as the A operand (128 KB, K-blocked) and
-// every 32-test-point tile of K*_i streams through a two-slot TMA ring as the B operand -- 32 KB in, one
-// mma_stage<1,4,128> per consumer warp (16 rows each), 32 KB out.  (The dataflow kernel of predict.cu, run with an empty
-// history, reloads inv(L_ii) for every tile and serialises the right-hand-side load with the product: 16 ms at C3.)
+// the forward substitution: one persistent launch
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int KT_BN = 32;
-constexpr int KT_A_BYTES = NB * NB * 8, KT_B_BYTES = KT_BN * NB * 8;
-constexpr int KT_SMEM = KT_A_BYTES + 2 * KT_B_BYTES + 128 + 128;
-
-struct KtParams {
-    double* W;
-    int64_t w_stride, n_pad;
-    int T, tiles, count;        // tiles of KT_BN test points per output
-    int outs[MAXG];
-};
-
-__global__ void __launch_bounds__(288, 1)
-i8_ktilde_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW, const KtParams p) {
-    extern __shared__ __align__(128) unsigned char kt_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(kt_smem_raw) + 127) & ~uintptr_t(127));
-    double* As = reinterpret_cast<double*>(base);                                  // [16][128][8]
-    unsigned char* Bring = base + KT_A_BYTES;                                      // 2 x [16][32][8]
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(Bring + 2 * KT_B_BYTES);
-    uint64_t* a_empty = a_full + 1;
-    uint64_t* b_full = a_empty + 1;   // [2]
-    uint64_t* b_empty = b_full + 2;   // [2]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int units = p.count * p.T;
-    if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 8);
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 8);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (warp == 8) {
-        if (lane == 0) {
-            prefetch_tmap(&tmD);
-            prefetch_tmap(&tmW);
-            int it = 0, k = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x, k++) {
-                const int o = u / p.T, i = u - o * p.T;
-                if (k > 0) i8_wait(a_empty, (uint32_t)((k - 1) & 1));       // consumers are done with the previous inv(L_ii)
-                mbar_arrive_expect_tx(a_full, KT_A_BYTES);
-                for (int ch = 0; ch < NB / KC; ch++)
-                    tma_load_3d(reinterpret_cast<unsigned char*>(As) + ch * (KC / 8) * NB * 64, &tmD, 0,
-                                (int)(p.outs[o] * p.n_pad) + i * NB, ch * (KC / 8), a_full);
-                for (int tl = 0; tl < p.tiles; tl++, it++) {
-                    const int slot = it & 1;
-                    if (it >= 2) i8_wait(&b_empty[slot], (uint32_t)(((it >> 1) - 1) & 1));
-                    mbar_arrive_expect_tx(&b_full[slot], KT_B_BYTES);
-                    for (int ch = 0; ch < NB / KC; ch++)
-                        tma_load_3d(Bring + slot * KT_B_BYTES + ch * (KC / 8) * KT_BN * 64, &tmW, 0,
-                                    (int)(o * p.w_stride) + tl * KT_BN, i * (NB / 8) + ch * (KC / 8), &b_full[slot]);
-                }
-            }
-        }
-        return;
-    }
-    const int g = lane >> 2, t4 = lane & 3;
-    const int arow0 = warp * 16;
-    int it = 0, k = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, k++) {
-        const int o = u / p.T, i = u - o * p.T;
-        i8_wait(a_full, (uint32_t)(k & 1));
-        for (int tl = 0; tl < p.tiles; tl++, it++) {
-            const int slot = it & 1;
-            i8_wait(&b_full[slot], (uint32_t)((it >> 1) & 1));
-            double acc[1][4][4];
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-                for (int e = 0; e < 4; e++) acc[0][nt][e] = 0.0;
-            mma_stage<1, 4, NB>(acc, As, NB, arow0, reinterpret_cast<const double*>(Bring + slot * KT_B_BYTES), KT_BN, 0, g, t4);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_empty[slot]);
-            // W[test point c][i*128 + row] <- acc (row = arow0 + g (+8), c = 8 nt + 2 t4 (+1))
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-                for (int e1 = 0; e1 < 2; e1++) {
-                    const int c = nt * 8 + 2 * t4 + e1;
-                    double* wr = p.W + ((int64_t)o * p.w_stride + (int64_t)tl * KT_BN + c) * p.n_pad + (int64_t)i * NB + arow0 + g;
-                    wr[0] = acc[0][nt][e1];
-                    wr[8] = acc[0][nt][2 + e1];
-                }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// one block row of the forward substitution
-// ------------------------------------------------------------------------------------------------------------------
-struct I8RowParams {
+struct I8TrsmParams {
     const int8_t* Lq;
     int64_t lq_stride;
-    const int* eL;          // [E][n_pad]
-    int8_t* Vq;             // [count][panels][T][I8_VBLOCK]
-    const double* W;        // K~* (test-major): [count][w_stride][n_pad]
+    int8_t* Vq;             // [count][panels][T][VBLOCK]
+    const double* W;        // K* (test-major): [count][w_stride][n_pad]; read only
     int64_t w_stride, n_pad, m;
-    int T, panels, count, i;
+    int T, panels, count;
     int outs[MAXG];
-    int eV[MAXG];           // scale exponent of V per local output
+    int eS[MAXG];           // scale exponent of L and of V per local output (both bounded by sqrt(sigma2 + nugget))
     const double* hyper;
     int hyper_stride, d, include_nugget, no_clip;
-    int wide;               // wide-N MMA form (default); MOGP_I8_WIDE=0 keeps one MMA per plane pair
     double* var;
     int64_t var_stride;
     double* normacc;        // [count][w_stride]
+    int* sync;              // [0] ticket counter, [32 ..] block rows finished per (output, panel); zeroed per launch
 };
 
+constexpr int I8_SYNC_HDR = 32;
+
 template <int S>
-__global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams p) {
+__global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const I8TrsmParams p) {
     using Cfg = I8Cfg<S>;
-    constexpr int I8_NS = Cfg::NS, I8_STAGE = Cfg::STAGE, I8_ASTAGE = Cfg::ASTAGE, I8_BSTAGE = Cfg::BSTAGE;
-    constexpr int I8_LBLOCK = Cfg::LBLOCK, I8_VBLOCK = Cfg::VBLOCK, I8_S = S;
+    constexpr int NS = Cfg::NS, STAGE = Cfg::STAGE, ASTAGE = Cfg::ASTAGE, BSTAGE = Cfg::BSTAGE;
+    constexpr int LBLOCK = Cfg::LBLOCK, VBLOCK = Cfg::VBLOCK;
     extern __shared__ __align__(128) unsigned char i8_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 127) & ~uintptr_t(127));
-    double* nred = reinterpret_cast<double*>(base + I8_NS * I8_STAGE);              // [4][64]
-    uint64_t* full = reinterpret_cast<uint64_t*>(nred + 4 * I8_BN);                 // [NS]
-    uint64_t* empty = full + I8_NS;                                                 // [NS]
-    uint64_t* acc_full = empty + I8_NS;
+    double* Ts = reinterpret_cast<double*>(base + Cfg::OFF_T);                       // [16 slabs][64 columns][8]
+    unsigned char* img = base + Cfg::OFF_T;                                          // [4 K steps][S planes][2048]
+    unsigned char* dring = base + Cfg::OFF_D;
+    double* nred = reinterpret_cast<double*>(base + Cfg::OFF_NRED);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + Cfg::OFF_BAR);               // [NS]
+    uint64_t* empty = full + NS;                                                     // [NS]
+    uint64_t* acc_full = empty + NS;
     uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* d_full = acc_empty + 1;                                                // [2]
+    uint64_t* d_empty = d_full + 2;                                                  // [2]
+    uint64_t* tq_full = d_empty + 2;                                                 // [QN]
+    uint64_t* tq_empty = tq_full + I8_QN;                                            // [QN]
+    int* tq = reinterpret_cast<int*>(tq_empty + I8_QN);                              // [QN]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tq + I8_QN);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int i = p.i;
-    const int nst = 4 * i;                          // K = 32 steps per tile
-    const int ntiles = p.count * p.panels;
-    const bool last = (i + 1 == p.T);
+    const int T = p.T;
+    const int per_row = p.count * p.panels;
+    const int total = T * per_row;
+    int* flags = p.sync + I8_SYNC_HDR;
 
-    if (warp == 8 && nst > 0) {
+    if (warp == I8_NCW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < I8_NS; s++) {
+        for (int s = 0; s < NS; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 8);
+        mbar_init(acc_empty, I8_NCW);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], I8_NCW);
+        }
+        for (int s = 0; s < I8_QN; s++) {
+            mbar_init(&tq_full[s], 1);
+            mbar_init(&tq_empty[s], I8_NCW + 2);     // consumer warps + MMA issuer + inv(L_ii) loader
+        }
         fence_mbar_init();
     }
     i8_fence_before();
     __syncthreads();
     i8_fence_after();
-    const uint32_t tmem = (nst > 0) ? *tmem_slot : 0u;
+    const uint32_t tmem = *tmem_slot;
 
-    if (warp == 9) {
-        // ================================ loader ================================
-        if (lane == 0 && nst > 0) {
+    if (warp == I8_NCW + 1) {
+        // ================================ tickets + operand loader ================================
+        if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int nq = 0;; nq++) {
+                const int slot = nq % I8_QN;
+                if (nq >= I8_QN) i8_wait(&tq_empty[slot], (uint32_t)(((nq / I8_QN) - 1) & 1));
+                const int t = atomicAdd(p.sync, 1);
+                tq[slot] = (t < total) ? t : -1;
+                mbar_arrive(&tq_full[slot]);
+                if (t >= total) break;
+                const int i = t / per_row, tile = t - i * per_row;
+                if (i == 0) continue;
                 const int o = tile / p.panels;
-                const int8_t* a_src = p.Lq + (size_t)p.outs[o] * p.lq_stride + (size_t)(i * (i - 1) / 2) * I8_LBLOCK;
-                const int8_t* b_src = p.Vq + (size_t)tile * p.T * I8_VBLOCK;
-                for (int st = 0; st < nst; st++, it++) {
-                    const int slot = it % I8_NS;
-                    if (it >= I8_NS) i8_wait(&empty[slot], (uint32_t)(((it / I8_NS) - 1) & 1));
-                    unsigned char* dst = base + slot * I8_STAGE;
-                    mbar_arrive_expect_tx(&full[slot], I8_STAGE);
-                    i8_bulk_load(dst, a_src + (size_t)st * I8_ASTAGE, I8_ASTAGE, &full[slot]);
-                    i8_bulk_load(dst + I8_ASTAGE, b_src + (size_t)st * I8_BSTAGE, I8_BSTAGE, &full[slot]);
+                // the panel's block rows 0 .. i-1 are solved and their planes stored (async-proxy writes of another CTA,
+                // published by red.release after the bulk store completed)
+                wait_counter(flags + tile, i);
+                fence_proxy_async();
+                const int8_t* a_src = p.Lq + (size_t)p.outs[o] * p.lq_stride + (size_t)(i * (i - 1) / 2) * LBLOCK;
+                const int8_t* b_src = p.Vq + (size_t)tile * T * VBLOCK;
+                for (int st = 0; st < 4 * i; st++, it++) {
+                    const int rs = it % NS;
+                    if (it >= NS) i8_wait(&empty[rs], (uint32_t)(((it / NS) - 1) & 1));
+                    unsigned char* dst = base + rs * STAGE;
+                    mbar_arrive_expect_tx(&full[rs], STAGE);
+                    i8_bulk_load(dst, a_src + (size_t)st * ASTAGE, ASTAGE, &full[rs]);
+                    i8_bulk_load(dst + ASTAGE, b_src + (size_t)st * BSTAGE, BSTAGE, &full[rs]);
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == I8_NCW + 2) {
+        // ================================ inv(L_ii) loader ================================
+        if (lane == 0) {
+            prefetch_tmap(&tmD);
+            int dc = 0;
+            for (int nq = 0;; nq++) {
+                const int slot = nq % I8_QN;
+                i8_wait(&tq_full[slot], (uint32_t)((nq / I8_QN) & 1));
+                const int t = tq[slot];
+                mbar_arrive(&tq_empty[slot]);
+                if (t < 0) break;
+                const int i = t / per_row, tile = t - i * per_row;
+                const int o = tile / p.panels;
+                const int drow = (int)(p.outs[o] * p.n_pad) + i * NB;
+                for (int ch = 0; ch < NB / KC; ch++, dc++) {
+                    const int ds = dc & 1;
+                    if (dc >= 2) i8_wait(&d_empty[ds], (uint32_t)(((dc >> 1) - 1) & 1));
+                    mbar_arrive_expect_tx(&d_full[ds], I8_DCHUNK);
+                    tma_load_3d(dring + ds * I8_DCHUNK, &tmD, 0, drow, ch * (KC / 8), &d_full[ds]);
+                }
+            }
+        }
+    } else if (warp == I8_NCW) {
         // ================================ MMA issuer ================================
-        if (lane == 0 && nst > 0) {
+        if (lane == 0) {
             int it = 0, k = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+            for (int nq = 0;; nq++) {
+                const int slot = nq % I8_QN;
+                i8_wait(&tq_full[slot], (uint32_t)((nq / I8_QN) & 1));
+                const int t = tq[slot];
+                mbar_arrive(&tq_empty[slot]);
+                if (t < 0) break;
+                const int i = t / per_row;
+                if (i == 0) continue;
                 if (k > 0) {          // the consumers must have drained the accumulators of the previous tile
                     i8_wait(acc_empty, (uint32_t)((k - 1) & 1));
                     i8_fence_after();
                 }
-                for (int st = 0; st < nst; st++, it++) {
-                    const int slot = it % I8_NS;
-                    i8_wait(&full[slot], (uint32_t)((it / I8_NS) & 1));
+                k++;
+                for (int st = 0; st < 4 * i; st++, it++) {
+                    const int rs = it % NS;
+                    i8_wait(&full[rs], (uint32_t)((it / NS) & 1));
                     i8_fence_after();
-                    const uint32_t a0 = smem_u32(base + slot * I8_STAGE), b0 = a0 + I8_ASTAGE;
-                    if (p.wide) {
-                        // plane t of L~ against planes 1 .. S+1-t of V in one instruction chain: the planes of V are contiguous in N
-                        // (a plane is 8 row groups of 256 B) and the accumulators are contiguous in TMEM in weight order, so
-                        // D[:, 64 (t-1) ...] += A_t [B_1 | B_2 | ... | B_{S+1-t}] lands every pair (t, u) in the accumulator of weight
-                        // t + u.  10 MMAs of N <= 256 per K step instead of 28 of N = 64: the A plane is read from shared memory once
-                        // per t instead of once per pair (the N = 64 shape is bound by those reads: 6 KB per 32-cycle MMA).
+                    const uint32_t a0 = smem_u32(base + rs * STAGE), b0 = a0 + ASTAGE;
 #pragma unroll
-                        for (int t = 1; t <= I8_S; t++) {
-                            const int ncols = I8_BN * (I8_S + 1 - t);
-                            const uint32_t accum = (st == 0 && t == 1) ? 0u : 1u;
-                            const uint32_t d0 = tmem + (uint32_t)(t - 1) * I8_BN;
-                            const uint64_t ad = i8_desc(a0 + (t - 1) * I8_APLANE);
-                            const int n1 = ncols > 256 ? 256 : ncols;
-                            i8_mma(d0, ad, i8_desc(b0), accum, i8_idesc(n1));
-                            if (ncols > 256) i8_mma(d0 + 256, ad, i8_desc(b0 + 4 * I8_BPLANE), accum, i8_idesc(ncols - 256));
-                        }
-                    } else {
-#pragma unroll
-                    for (int w = 2; w <= I8_S + 1; w++) {
-                        uint32_t accum = (st == 0) ? 0u : 1u;
-#pragma unroll
-                        for (int t = 1; t < w; t++) {
-                            const int u = w - t;
-                            if (t > I8_S || u > I8_S) continue;
-                            i8_mma(tmem + (uint32_t)(w - 2) * I8_BN, i8_desc(a0 + (t - 1) * I8_APLANE),
-                                   i8_desc(b0 + (u - 1) * I8_BPLANE), accum, i8_idesc(I8_BN));
-                            accum = 1u;
-                        }
+                    for (int tt = 1; tt <= S; tt++) {
+                        const int ncols = I8_BN * (S + 1 - tt);
+                        const uint32_t accum = (st == 0 && tt == 1) ? 0u : 1u;
+                        const uint32_t d0 = tmem + (uint32_t)(tt - 1) * I8_BN;
+                        const uint64_t ad = i8_desc(a0 + (tt - 1) * I8_APLANE);
+                        const int n1 = ncols > 256 ? 256 : ncols;
+                        i8_mma(d0, ad, i8_desc(b0), accum, i8_idesc(n1));
+                        if (ncols > 256) i8_mma(d0 + 256, ad, i8_desc(b0 + 4 * I8_BPLANE), accum, i8_idesc(ncols - 256));
                     }
-                    }
-                    i8_commit(&empty[slot]);      // the slot is free once these MMAs have read it
+                    i8_commit(&empty[rs]);        // the slot is free once these MMAs have read it
                 }
                 i8_commit(acc_full);              // every MMA of the tile has completed
             }
@@ -453,61 +357,125 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
         // ================================ consumers ================================
         const int q4 = warp & 3, h = warp >> 2;
         const int r = q4 * 32 + lane;             // row of the block row = TMEM lane
-        int k = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+        const int g = lane >> 2, t4 = lane & 3;   // DMMA fragment coordinates
+        int k = 0, dc = 0;
+        for (int nq = 0;; nq++) {
+            const int slot = nq % I8_QN;
+            i8_wait(&tq_full[slot], (uint32_t)((nq / I8_QN) & 1));
+            const int t = tq[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tq_empty[slot]);
+            if (t < 0) break;
+            const int i = t / per_row, tile = t - i * per_row;
             const int o = tile / p.panels, pnl = tile - o * p.panels;
-            double acc[32];
+            const bool last = (i + 1 == T);
+            const int es = p.eS[o];
+
+            // ---- T_i = K*_i - 2^(2 eS) sum_w 2^-7w acc_w  -> shared memory, K-blocked (the B operand of the diagonal product) ----
+            {
+                double acc[32];
 #pragma unroll
-            for (int c = 0; c < 32; c++) acc[c] = 0.0;
-            if (nst > 0) {
-                i8_wait(acc_full, (uint32_t)(k & 1));
-                i8_fence_after();
+                for (int c = 0; c < 32; c++) acc[c] = 0.0;
+                if (i > 0) {
+                    i8_wait(acc_full, (uint32_t)(k & 1));
+                    k++;
+                    i8_fence_after();
 #pragma unroll
-                for (int g = 0; g < I8_S; g++) {
-                    uint32_t v[32];
-                    i8_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(g * I8_BN + h * 32), v);
-                    const double wgt = __longlong_as_double((long long)(1023 - I8_BITS * (g + 2)) << 52);   // 2^-7(g+2)
+                    for (int w = 0; w < S; w++) {
+                        uint32_t v[32];
+                        i8_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(w * I8_BN + h * 32), v);
+                        const double wgt = __longlong_as_double((long long)(1023 - I8_BITS * (w + 2)) << 52);   // 2^-7(w+2)
 #pragma unroll
-                    for (int c = 0; c < 32; c++) acc[c] = fma((double)(int32_t)v[c], wgt, acc[c]);
+                        for (int c = 0; c < 32; c++) acc[c] = fma((double)(int32_t)v[c], wgt, acc[c]);
+                    }
+                    i8_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
                 }
-                i8_fence_before();
+                const double scale = ldexp(1.0, 2 * es);
+                const double* wsrc = p.W + ((size_t)o * p.w_stride + (size_t)pnl * I8_BN + h * 32) * p.n_pad + (size_t)i * NB + r;
+                // element (r, col) at Ts[r / 8][col ^ swz][r % 8]; swz flips the column parity for every second pair of slabs so
+                // that the four slabs a warp writes at once fall into distinct banks
+                const int ks = r >> 3, sw = (ks >> 1) & 1;
+                double* trow = Ts + (size_t)ks * I8_BN * 8 + (r & 7);
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const double v = __ldcs(wsrc + (size_t)c * p.n_pad) - acc[c] * scale;
+                    trow[((h * 32 + c) ^ sw) * 8] = v;
+                }
+            }
+            named_bar_sync(1, I8_NCW * 32);
+
+            // ---- V_i = inv(L_ii) T_i : warp w owns rows 16 w .. 16 w + 15, all 64 columns ----
+            double vf[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) vf[nt][e] = 0.0;
+            for (int ch = 0; ch < NB / KC; ch++, dc++) {
+                const int ds = dc & 1;
+                i8_wait(&d_full[ds], (uint32_t)((dc >> 1) & 1));
+                if (ch <= warp) {                                      // inv(L_ii) is lower triangular: columns > row are zero
+                    const double* As = reinterpret_cast<const double*>(dring + ds * I8_DCHUNK);
+#pragma unroll
+                    for (int ksl = 0; ksl < KC / 8; ksl++) {
+                        const double* ap = As + ((size_t)(ksl * NB + warp * 16 + g) * 8 + 2 * t4);
+                        const double2 a0 = *reinterpret_cast<const double2*>(ap);
+                        const double2 a1 = *reinterpret_cast<const double2*>(ap + 64);
+                        const int ks = ch * (KC / 8) + ksl, sw = (ks >> 1) & 1;
+                        const double* bp = Ts + (size_t)ks * I8_BN * 8 + 2 * t4;
+#pragma unroll
+                        for (int nt = 0; nt < 8; nt++) {
+                            const double2 bf = *reinterpret_cast<const double2*>(bp + ((nt * 8 + g) ^ sw) * 8);
+                            dmma_16x8x8(vf[nt], a0.x, a1.x, a0.y, a1.y, bf.x, bf.y);
+                        }
+                    }
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
+                if (lane == 0) mbar_arrive(&d_empty[ds]);
             }
-            // ---- V_i = K~*_i - 2^(eL + eV) acc ----
-            const int ev = p.eV[o];
-            const double scale = (nst > 0) ? ldexp(1.0, p.eL[(size_t)p.outs[o] * p.n_pad + (size_t)i * NB + r] + ev) : 0.0;
-            const double vinv = ldexp(1.0, -ev);
-            const double* wsrc = p.W + ((size_t)o * p.w_stride + (size_t)pnl * I8_BN + h * 32) * p.n_pad + (size_t)i * NB + r;
-            // digits of V_i go straight to the planes in global memory (K step of the later products = r / 32); a warp's
-            // store of one (column, plane) is two 16-byte runs
-            int8_t* dimg = p.Vq + ((size_t)tile * p.T + i) * I8_VBLOCK + q4 * I8_BSTAGE;
+            named_bar_sync(1, I8_NCW * 32);       // every warp is done reading T_i: the buffer becomes the plane image of V_i
+
+            // ---- column norms, digits of V_i ----
+            // vf[nt][e]: row 16 warp + g (+ 8 for e >= 2), column 8 nt + 2 t4 (+ 1 for odd e)
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const double v = __ldcs(wsrc + (size_t)c * p.n_pad) - acc[c] * scale;
-                if (!last) {
-                    int8_t dig[I8_S];
-                    i8_digits<I8_S>(v * vinv, dig);
-                    int8_t* dst = dimg + i8_plane_off(h * 32 + c, lane);
+            for (int nt = 0; nt < 8; nt++)
 #pragma unroll
-                    for (int t = 0; t < I8_S; t++) dst[t * I8_BPLANE] = dig[t];
+                for (int e1 = 0; e1 < 2; e1++) {
+                    double s = fma(vf[nt][e1], vf[nt][e1], vf[nt][2 + e1] * vf[nt][2 + e1]);
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (g == 0) nred[warp * I8_BN + nt * 8 + 2 * t4 + e1] = s;
                 }
-                double s = v * v;
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                if (lane == 0) nred[q4 * I8_BN + h * 32 + c] = s;
+            if (!last) {
+                const double vinv = ldexp(1.0, -es);
+                // K step of the later products = row / 32 = warp / 2, K half = warp & 1, byte in the 16-byte run = g (+ 8)
+                unsigned char* ib = img + (size_t)(warp >> 1) * BSTAGE + (warp & 1) * 128 + g;
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        int8_t dig[S];
+                        i8_digits<S>(vf[nt][e] * vinv, dig);
+                        unsigned char* dst = ib + nt * 256 + (2 * t4 + (e & 1)) * 16 + (e >> 1) * 8;
+#pragma unroll
+                        for (int tt = 0; tt < S; tt++) dst[tt * I8_BPLANE] = (unsigned char)dig[tt];
+                    }
+                fence_proxy_async();              // generic-proxy writes of the image -> the bulk store's async-proxy read
             }
-            named_bar_sync(1, 256);
+            named_bar_sync(1, I8_NCW * 32);
+            if (tid == 0 && !last) i8_bulk_store(p.Vq + ((size_t)tile * T + i) * VBLOCK, img, VBLOCK);
             if (tid < I8_BN) {
                 const int64_t cg = (int64_t)pnl * I8_BN + tid;
-                double nrm = (nred[tid] + nred[I8_BN + tid]) + (nred[2 * I8_BN + tid] + nred[3 * I8_BN + tid]);
+                double nrm = 0.0;
+#pragma unroll
+                for (int w = 0; w < I8_NCW; w++) nrm += nred[w * I8_BN + tid];
                 double* na = p.normacc + (int64_t)o * p.w_stride + cg;
-                if (i > 0) nrm += *na;
+                if (i > 0) nrm += __ldcg(na);
                 if (!last) {
                     *na = nrm;
+                    __threadfence();
                 } else if (cg < p.m) {
                     const int og = p.outs[o];
                     const double* hyp = p.hyper + (int64_t)og * p.hyper_stride;
@@ -515,12 +483,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
                     p.var[(int64_t)og * p.var_stride + cg] = p.no_clip ? (top - nrm) : fmax(top - nrm, 0.0);
                 }
             }
-            named_bar_sync(1, 256);      // nred is reused by the next tile
+            if (tid == 0 && !last) i8_bulk_store_wait();      // planes of V_i are in global memory; the image may be overwritten
+            named_bar_sync(1, I8_NCW * 32);
+            if (tid == 0 && !last) {
+                fence_proxy_async();
+                __threadfence();
+                red_release_gpu_add(flags + tile, 1);
+            }
         }
     }
     i8_fence_before();
     __syncthreads();
-    if (warp == 8 && nst > 0) {
+    if (warp == I8_NCW) {
         i8_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
     }
@@ -529,21 +503,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_row_kernel(const I8RowParams
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-int i8_ktilde(const int* outs, int count, const CUtensorMap& tmD, const CUtensorMap& tmW32, double* W, int64_t w_stride,
-              int64_t n_pad, int64_t m_rows, int n_sms, cudaStream_t st) {
-    KtParams p{};
-    p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.T = (int)(n_pad / NB); p.count = count;
-    p.tiles = (int)((m_rows + KT_BN - 1) / KT_BN);
-    for (int k = 0; k < count; k++) p.outs[k] = outs[k];
-    const int units = count * p.T;
-    i8_ktilde_kernel<<<(unsigned)(units < n_sms ? units : n_sms), 288, KT_SMEM, st>>>(tmD, tmW32, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
-}
-
 int i8_init() {
-    if (cudaFuncSetAttribute(i8_ktilde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(i8_row_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6>::SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(i8_row_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<7>::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(i8_trsm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(i8_trsm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<7>::SMEM) != cudaSuccess)
         return 1;
     return 0;
 }
@@ -553,58 +515,56 @@ static size_t vblock(int S) { return S == 6 ? I8Cfg<6>::VBLOCK : I8Cfg<7>::VBLOC
 size_t i8_lq_bytes(int T, int S) { return (size_t)T * (T - 1) / 2 * lblock(S); }
 size_t i8_vq_bytes(int count, int panels, int T, int S) { return (size_t)count * panels * T * vblock(S); }
 int i8_panel_width() { return I8_BN; }
+size_t i8_sync_bytes(int count, int panels) { return sizeof(int) * ((size_t)I8_SYNC_HDR + (size_t)count * panels); }
 
-size_t i8_scratch_bytes(int count, int T) { return (size_t)(count < MAXG ? count : MAXG) * (T * (T - 1) / 2) * NB * NB * 8; }
+// |L_rc| <= sqrt(K_rr) = sqrt(sigma2 + nugget) and |V| <= sqrt(k(x*, x*)) = sqrt(sigma2): one scale 2^e with
+// sqrt(sigma2 + nugget) <= 2^(e-1) serves both operands (scaled entries in [-0.5, 0.5])
+int i8_scale_exponent(double sigma2, double nugget) {
+    const double bound = sqrt(sigma2 + nugget);
+    int e = 0;
+    frexp(bound > 0.0 ? bound : 1.0, &e);      // bound = f 2^e, f in [0.5, 1)
+    return e + 1;
+}
 
-int i8_prepare_L(int S, const double* A_slab, const double* Dinv_slab, int64_t n_pad, const int* outs, int count, int8_t* Lq,
-                 int64_t lq_stride, int* eL, unsigned long long* rowmax, double* scratch, cudaStream_t st) {
+int i8_slice_L(int S, const double* A_slab, int64_t n_pad, const int* outs, const int* exps, int count, int8_t* Lq,
+               int64_t lq_stride, cudaStream_t st) {
     const int T = (int)(n_pad / NB);
     if (T < 2 || count < 1) return 0;
     for (int g0 = 0; g0 < count; g0 += MAXG) {
         const int cnt = count - g0 < MAXG ? count - g0 : MAXG;
-        I8PrepParams p{};
-        p.A = A_slab; p.Dinv = Dinv_slab; p.n_pad = n_pad; p.rowmax = rowmax; p.Lq = Lq; p.lq_stride = lq_stride; p.eL = eL;
-        p.scratch = scratch;
-        for (int k = 0; k < cnt; k++) p.outs[k] = outs[g0 + k];
-        if (cudaMemsetAsync(rowmax, 0, sizeof(unsigned long long) * (size_t)cnt * n_pad, st) != cudaSuccess) return 1;
+        I8SliceParams p{};
+        p.A = A_slab; p.n_pad = n_pad; p.Lq = Lq; p.lq_stride = lq_stride;
+        for (int k = 0; k < cnt; k++) {
+            p.outs[k] = outs[g0 + k];
+            p.eL[k] = exps[g0 + k];
+        }
         const dim3 grid((unsigned)(T * (T - 1) / 2), (unsigned)cnt);
-        i8_lprep_kernel<0, 6><<<grid, 256, 0, st>>>(p);
-        if (S == 6) i8_lprep_kernel<1, 6><<<grid, 256, 0, st>>>(p);
-        else i8_lprep_kernel<1, 7><<<grid, 256, 0, st>>>(p);
+        if (S == 6) i8_slice_kernel<6><<<grid, 256, 0, st>>>(p);
+        else i8_slice_kernel<7><<<grid, 256, 0, st>>>(p);
         if (cudaGetLastError() != cudaSuccess) return 1;
     }
     return 0;
 }
 
-// W holds K~* = blockdiag(L_ii)^-1 K* on entry (test-major); var receives the variances after the last block row
-int i8_trsm(int S, const int* outs, int count, int panels, const int8_t* Lq, int64_t lq_stride, const int* eL, int8_t* Vq,
-            const double* W, int64_t w_stride, const double* hyper, const double* h_hyper, int d, int include_nugget,
-            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int n_sms,
+// W holds K* (test-major, left untouched); var receives the variances after the last block row
+int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, const int8_t* Lq, int64_t lq_stride, int8_t* Vq,
+            const CUtensorMap& tmD, const double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
+            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync, int n_sms,
             cudaStream_t st) {
-    I8RowParams p{};
-    p.Lq = Lq; p.lq_stride = lq_stride; p.eL = eL; p.Vq = Vq; p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m;
+    I8TrsmParams p{};
+    p.Lq = Lq; p.lq_stride = lq_stride; p.Vq = Vq; p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m;
     p.T = (int)(n_pad / NB); p.panels = panels; p.count = count;
     p.hyper = hyper; p.hyper_stride = d + 2; p.d = d; p.include_nugget = include_nugget; p.no_clip = no_clip;
-    p.var = var; p.var_stride = var_stride; p.normacc = normacc;
+    p.var = var; p.var_stride = var_stride; p.normacc = normacc; p.sync = sync;
     for (int k = 0; k < count; k++) {
         p.outs[k] = outs[k];
-        // |V| <= sqrt(k(x*, x*)) = sqrt(sigma2); one more binade of head-room for rounding
-        const double bound = sqrt(h_hyper[(size_t)outs[k] * (d + 2) + d] + h_hyper[(size_t)outs[k] * (d + 2) + d + 1]);
-        int e = 0;
-        frexp(bound > 0.0 ? bound : 1.0, &e);
-        p.eV[k] = e + 1;
+        p.eS[k] = exps[k];
     }
-    {
-        const char* e = getenv("MOGP_I8_WIDE");
-        p.wide = (e && e[0] == '0') ? 0 : 1;
-    }
-    const int ntiles = count * panels;
-    const unsigned grid = (unsigned)(ntiles < n_sms ? ntiles : n_sms);
-    for (int i = 0; i < p.T; i++) {
-        p.i = i;
-        if (S == 6) i8_row_kernel<6><<<grid, I8_THREADS, I8Cfg<6>::SMEM, st>>>(p);
-        else i8_row_kernel<7><<<grid, I8_THREADS, I8Cfg<7>::SMEM, st>>>(p);
-    }
+    if (cudaMemsetAsync(sync, 0, i8_sync_bytes(count, panels), st) != cudaSuccess) return 1;
+    const int64_t total = (int64_t)p.T * count * panels;
+    const unsigned grid = (unsigned)(total < n_sms ? total : n_sms);
+    if (S == 6) i8_trsm_kernel<6><<<grid, I8_THREADS, I8Cfg<6>::SMEM, st>>>(tmD, p);
+    else i8_trsm_kernel<7><<<grid, I8_THREADS, I8Cfg<7>::SMEM, st>>>(tmD, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

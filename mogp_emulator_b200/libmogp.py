@@ -321,7 +321,7 @@ class Handle(object):
         out = np.zeros(15)
         check(_lib.mogp_timings(self._h, dptr(out), 15, int(reset)))
         keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms",
-                "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_ktilde_ms", "i8_rows_ms", "i8_row_launches"]
+                "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_ktilde_ms", "i8_rows_ms", "i8_block_rows"]
         return dict(zip(keys, out.tolist()))
 
 

@@ -14,7 +14,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 KEYS = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms",
-        "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_ktilde_ms", "i8_rows_ms", "i8_row_launches"]
+        "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_ktilde_ms", "i8_rows_ms", "i8_block_rows"]
 
 
 @pytest.mark.parametrize("i8", [True, False])
@@ -25,7 +25,7 @@ def test_bench_line_contract(monkeypatch, capsys, i8):
     class Handle(FakeHandle):
         def timings(self, reset=False):
             d = {k: 1.0 for k in KEYS}
-            d["i8_row_launches"] = 2.0 if i8 else 0.0
+            d["i8_block_rows"] = 2.0 if i8 else 0.0
             return d
 
     monkeypatch.setattr(libmogp, "Handle", Handle)

@@ -638,14 +638,14 @@ def test_i8_trsm_matches_oracle_and_dmma(mogp, monkeypatch, planes, kernel, nugg
     gp = mogp.MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget)
     gp.fit(thetas)
     ref = gp.predict(Xs, deriv=False)
-    assert gp.timings()["i8_row_launches"] == 0
+    assert gp.timings()["i8_block_rows"] == 0
     gp.close()
     _with_planes(monkeypatch, planes)
     gp = mogp.MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget)
     gp.fit(thetas)
     gp.timings(reset=True)
     res = gp.predict(Xs, deriv=False)
-    assert gp.timings()["i8_row_launches"] == (n + 127) // 128
+    assert gp.timings()["i8_block_rows"] == (n + 127) // 128
     res_nn = gp.predict(Xs, deriv=False, include_nugget=False)
     gp.close()
     assert np.array_equal(res.mean, ref.mean)
@@ -672,10 +672,10 @@ def test_i8_trsm_gating_and_refit(mogp, monkeypatch):
     t1 = gp.timings(reset=True)
     v2 = gp.predict(Xs, deriv=False).unc
     t2 = gp.timings(reset=True)
-    assert t1["i8_row_launches"] == 3 and t2["i8_row_launches"] == 3
+    assert t1["i8_block_rows"] == 3 and t2["i8_block_rows"] == 3
     assert np.array_equal(v1, v2)                                  # deterministic, planes reused
     gp.predict(Xs[:100], deriv=False)                              # few right-hand sides: FP64 DMMA path
-    assert gp.timings(reset=True)["i8_row_launches"] == 0
+    assert gp.timings(reset=True)["i8_block_rows"] == 0
     thetas2 = thetas + 0.3
     gp.fit(thetas2)                                                # new factors: stale planes must not be used
     v3 = gp.predict(Xs, deriv=False).unc
@@ -687,7 +687,7 @@ def test_i8_trsm_gating_and_refit(mogp, monkeypatch):
         gp.fit(thetas)
         gp.timings(reset=True)
         gp.predict(Xs, deriv=False)
-        assert gp.timings()["i8_row_launches"] == 0
+        assert gp.timings()["i8_block_rows"] == 0
         gp.close()
 
 
@@ -701,7 +701,7 @@ def test_i8_trsm_with_mean_function(mogp, monkeypatch):
     gp.fit(thetas)
     gp.timings(reset=True)
     res = gp.predict(Xs, deriv=False)
-    assert gp.timings()["i8_row_launches"] == 3
+    assert gp.timings()["i8_block_rows"] == 3
     gp.close()
     for o in (3, 39):
         rm, rv = orc.OracleGP(X, Y[o], mean="x[0]", nugget=1e-5, priors="weak").fit(thetas[o]).predict(Xs)

@@ -165,7 +165,7 @@ def test_gpu_history_matching_many_query_points():
     hm = mogp.HistoryMatching(gp=gp, obs=obs, coords=Xq, threshold=3.0)
     gp.timings(reset=True)
     I = hm.get_implausibility(rank=0)
-    assert gp.timings()["i8_row_launches"] == 4
+    assert gp.timings()["i8_block_rows"] == 4
     post = gp.predict(Xq[:300], deriv=False)
     refs = [orc.OracleGP(X, Y[k], nugget=1e-5, priors="weak").fit(thetas[k]).predict(Xq[:300]) for k in range(24)]
     want = orc.implausibility(np.array([r[0] for r in refs]), np.array([r[1] for r in refs]), obs[0], obs[1], rank=0)
