@@ -142,7 +142,8 @@ int mogp_kstar_dot(mogp_handle* h, const double* Xs, int64_t m, const double* ve
 /* accumulated device time per phase in ms since the last call with reset != 0:
  * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),
  *              predict host wall up to the last kernel's completion, predict result copy-out host wall;
- * out[11..14] = int8 path of the predict TRSM (inside predict_trsm): L~ planes, K~* pass, block-row launches (ms), #row launches */
+ * out[11..14] = int8 path of the predict TRSM (inside predict_trsm): slicing L into planes (ms), unused (0), the
+ *               persistent integer TRSM kernel (ms), block rows solved by it */
 int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset);
 
 /* NCCL plumbing (no reference equivalent: the reference is single-device, multioutputgp_gpu.hpp:183). */
@@ -151,6 +152,12 @@ int mogp_comm_create(const char* uid128, int32_t rank, int32_t world, int32_t de
 int mogp_comm_destroy(mogp_comm* c);
 /* max-reduce of one double over ranks + barrier (bench timing). */
 int mogp_comm_allreduce_max(mogp_comm* c, double* value);
+/* all-gather of `count` doubles per rank between HOST buffers (recv: world * count doubles, rank-major): one ncclAllGather
+ * bracketed by the two copies.  Carries what mogp_predict_allgather does not: fit status after a sharded fit, and the
+ * posteriors of sharded emulators with a mean function or predictive derivatives (finished on the host per rank).  A rank
+ * that holds no outputs joins mogp_predict_allgather's collective through this entry point with a padding block of the
+ * same length. */
+int mogp_comm_allgather(mogp_comm* c, const double* send, int64_t count, double* recv);
 
 /* measured FP64 tensor-pipe (DMMA) issue peak of `device` in TFLOP/s: the roofline denominator bench.py uses
  * (MEASURED_PEAKS.json has no FP64 entry). */

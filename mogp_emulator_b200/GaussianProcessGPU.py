@@ -252,18 +252,29 @@ class GaussianProcessGPU(object):
         if status[0] != libmogp.OK:
             self._theta.unset_data()
             self._logpost_data = None
-            raise RuntimeError("Unable to fit the Gaussian process: matrix not positive definite" +
-                               (", even with jitter." if self.nugget_type == "adaptive" else ""))
-        self._theta.set_data(theta)
-        self._theta.nugget = float(nug[0])
-        if self.n_mean == 0:
-            self._logpost_data = 0.5 * (float(quad[0]) + float(logdet[0]) + self.n * np.log(2.0 * np.pi))
-        else:
+            raise libmogp.NotPositiveDefiniteError("Unable to fit the Gaussian process: matrix not positive definite" +
+                                                   (", even with jitter." if self.nugget_type == "adaptive" else ""))
+        mf = None
+        if self.n_mean > 0:
             # analytic mean (GaussianProcess.py:657-685): K^-1 H on the device, the n_mean x n_mean algebra here, then the
             # device's alpha becomes K^-1 (y - H beta) and it learns the rank-n_mean correction of the gradient
             self._Kinv_t_host = self._handle.get(0, libmogp.GET_ALPHA)
             W = np.column_stack([self._handle.solve_list([0], self._dm[:, q])[0] for q in range(self.n_mean)])
-            mf = MeanFit(self._dm, self._targets, self._Kinv_t_host, W, self.n)
+            try:
+                mf = MeanFit(self._dm, self._targets, self._Kinv_t_host, W, self.n)
+            except np.linalg.LinAlgError:
+                # H^T K^-1 H is numerically not positive definite (the reference's calc_Ainv raises LinAlgError, which its MAP
+                # loop skips, fitting.py:244-249): the emulator stays "not fit" on the host and on the device
+                self._theta.unset_data()
+                self._logpost_data = None
+                self._handle.reset(0)
+                raise libmogp.NotPositiveDefiniteError("Unable to fit the Gaussian process: mean-function matrix H^T K^-1 H "
+                                                       "not positive definite")
+        self._theta.set_data(theta)
+        self._theta.nugget = float(nug[0])
+        if mf is None:
+            self._logpost_data = 0.5 * (float(quad[0]) + float(logdet[0]) + self.n * np.log(2.0 * np.pi))
+        else:
             self._handle.set_alpha_list([0], mf.alpha_mean)
             self._handle.set_mean_vectors_list([0], mf.U.T[np.newaxis])
             self._meanfit = mf

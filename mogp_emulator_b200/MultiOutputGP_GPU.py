@@ -1,11 +1,11 @@
 """``MultiOutputGP_GPU`` -- drop-in for the reference class of the same name
 (mogp_emulator/MultiOutputGP_GPU.py:27-382): E independent GPs over shared inputs.
 
-One libmogp_b200 handle holds this rank's outputs; ``fit`` runs one GP per CUDA stream, ``predict`` is one
-batched launch per phase.  With a communicator (``comm=``) the outputs are block-partitioned over the ranks
-(one process per GPU) and ``predict`` ends with a single NCCL all-gather of the packed means/variances, so
-every rank returns the full ``(n_emulators, n_predict)`` arrays.  Values follow the CPU ``MultiOutputGP``
-(MultiOutputGP.py:182-319, 331-459).
+One libmogp_b200 handle holds this rank's outputs; every phase of ``fit`` and ``predict`` is one batched launch
+over them.  With a communicator (``comm=``) the outputs are block-partitioned over the ranks (one process per
+GPU, ``sharding.py``) and ``predict`` ends with a single NCCL all-gather of the packed posteriors, so every rank
+returns the full ``(n_emulators, n_predict)`` arrays (and ``(n_emulators, n_predict, D)`` derivatives).  Values
+follow the CPU ``MultiOutputGP`` (MultiOutputGP.py:182-319, 331-459).
 """
 import numpy as np
 
@@ -55,9 +55,6 @@ class MultiOutputGP_GPU(object):
         self._inputs = np.ascontiguousarray(inputs)
         self._targets = np.ascontiguousarray(targets)
         self._dm = design_matrix(self._mean_spec, self._inputs)
-        if comm is not None and self._dm.shape[1] > 0:
-            raise ValueError("a mean function is not supported together with a communicator (sharded predict gathers "
-                             "zero-mean posteriors)")
         self._nugget_type = nugtype
         self._nugget_size = nugsize
         self.kernel_type, self.kernel = interpret_kernel(kernel)
@@ -72,7 +69,7 @@ class MultiOutputGP_GPU(object):
         self._thetas = [GPParams(self.D, self.nugget_type, nugsize if nugtype == libmogp.nugget_type.fixed else None)
                         for _ in range(E)]
         self._logpost_data = [None] * E
-        self._fit = [False] * E
+        self._fit = [False] * E                # outputs of other ranks: their status as of the last exchange (fit / predict)
         self._meanfit = [None] * E
         if isinstance(priors, (GPPriors, dict)) or priors is None:
             priorslist = E * [priors]
@@ -175,18 +172,27 @@ class MultiOutputGP_GPU(object):
         local = [i - self._lo for i in indices]
         M = self._dm.shape[1]
         cols = [self._handle.solve_list(local, np.tile(self._dm[:, q], (len(local), 1))) for q in range(M)]
-        alphas, Us = [], []
+        good, alphas, Us = [], [], []
         for k, i in enumerate(indices):
             t = self._handle.get(local[k], libmogp.GET_ALPHA)
             W = np.column_stack([cols[q][k] for q in range(M)])
-            mf = MeanFit(self._dm, self._targets[i], t, W, self.n)
+            try:
+                mf = MeanFit(self._dm, self._targets[i], t, W, self.n)
+            except np.linalg.LinAlgError:
+                # H^T K^-1 H numerically not positive definite: this emulator stays "not fit" (host and device), the
+                # others of the batch are unaffected (reference: calc_Ainv raises LinAlgError, fitting.py:244-249 skips)
+                self._record(i, None, 0.0, 0.0, 0.0, libmogp.ERR_NOT_PD)
+                self._handle.reset(local[k])
+                continue
             self._meanfit[i] = mf
             self._thetas[i].mean = mf.beta.copy()
             self._logpost_data[i] = mf.data_logpost(float(quad[k]), float(logdet[k]), self.n)
+            good.append(local[k])
             alphas.append(mf.alpha_mean)
             Us.append(mf.U.T)
-        self._handle.set_alpha_list(local, np.array(alphas))
-        self._handle.set_mean_vectors_list(local, np.array(Us))
+        if good:
+            self._handle.set_alpha_list(good, np.array(alphas))
+            self._handle.set_mean_vectors_list(good, np.array(Us))
 
     def _record(self, index, theta, quad, logdet, nug, status):
         self._meanfit[index] = None
@@ -216,6 +222,22 @@ class MultiOutputGP_GPU(object):
                 self._record(i, thetas[i], quad[k], logdet[k], nug[k], status[k])
             ok = [k for k in range(self._hi - self._lo) if status[k] == libmogp.OK]
             self._apply_mean([self._lo + k for k in ok], quad[ok], logdet[ok])
+        self.sync_fit_status()
+
+    def sync_fit_status(self):
+        """With a communicator: exchange which outputs are fit (one all-gather of ``e_pad`` words per rank), so that
+        ``get_indices_fit`` / ``get_indices_not_fit`` and ``fit_GP_MAP``'s failure check see the outputs of every rank.
+        Collective: every rank must call it (``fit`` does)."""
+        if self._comm is None:
+            return
+        block = np.zeros(self._e_pad)
+        block[:self._hi - self._lo] = [1.0 if f else 0.0 for f in self._fit[self._lo:self._hi]]
+        got = self._comm.allgather(block)
+        for r in range(self._comm.world):
+            lo, hi, _ = shard_bounds(self.n_emulators, r, self._comm.world)
+            if r != self._comm.rank:
+                for k in range(hi - lo):
+                    self._fit[lo + k] = bool(got[r, k] > 0.5)
 
     def fit_emulator(self, index, theta):
         theta = np.array(theta, dtype=np.float64).reshape(-1)
@@ -237,7 +259,7 @@ class MultiOutputGP_GPU(object):
             if not t.data_has_been_set() or not np.allclose(theta, t.get_data(), rtol=1.0e-10, atol=1.0e-15):
                 self.fit_emulator(index, theta)
                 if not self._fit[index]:
-                    raise RuntimeError("Unable to fit the Gaussian process: matrix not positive definite")
+                    raise libmogp.NotPositiveDefiniteError("Unable to fit the Gaussian process: matrix not positive definite")
         if not self._fit[index]:
             return None
         return self._logpost_data[index] - self.priors[index].logp(self._thetas[index])
@@ -265,6 +287,7 @@ class MultiOutputGP_GPU(object):
                 ok.append(k)
         out = {i: None for i in indices}
         self._apply_mean([indices[k] for k in ok], quad[ok], logdet[ok])
+        ok = [k for k in ok if self._fit[indices[k]]]          # the mean step may have failed for some of them
         if ok:
             grads = self._handle.logpost_grad_list([local[k] for k in ok], self.n_params[indices[ok[0]]])
             for row, k in enumerate(ok):
@@ -274,25 +297,20 @@ class MultiOutputGP_GPU(object):
         return out
 
     def get_indices_fit(self):
-        return [i for i in range(self.n_emulators) if self._global_fit(i)]
+        return [i for i in range(self.n_emulators) if self._fit[i]]
 
     def get_indices_not_fit(self):
-        return [i for i in range(self.n_emulators) if not self._global_fit(i)]
-
-    def _global_fit(self, i):
-        # without a communicator every output is local; with one, fit status of remote outputs is learnt at
-        # the gather in predict (until then they are reported from the local mirror, which fit() keeps
-        # consistent because every rank calls fit with the full thetas array)
-        return self._fit[i] if self._lo <= i < self._hi else self._remote_fit.get(i, True)
-
-    _remote_fit = {}
+        """Outputs without hyperparameters.  Sharded emulators report the outputs of other ranks as of the last status
+        exchange (every ``fit`` and ``predict`` ends with one; ``sync_fit_status`` after ``fit_emulator`` calls)."""
+        return [i for i in range(self.n_emulators) if not self._fit[i]]
 
     # -- prediction (MultiOutputGP_GPU.py:185-297; CPU semantics MultiOutputGP.py:182-319) ---------------
     def predict(self, testing, unc=True, deriv=True, include_nugget=True, allow_not_fit=False, processes=None,
                 full_cov=False):
         """Means / variances ``(n_emulators, m)`` and, with ``deriv=True`` (the reference's default,
-        MultiOutputGP_GPU.py:185), mean derivatives ``(n_emulators, m, D)``.  Sharded (``comm=``) emulators gather
-        means and variances only: pass ``deriv=False`` there."""
+        MultiOutputGP_GPU.py:185), mean derivatives ``(n_emulators, m, D)``; NaN rows for emulators that are not fit
+        under ``allow_not_fit`` (MultiOutputGP.py:476-546).  Sharded (``comm=``): every rank predicts its own outputs
+        and one all-gather leaves the full arrays on every rank; ``full_cov`` is not gathered."""
         testing = np.array(testing, dtype=np.float64)
         if self.D == 1 and testing.ndim == 1:
             testing = np.reshape(testing, (-1, 1))
@@ -304,64 +322,110 @@ class MultiOutputGP_GPU(object):
         if self._comm is None:
             if not allow_not_fit and len(self.get_indices_not_fit()) > 0:
                 raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
-            dmean = self._handle.predict_deriv(testing)[0] if deriv else None
-            if self._dm.shape[1] > 0:
-                return self._predict_with_mean(testing, unc, include_nugget, full_cov, dmean)
-            if unc and full_cov:
-                # (E, m, m) covariances, one output at a time (MultiOutputGP.py:183, 303); NaN for unfit emulators
-                mean = np.full((E, m), np.nan)
-                cov = np.full((E, m, m), np.nan)
-                for i in self.get_indices_fit():
-                    mean[i], cov[i] = self._handle.predict_cov(i, testing, include_nugget=include_nugget)
-                return PredictResult(mean=mean, unc=cov, deriv=dmean)
-            mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
-            return PredictResult(mean=mean, unc=var if unc else None, deriv=dmean)
-        if deriv:
-            raise GPUUnavailableError("predictive derivatives are not gathered across ranks: pass deriv=False")
-        # sharded: local predict + the one all-gather of the path
-        if self._handle is None:
-            raise RuntimeError("this rank holds no outputs: use at most n_emulators ranks")
-        mean_all, var_all, status_all = self._handle.predict_allgather(self._comm, testing, include_nugget, self._e_pad)
-        # rank r's block starts at row r*e_pad == its first global output index (block partition, sharding.py), so the
-        # gathered rows are already in output order; only the last rank's padding rows trail behind: slice, no copy
-        status = status_all[:E]
-        self._remote_fit = {i: bool(status[i] == libmogp.OK) for i in range(E)}
+            mean, var, dmean = self._local_predict(testing, unc, deriv, include_nugget, full_cov)
+            return PredictResult(mean=mean, unc=var, deriv=dmean)
+        if unc and full_cov:
+            raise GPUUnavailableError("full predictive covariances are not gathered across ranks: predict them on the "
+                                      "rank that holds the output (local_range)")
+        world, rank, e_pad, e_loc = self._comm.world, self._comm.rank, self._e_pad, self._hi - self._lo
+        rows = np.array([r * e_pad + k for r in range(world) for k in range(shard_bounds(E, r, world)[1] - shard_bounds(E, r, world)[0])])
+        in_order = bool(np.array_equal(rows, np.arange(E)))
+        dmean_all = None
+        if not deriv and self._dm.shape[1] == 0:
+            # the path of the BASELINE metric: device-resident results, ONE ncclAllGather of the packed [e_pad][2][m] blocks
+            if self._handle is not None:
+                mean_all, var_all, status_all = self._handle.predict_allgather(self._comm, testing, include_nugget, e_pad)
+            else:
+                # this rank holds no outputs (more ranks than outputs): an all-padding block of the same length
+                block = np.full(e_pad * 2 * m + e_pad, np.nan)
+                block[e_pad * 2 * m:] = float(libmogp.ERR_ARG)
+                got = self._comm.allgather(block)
+                mean_all = got[:, :e_pad * 2 * m].reshape(world * e_pad, 2, m)[:, 0]
+                var_all = got[:, :e_pad * 2 * m].reshape(world * e_pad, 2, m)[:, 1]
+                status_all = got[:, e_pad * 2 * m:].reshape(-1).astype(np.int32)
+        else:
+            # mean function and / or derivatives: each rank finishes its own posteriors on the host, then one all-gather of
+            # [e_pad][(2 + D) m] + status
+            width = (2 + (self.D if deriv else 0)) * m
+            block = np.full(e_pad * width + e_pad, np.nan)
+            block[e_pad * width:] = float(libmogp.ERR_ARG)
+            if e_loc:
+                mean, var, dmean = self._local_predict(testing, True, deriv, include_nugget, False)
+                body = block[:e_pad * width].reshape(e_pad, width)
+                body[:e_loc, :m] = mean
+                body[:e_loc, m:2 * m] = var
+                if deriv:
+                    body[:e_loc, 2 * m:] = dmean.reshape(e_loc, m * self.D)
+                block[e_pad * width:e_pad * width + e_loc] = [float(libmogp.OK if f else libmogp.ERR_NOT_FIT)
+                                                              for f in self._fit[self._lo:self._hi]]
+            got = self._comm.allgather(block)
+            body = got[:, :e_pad * width].reshape(world * e_pad, width)
+            mean_all, var_all = body[:, :m], body[:, m:2 * m]
+            if deriv:
+                dmean_all = body[:, 2 * m:].reshape(world * e_pad, m, self.D)
+            status_all = got[:, e_pad * width:].reshape(-1).astype(np.int32)
+        # rank r's block starts at row r*e_pad; when the partition is even that is its first global output index and the
+        # gathered rows are already in output order (slice, no copy); otherwise pick the rows
+        pick = (lambda a: a[:E]) if in_order else (lambda a: a[rows])
+        status = pick(status_all)
+        for i in range(E):
+            if not self._lo <= i < self._hi:
+                self._fit[i] = bool(status[i] == libmogp.OK)
         if not allow_not_fit and np.any(status != libmogp.OK):
             raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
-        return PredictResult(mean=mean_all[:E], unc=var_all[:E] if unc else None, deriv=None)
+        return PredictResult(mean=pick(mean_all), unc=pick(var_all) if unc else None,
+                             deriv=pick(dmean_all) if deriv else None)
 
-    def _predict_with_mean(self, testing, unc, include_nugget, full_cov, dmean):
+    def _local_predict(self, testing, unc, deriv, include_nugget, full_cov):
+        """Posterior of the outputs this rank holds (local index k <-> output lo + k): mean (e, m), var (e, m) or
+        covariances (e, m, m) or None, derivatives (e, m, D) or None; NaN rows for outputs that are not fit."""
+        e, m = self._hi - self._lo, testing.shape[0]
+        dmean = self._handle.predict_deriv(testing)[0] if deriv else None
+        if self._dm.shape[1] > 0:
+            return self._local_predict_with_mean(testing, unc, include_nugget, full_cov, dmean)
+        if unc and full_cov:
+            # (e, m, m) covariances, one output at a time (MultiOutputGP.py:183, 303); NaN for unfit emulators
+            mean = np.full((e, m), np.nan)
+            cov = np.full((e, m, m), np.nan)
+            for k in range(e):
+                if self._fit[self._lo + k]:
+                    mean[k], cov[k] = self._handle.predict_cov(k, testing, include_nugget=include_nugget)
+            return mean, cov, dmean
+        mean, var, _ = self._handle.predict(testing, want_var=unc, include_nugget=include_nugget)
+        return mean, (var if unc else None), dmean
+
+    def _local_predict_with_mean(self, testing, unc, include_nugget, full_cov, dmean):
         """Posterior with the analytic mean function (GaussianProcess.py:887-920): mean shifted by H* beta, variance plus
         R^T A^-1 R with R = H*^T - H^T K^-1 K* (one fused kernel-matrix pass per design-matrix column), clipped last."""
-        E, m = self.n_emulators, testing.shape[0]
+        e, m, lo = self._hi - self._lo, testing.shape[0], self._lo
         Hs = design_matrix(self._mean_spec, testing)
         M = Hs.shape[1]
-        fit = self.get_indices_fit()
+        fit = [k for k in range(e) if self._fit[lo + k]]
         if dmean is not None and self._mean_spec.terms:
             dHs = design_matrix_inputderiv(self._mean_spec, testing)          # (m, D, M)
-            for i in fit:
-                dmean[i] += np.dot(dHs, self._meanfit[i].beta)
+            for k in fit:
+                dmean[k] += np.dot(dHs, self._meanfit[lo + k].beta)
         extra = {}
         if unc and fit:
-            vecs = np.zeros((E, M, self.n))
-            for i in fit:
-                vecs[i] = self._meanfit[i].W.T
+            vecs = np.zeros((e, M, self.n))
+            for k in fit:
+                vecs[k] = self._meanfit[lo + k].W.T
             dots = self._handle.kstar_dot(testing, vecs)
-            extra = {i: self._meanfit[i].variance_term(Hs, dots[i], full_cov=full_cov) for i in fit}
+            extra = {k: self._meanfit[lo + k].variance_term(Hs, dots[k], full_cov=full_cov) for k in fit}
         if unc and full_cov:
-            mean = np.full((E, m), np.nan)
-            cov = np.full((E, m, m), np.nan)
-            for i in fit:
-                mean[i], cov[i] = self._handle.predict_cov(i, testing, include_nugget=include_nugget)
-                mean[i] += np.dot(Hs, self._meanfit[i].beta)
-                cov[i] += extra[i]
-            return PredictResult(mean=mean, unc=cov, deriv=dmean)
+            mean = np.full((e, m), np.nan)
+            cov = np.full((e, m, m), np.nan)
+            for k in fit:
+                mean[k], cov[k] = self._handle.predict_cov(k, testing, include_nugget=include_nugget)
+                mean[k] += np.dot(Hs, self._meanfit[lo + k].beta)
+                cov[k] += extra[k]
+            return mean, cov, dmean
         mean, var, _ = self._handle.predict(testing, want_var=2 if unc else 0, include_nugget=include_nugget)
-        for i in fit:
-            mean[i] += np.dot(Hs, self._meanfit[i].beta)
+        for k in fit:
+            mean[k] += np.dot(Hs, self._meanfit[lo + k].beta)
             if unc:
-                var[i] = np.maximum(var[i] + extra[i], 0.0)
-        return PredictResult(mean=mean, unc=var if unc else None, deriv=dmean)
+                var[k] = np.maximum(var[k] + extra[k], 0.0)
+        return mean, (var if unc else None), dmean
 
     def __call__(self, testing, processes=None):
         return self.predict(testing, unc=False, deriv=False, processes=processes)[0]

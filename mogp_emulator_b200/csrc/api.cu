@@ -676,7 +676,7 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     API_CUDA(cudaEventRecord(h->ev_e, h->main));
                     API_CUDA(cudaEventRecord(h->ev_f, h->main));
                     // the integer forward substitution with its FP64 epilogue (K* in W is only read)
-                    if (i8_trsm(S8, outs, exps.data(), cnt, plan.panels, h->Lq, (int64_t)lq_stride, (int8_t*)h->Vq, h->maps.d128, h->W,
+                    if (i8_trsm(S8, outs, exps.data(), cnt, plan.panels, h->Lq, (int64_t)lq_stride, (int8_t*)h->Vq, h->maps.d128, tmW, h->W,
                                 w_stride, h->hyper, d, include_nugget, want_var == 2 ? 1 : 0, np, mc, h->res + m + m0, 2 * m,
                                 h->normacc, (int*)h->sync, h->n_sms, h->main)) {
                         set_error("i8 predict launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1235,6 +1235,28 @@ int mogp_comm_allreduce_max(mogp_comm* c, double* value) {
         return MOGP_ERR_NCCL;
     }
     API_CUDA(cudaMemcpyAsync(value, c->dscalar + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    API_CUDA(cudaStreamSynchronize(c->stream));
+    return MOGP_OK;
+}
+
+int mogp_comm_allgather(mogp_comm* c, const double* send, int64_t count, double* recv) {
+    if (!c || !send || !recv || count < 1) {
+        set_error("mogp_comm_allgather: bad arguments");
+        return MOGP_ERR_ARG;
+    }
+    const NcclApi* api = nccl_api();
+    API_CUDA(cudaSetDevice(c->device));
+    int rc;
+    const size_t n = (size_t)count;
+    if ((rc = grow(&c->sendbuf, &c->send_cap, sizeof(double) * n, c->device))) return rc;
+    if ((rc = grow(&c->recvbuf, &c->recv_cap, sizeof(double) * n * c->world, c->device))) return rc;
+    API_CUDA(cudaMemcpyAsync(c->sendbuf, send, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = api->AllGather(c->sendbuf, c->recvbuf, n, ncclDouble, c->comm, c->stream);
+    if (r != ncclSuccess) {
+        set_error("ncclAllGather failed: %s", api->GetErrorString(r));
+        return MOGP_ERR_NCCL;
+    }
+    API_CUDA(cudaMemcpyAsync(recv, c->recvbuf, sizeof(double) * n * c->world, cudaMemcpyDeviceToHost, c->stream));
     API_CUDA(cudaStreamSynchronize(c->stream));
     return MOGP_OK;
 }

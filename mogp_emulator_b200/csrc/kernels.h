@@ -74,12 +74,12 @@ int i8_scale_exponent(double sigma2, double nugget);
 // planes of the strictly lower 128 x 128 blocks of L of the listed outputs (exps[k] = i8_scale_exponent of outs[k])
 int i8_slice_L(int S, const double* A_slab, int64_t n_pad, const int* outs, const int* exps, int count, int8_t* Lq,
                int64_t lq_stride, cudaStream_t st);
-// forward substitution + variances, one persistent launch; W holds K* (test-major) and is only read; tmD: K-blocked map
-// over the Dinv slab (box 128 rows); sync: i8_sync_bytes(count, panels) bytes (zeroed by the call)
+// forward substitution + variances, one persistent launch; W holds K* (test-major) and is only read (tmW: its K-blocked map,
+// box 64 rows); tmD: K-blocked map over the Dinv slab (box 128 rows); sync: i8_sync_bytes(count, panels) bytes (zeroed by the call)
 int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, const int8_t* Lq, int64_t lq_stride, int8_t* Vq,
-            const CUtensorMap& tmD, const double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
-            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync, int n_sms,
-            cudaStream_t st);
+            const CUtensorMap& tmD, const CUtensorMap& tmW, const double* W, int64_t w_stride, const double* hyper, int d,
+            int include_nugget, int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync,
+            int n_sms, cudaStream_t st);
 
 // ---- grad.cu ----
 int grad_init();

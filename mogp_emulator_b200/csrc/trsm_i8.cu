@@ -18,10 +18,12 @@
 //     weight -- 10 MMAs of N <= 256 per K = 32 step instead of 28 of N = 64 (the N = 64 form is bound by its shared-memory
 //     operand reads: 6 KB per 32-cycle MMA).  Integer accumulation is exact: |digit| <= 64, a column of n = 16384 terms
 //     times 7 pairs stays below 2^30;
-//   * the epilogue is FP64: T_i = K*_i - 2^(eL+eV) sum_w 2^-7w acc_w (TMEM -> registers -> shared memory, K-blocked), then
-//     V_i = inv(L_ii) T_i on the FP64 tensor pipe (DMMA, inv(L_ii) streamed by TMA in 16 KB chunks, the zero upper triangle
-//     skipped), column norms, and the S digits of V_i assembled as a plane image in shared memory that one cp.async.bulk
-//     stores.  The MMA warp works on the next tile meanwhile.
+//   * the epilogue is FP64: K*_i is TMA-loaded K-blocked into shared memory ahead of time, T_i = K*_i - 2^(eL+eV) sum_w 2^-7w acc_w
+//     is formed in place (TMEM -> registers -> shared memory), then V_i = inv(L_ii) T_i on the FP64 tensor pipe (DMMA; every
+//     consumer warp owns 8 columns and all 128 rows, inv(L_ii) streamed by TMA in 16 KB chunks, the zero upper triangle
+//     skipped), column norms inside the warp, and the S digits of V_i assembled as a plane image in shared memory (4 x 4 byte
+//     transposes by shuffle, conflict-free word stores) that one cp.async.bulk stores.  The MMA warp works on the next tile
+//     meanwhile.
 //
 // ONE persistent launch for the whole solve: tiles (block row i, panel of 64 test points, output) are drawn from a global
 // ticket counter in block-row-major order; the only dependency of a tile is the same panel's previous block row, which
@@ -30,7 +32,7 @@
 //
 // Per CTA (352 threads): warps 0-7 consumers (TMEM drain, FP64 epilogue), warp 8 MMA issuer (one elected thread),
 // warp 9 ticket + operand loader (cp.async.bulk of contiguous plane blocks into a 3-stage mbarrier ring), warp 10 loader
-// of the inv(L_ii) chunks.  S = 7 is the library default, S = 6 opt-in (MOGP_TRSM_I8=6); DESIGN.md section 3 has the
+// of the K*_i tile and the inv(L_ii) chunks.  S = 7 is the library default, S = 6 opt-in (MOGP_TRSM_I8=6); DESIGN.md section 3 has the
 // error table, oracle/i8_emulation.py the exact CPU emulation of this arithmetic, tools/probe_i8*.cu the instruction probes.
 #include <cstdlib>
 
@@ -60,8 +62,8 @@ struct I8Cfg {
     static constexpr int VBLOCK = 4 * BSTAGE;               // one 128-row block of V for one panel
     static constexpr int OFF_T = NS * STAGE;                // T_i (FP64, K-blocked, 64 KB); later the plane image of V_i
     static constexpr int OFF_D = OFF_T + NB * I8_BN * 8;    // two chunks of inv(L_ii)
-    static constexpr int OFF_NRED = OFF_D + 2 * I8_DCHUNK;  // [8 warps][64] column-norm partials
-    static constexpr int OFF_BAR = OFF_NRED + I8_NCW * I8_BN * 8;
+    static constexpr int OFF_NRED = OFF_D + 2 * I8_DCHUNK;  // [64] squared column norms of V_i
+    static constexpr int OFF_BAR = OFF_NRED + I8_BN * 8;
     static constexpr int SMEM = OFF_BAR + 256 + 128;
     static_assert(S * I8_BN <= 512, "one s32 accumulator group per weight must fit TMEM");
     static_assert(SMEM <= 232448, "shared memory per CTA");
@@ -211,7 +213,8 @@ struct I8TrsmParams {
 constexpr int I8_SYNC_HDR = 32;
 
 template <int S>
-__global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const I8TrsmParams p) {
+__global__ void __launch_bounds__(I8_THREADS, 1)
+i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW, const I8TrsmParams p) {
     using Cfg = I8Cfg<S>;
     constexpr int NS = Cfg::NS, STAGE = Cfg::STAGE, ASTAGE = Cfg::ASTAGE, BSTAGE = Cfg::BSTAGE;
     constexpr int LBLOCK = Cfg::LBLOCK, VBLOCK = Cfg::VBLOCK;
@@ -227,7 +230,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
     uint64_t* acc_empty = acc_full + 1;
     uint64_t* d_full = acc_empty + 1;                                                // [2]
     uint64_t* d_empty = d_full + 2;                                                  // [2]
-    uint64_t* tq_full = d_empty + 2;                                                 // [QN]
+    uint64_t* ts_full = d_empty + 2;                                                 // K*_i has landed in the T buffer
+    uint64_t* ts_free = ts_full + 1;                                                 // the plane image of the previous tile has been read
+    uint64_t* tq_full = ts_free + 1;                                                 // [QN]
     uint64_t* tq_empty = tq_full + I8_QN;                                            // [QN]
     int* tq = reinterpret_cast<int*>(tq_empty + I8_QN);                              // [QN]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tq + I8_QN);
@@ -253,6 +258,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
             mbar_init(&d_full[s], 1);
             mbar_init(&d_empty[s], I8_NCW);
         }
+        mbar_init(ts_full, 1);
+        mbar_init(ts_free, 1);
         for (int s = 0; s < I8_QN; s++) {
             mbar_init(&tq_full[s], 1);
             mbar_init(&tq_empty[s], I8_NCW + 2);     // consumer warps + MMA issuer + inv(L_ii) loader
@@ -295,9 +302,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
             }
         }
     } else if (warp == I8_NCW + 2) {
-        // ================================ inv(L_ii) loader ================================
+        // ================================ K*_i and inv(L_ii) loader ================================
         if (lane == 0) {
             prefetch_tmap(&tmD);
+            prefetch_tmap(&tmW);
             int dc = 0;
             for (int nq = 0;; nq++) {
                 const int slot = nq % I8_QN;
@@ -306,9 +314,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
                 mbar_arrive(&tq_empty[slot]);
                 if (t < 0) break;
                 const int i = t / per_row, tile = t - i * per_row;
-                const int o = tile / p.panels;
+                const int o = tile / p.panels, pnl = tile - o * p.panels;
                 const int drow = (int)(p.outs[o] * p.n_pad) + i * NB;
+                const int wrow = (int)(o * p.w_stride) + pnl * I8_BN;
                 for (int ch = 0; ch < NB / KC; ch++, dc++) {
+                    if (ch == 2) {
+                        // K*_i -> T buffer ([16 slabs][64 test points][8], what the 3-D box of the K-blocked map writes) once the
+                        // previous tile's plane image has been read out of it; the first two chunks of inv(L_ii) go first
+                        if (nq > 0) i8_wait(ts_free, (uint32_t)((nq - 1) & 1));
+                        mbar_arrive_expect_tx(ts_full, NB * I8_BN * 8);
+                        for (int c2 = 0; c2 < NB / KC; c2++)
+                            tma_load_3d(Ts + c2 * (KC / 8) * I8_BN * 8, &tmW, 0, wrow, i * (NB / 8) + c2 * (KC / 8), ts_full);
+                    }
                     const int ds = dc & 1;
                     if (dc >= 2) i8_wait(&d_empty[ds], (uint32_t)(((dc >> 1) - 1) & 1));
                     mbar_arrive_expect_tx(&d_full[ds], I8_DCHUNK);
@@ -371,64 +388,65 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
             const bool last = (i + 1 == T);
             const int es = p.eS[o];
 
-            // ---- T_i = K*_i - 2^(2 eS) sum_w 2^-7w acc_w  -> shared memory, K-blocked (the B operand of the diagonal product) ----
-            {
+            // ---- T_i = K*_i - 2^(2 eS) sum_w 2^-7w acc_w, in place in the K-blocked buffer K*_i was loaded into ----
+            if (i > 0) {
                 double acc[32];
 #pragma unroll
                 for (int c = 0; c < 32; c++) acc[c] = 0.0;
-                if (i > 0) {
-                    i8_wait(acc_full, (uint32_t)(k & 1));
-                    k++;
-                    i8_fence_after();
+                i8_wait(acc_full, (uint32_t)(k & 1));
+                k++;
+                i8_fence_after();
 #pragma unroll
-                    for (int w = 0; w < S; w++) {
-                        uint32_t v[32];
-                        i8_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(w * I8_BN + h * 32), v);
-                        const double wgt = __longlong_as_double((long long)(1023 - I8_BITS * (w + 2)) << 52);   // 2^-7(w+2)
+                for (int w = 0; w < S; w++) {
+                    uint32_t v[32];
+                    i8_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(w * I8_BN + h * 32), v);
+                    const double wgt = __longlong_as_double((long long)(1023 - I8_BITS * (w + 2)) << 52);   // 2^-7(w+2)
 #pragma unroll
-                        for (int c = 0; c < 32; c++) acc[c] = fma((double)(int32_t)v[c], wgt, acc[c]);
-                    }
-                    i8_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
+                    for (int c = 0; c < 32; c++) acc[c] = fma((double)(int32_t)v[c], wgt, acc[c]);
                 }
-                const double scale = ldexp(1.0, 2 * es);
-                const double* wsrc = p.W + ((size_t)o * p.w_stride + (size_t)pnl * I8_BN + h * 32) * p.n_pad + (size_t)i * NB + r;
-                // element (r, col) at Ts[r / 8][col ^ swz][r % 8]; swz flips the column parity for every second pair of slabs so
-                // that the four slabs a warp writes at once fall into distinct banks
-                const int ks = r >> 3, sw = (ks >> 1) & 1;
-                double* trow = Ts + (size_t)ks * I8_BN * 8 + (r & 7);
+                i8_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                i8_wait(ts_full, (uint32_t)(nq & 1));
+                const double nscale = -ldexp(1.0, 2 * es);
+                // element (r, col) at Ts[r / 8][col][r % 8]: the four 8-lane groups of a warp write four slabs 4 KB apart, so the
+                // odd groups take the two columns of a pair in the opposite order (two wavefronts per 256-byte access, the minimum)
+                const int odd = (lane >> 3) & 1;
+                double* trow = Ts + (size_t)(r >> 3) * I8_BN * 8 + (size_t)h * 32 * 8 + (r & 7);
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const double v = __ldcs(wsrc + (size_t)c * p.n_pad) - acc[c] * scale;
-                    trow[((h * 32 + c) ^ sw) * 8] = v;
+                for (int c = 0; c < 32; c += 2) {
+                    const double va = odd ? acc[c + 1] : acc[c], vb = odd ? acc[c] : acc[c + 1];
+                    double* pa = trow + (c + odd) * 8;
+                    double* pb = trow + (c + 1 - odd) * 8;
+                    *pa = fma(va, nscale, *pa);
+                    *pb = fma(vb, nscale, *pb);
                 }
+            } else {
+                i8_wait(ts_full, (uint32_t)(nq & 1));
             }
             named_bar_sync(1, I8_NCW * 32);
 
-            // ---- V_i = inv(L_ii) T_i : warp w owns rows 16 w .. 16 w + 15, all 64 columns ----
+            // ---- V_i = inv(L_ii) T_i : warp w owns the columns 8 w .. 8 w + 7 and all 128 rows (8 m-tiles) ----
             double vf[8][4];
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++)
+            for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-                for (int e = 0; e < 4; e++) vf[nt][e] = 0.0;
+                for (int e = 0; e < 4; e++) vf[mt][e] = 0.0;
+#pragma unroll
             for (int ch = 0; ch < NB / KC; ch++, dc++) {
                 const int ds = dc & 1;
                 i8_wait(&d_full[ds], (uint32_t)((dc >> 1) & 1));
-                if (ch <= warp) {                                      // inv(L_ii) is lower triangular: columns > row are zero
-                    const double* As = reinterpret_cast<const double*>(dring + ds * I8_DCHUNK);
+                const double* As = reinterpret_cast<const double*>(dring + ds * I8_DCHUNK);
 #pragma unroll
-                    for (int ksl = 0; ksl < KC / 8; ksl++) {
-                        const double* ap = As + ((size_t)(ksl * NB + warp * 16 + g) * 8 + 2 * t4);
+                for (int ksl = 0; ksl < KC / 8; ksl++) {
+                    const double2 bf =
+                        *reinterpret_cast<const double2*>(Ts + ((size_t)(ch * (KC / 8) + ksl) * I8_BN + warp * 8 + g) * 8 + 2 * t4);
+#pragma unroll
+                    for (int mt = ch; mt < 8; mt++) {          // inv(L_ii) is lower triangular: rows 16 mt .. need columns <= 16 mt + 15
+                        const double* ap = As + ((size_t)(ksl * NB + mt * 16 + g) * 8 + 2 * t4);
                         const double2 a0 = *reinterpret_cast<const double2*>(ap);
                         const double2 a1 = *reinterpret_cast<const double2*>(ap + 64);
-                        const int ks = ch * (KC / 8) + ksl, sw = (ks >> 1) & 1;
-                        const double* bp = Ts + (size_t)ks * I8_BN * 8 + 2 * t4;
-#pragma unroll
-                        for (int nt = 0; nt < 8; nt++) {
-                            const double2 bf = *reinterpret_cast<const double2*>(bp + ((nt * 8 + g) ^ sw) * 8);
-                            dmma_16x8x8(vf[nt], a0.x, a1.x, a0.y, a1.y, bf.x, bf.y);
-                        }
+                        dmma_16x8x8(vf[mt], a0.x, a1.x, a0.y, a1.y, bf.x, bf.y);
                     }
                 }
                 __syncwarp();
@@ -436,41 +454,58 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
             }
             named_bar_sync(1, I8_NCW * 32);       // every warp is done reading T_i: the buffer becomes the plane image of V_i
 
-            // ---- column norms, digits of V_i ----
-            // vf[nt][e]: row 16 warp + g (+ 8 for e >= 2), column 8 nt + 2 t4 (+ 1 for odd e)
+            // ---- column norms (complete inside the warp), digits of V_i ----
+            // vf[mt][e]: row 16 mt + g (+ 8 for e >= 2), column 8 warp + 2 t4 (+ 1 for odd e)
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++)
+            for (int e1 = 0; e1 < 2; e1++) {
+                double sq = 0.0;
 #pragma unroll
-                for (int e1 = 0; e1 < 2; e1++) {
-                    double s = fma(vf[nt][e1], vf[nt][e1], vf[nt][2 + e1] * vf[nt][2 + e1]);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    s += __shfl_xor_sync(0xffffffffu, s, 8);
-                    s += __shfl_xor_sync(0xffffffffu, s, 16);
-                    if (g == 0) nred[warp * I8_BN + nt * 8 + 2 * t4 + e1] = s;
-                }
+                for (int mt = 0; mt < 8; mt++) sq = fma(vf[mt][e1], vf[mt][e1], fma(vf[mt][2 + e1], vf[mt][2 + e1], sq));
+                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+                if (g == 0) nred[warp * 8 + 2 * t4 + e1] = sq;
+            }
             if (!last) {
                 const double vinv = ldexp(1.0, -es);
-                // K step of the later products = row / 32 = warp / 2, K half = warp & 1, byte in the 16-byte run = g (+ 8)
-                unsigned char* ib = img + (size_t)(warp >> 1) * BSTAGE + (warp & 1) * 128 + g;
+                // A lane holds 4 elements of an m-tile (e = 0..3); the four lanes g = 4a .. 4a+3 of one t4 hold 4 consecutive rows of
+                // each.  A 4 x 4 byte transpose over those lanes (two shuffle + permute steps) leaves lane j = g % 4 with the four
+                // row-consecutive digits of element slot e = j: one aligned 32-bit store, and a warp's store covers 128 contiguous
+                // bytes (conflict-free).  Byte (row rho, column c, plane tt) of the image: K step rho / 32, then plane, then
+                // (c / 8) 256 + (rho / 16 % 2) 128 + (c % 8) 16 + rho % 16.
+                const int j = g & 3;
+                unsigned char* ib = img + warp * 256 + (2 * t4 + (j & 1)) * 16 + (g >> 2) * 4 + (j >> 1) * 8;
 #pragma unroll
-                for (int nt = 0; nt < 8; nt++)
+                for (int mt = 0; mt < 8; mt++) {
+                    int8_t dig[4][S];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        int8_t dig[S];
-                        i8_digits<S>(vf[nt][e] * vinv, dig);
-                        unsigned char* dst = ib + nt * 256 + (2 * t4 + (e & 1)) * 16 + (e >> 1) * 8;
+                    for (int e = 0; e < 4; e++) i8_digits<S>(vf[mt][e] * vinv, dig[e]);
+                    unsigned char* dst = ib + (size_t)(mt >> 1) * BSTAGE + (mt & 1) * 128;
 #pragma unroll
-                        for (int tt = 0; tt < S; tt++) dst[tt * I8_BPLANE] = (unsigned char)dig[tt];
+                    for (int tt = 0; tt < S; tt++) {
+                        uint32_t x = (uint32_t)(uint8_t)dig[0][tt] | ((uint32_t)(uint8_t)dig[1][tt] << 8) |
+                                     ((uint32_t)(uint8_t)dig[2][tt] << 16) | ((uint32_t)(uint8_t)dig[3][tt] << 24);
+                        uint32_t y = __shfl_xor_sync(0xffffffffu, x, 4);
+                        x = __byte_perm(x, y, (j & 1) ? 0x3715 : 0x6240);
+                        y = __shfl_xor_sync(0xffffffffu, x, 8);
+                        x = __byte_perm(x, y, (j & 2) ? 0x3276 : 0x5410);
+                        *reinterpret_cast<uint32_t*>(dst + tt * I8_BPLANE) = x;
                     }
+                }
                 fence_proxy_async();              // generic-proxy writes of the image -> the bulk store's async-proxy read
             }
             named_bar_sync(1, I8_NCW * 32);
-            if (tid == 0 && !last) i8_bulk_store(p.Vq + ((size_t)tile * T + i) * VBLOCK, img, VBLOCK);
-            if (tid < I8_BN) {
-                const int64_t cg = (int64_t)pnl * I8_BN + tid;
-                double nrm = 0.0;
-#pragma unroll
-                for (int w = 0; w < I8_NCW; w++) nrm += nred[w * I8_BN + tid];
+            if (tid == 0) {
+                if (!last) {
+                    i8_bulk_store(p.Vq + ((size_t)tile * T + i) * VBLOCK, img, VBLOCK);
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the image has been read: K* of the next tile may land
+                }
+                mbar_arrive(ts_free);
+            }
+            if (tid >= 32 && tid < 32 + I8_BN) {
+                const int c = tid - 32;
+                const int64_t cg = (int64_t)pnl * I8_BN + c;
+                double nrm = nred[c];
                 double* na = p.normacc + (int64_t)o * p.w_stride + cg;
                 if (i > 0) nrm += __ldcg(na);
                 if (!last) {
@@ -483,7 +518,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_trsm_kernel(const __grid_con
                     p.var[(int64_t)og * p.var_stride + cg] = p.no_clip ? (top - nrm) : fmax(top - nrm, 0.0);
                 }
             }
-            if (tid == 0 && !last) i8_bulk_store_wait();      // planes of V_i are in global memory; the image may be overwritten
+            if (tid == 0 && !last) i8_bulk_store_wait();      // the planes of V_i are in global memory
             named_bar_sync(1, I8_NCW * 32);
             if (tid == 0 && !last) {
                 fence_proxy_async();
@@ -546,11 +581,12 @@ int i8_slice_L(int S, const double* A_slab, int64_t n_pad, const int* outs, cons
     return 0;
 }
 
-// W holds K* (test-major, left untouched); var receives the variances after the last block row
+// W holds K* (test-major, left untouched; tmW: its K-blocked map with a box of 64 rows); var receives the variances after
+// the last block row
 int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, const int8_t* Lq, int64_t lq_stride, int8_t* Vq,
-            const CUtensorMap& tmD, const double* W, int64_t w_stride, const double* hyper, int d, int include_nugget,
-            int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync, int n_sms,
-            cudaStream_t st) {
+            const CUtensorMap& tmD, const CUtensorMap& tmW, const double* W, int64_t w_stride, const double* hyper, int d,
+            int include_nugget, int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync,
+            int n_sms, cudaStream_t st) {
     I8TrsmParams p{};
     p.Lq = Lq; p.lq_stride = lq_stride; p.Vq = Vq; p.W = W; p.w_stride = w_stride; p.n_pad = n_pad; p.m = m;
     p.T = (int)(n_pad / NB); p.panels = panels; p.count = count;
@@ -563,8 +599,8 @@ int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, cons
     if (cudaMemsetAsync(sync, 0, i8_sync_bytes(count, panels), st) != cudaSuccess) return 1;
     const int64_t total = (int64_t)p.T * count * panels;
     const unsigned grid = (unsigned)(total < n_sms ? total : n_sms);
-    if (S == 6) i8_trsm_kernel<6><<<grid, I8_THREADS, I8Cfg<6>::SMEM, st>>>(tmD, p);
-    else i8_trsm_kernel<7><<<grid, I8_THREADS, I8Cfg<7>::SMEM, st>>>(tmD, p);
+    if (S == 6) i8_trsm_kernel<6><<<grid, I8_THREADS, I8Cfg<6>::SMEM, st>>>(tmD, tmW, p);
+    else i8_trsm_kernel<7><<<grid, I8_THREADS, I8Cfg<7>::SMEM, st>>>(tmD, tmW, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

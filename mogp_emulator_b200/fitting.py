@@ -9,24 +9,36 @@ so results are comparable with the CPU ``GaussianProcess`` fit by fit.
 import numpy as np
 from scipy.optimize import minimize
 
+from . import libmogp
 from .GaussianProcessGPU import GaussianProcessGPU
 from .MultiOutputGP_GPU import MultiOutputGP_GPU
 
 
-def _minimise_one(logpost, grad, sample, n_params, n_tries, theta0, method, options):
-    """n_tries restarts (first from theta0 when given, the rest from prior samples); a restart whose
-    factorisation fails or whose arithmetic overflows is skipped (fitting.py:237-258)."""
-    best_val, best_theta = None, None
+def _start_points(sample, n_params, n_tries, theta0):
+    """The n_tries start points of one emulator: theta0 first when given, the rest drawn from the prior
+    (fitting.py:237-243).  Drawn up front on the calling thread, so a multi-output search consumes the global numpy
+    random stream in emulator order -- reproducible under a seed like the reference's serial loop."""
+    starts = []
     for i in range(n_tries):
         if i == 0 and theta0 is not None:
             start = np.array(theta0, dtype=np.float64)
             assert start.shape == (n_params,), "theta0 must be a 1D array with length n_params"
         else:
-            start = sample()
+            start = np.array(sample(), dtype=np.float64)
+        starts.append(start)
+    return starts
+
+
+def _minimise_one(logpost, grad, starts, method, options):
+    """One L-BFGS-B run per start point; a restart whose factorisation fails (kernel matrix or H^T K^-1 H not positive
+    definite: ``NotPositiveDefiniteError`` / ``LinAlgError``) or whose arithmetic overflows is skipped
+    (fitting.py:237-258).  Any other error -- CUDA, argument, NCCL -- propagates."""
+    best_val, best_theta = None, None
+    for start in starts:
         try:
             with np.errstate(divide="raise", over="raise", invalid="raise"):
                 res = minimize(logpost, start, method=method, jac=grad, options=options)
-        except RuntimeError:
+        except (libmogp.NotPositiveDefiniteError, np.linalg.LinAlgError):
             print("Matrix not positive definite, skipping this iteration")
             continue
         except FloatingPointError:
@@ -35,6 +47,12 @@ def _minimise_one(logpost, grad, sample, n_params, n_tries, theta0, method, opti
         if best_val is None or res["fun"] < best_val:
             best_val, best_theta = res["fun"], res["x"]
     return best_theta
+
+
+def _check_dims(d):
+    if d > libmogp.GRAD_MAX_DIMS:
+        raise ValueError("fit_GP_MAP on the GPU needs log-posterior gradients, which libmogp_b200 provides for at most %d "
+                         "input dimensions (this emulator has %d)" % (libmogp.GRAD_MAX_DIMS, d))
 
 
 def _check_method(method):
@@ -49,8 +67,9 @@ def _fit_single_GPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", **kwar
     assert n_tries > 0, "number of attempts must be positive"
     if theta0 is not None and len(theta0) == 0:
         theta0 = None
-    best = _minimise_one(gp.logposterior, gp.logpost_deriv, gp.priors.sample, gp.n_params, n_tries, theta0, method,
-                         kwargs)
+    _check_dims(gp.D)
+    best = _minimise_one(gp.logposterior, gp.logpost_deriv, _start_points(gp.priors.sample, gp.n_params, n_tries, theta0),
+                         method, kwargs)
     if best is None:
         print("Minimization routine failed to return a value")
         gp.theta = None
@@ -87,8 +106,12 @@ class _LockstepEvaluator(object):
         thetas = [self._pending[i] for i in idx]
         self._pending = {}
         try:
-            res = self._batch_fn(idx, thetas)
-        except Exception as exc:            # a failure of the call itself: hand it to every waiter
+            # the batch runs on whichever worker arrived last, under that thread's np.errstate(raise): give it the default
+            # error state, so one emulator's host arithmetic cannot fail the whole batch (per-emulator failures come back
+            # as None / an exception object per index)
+            with np.errstate(divide="warn", over="warn", invalid="warn"):
+                res = self._batch_fn(idx, thetas)
+        except Exception as exc:            # a failure of the call itself (CUDA, memory ...): hand it to every waiter
             res = {i: exc for i in idx}
         self.n_batches += 1
         self.batch_sizes.append(len(idx))
@@ -106,7 +129,7 @@ class _LockstepEvaluator(object):
         if isinstance(res, Exception):
             raise res
         if res is None:
-            raise RuntimeError("Unable to fit the Gaussian process: matrix not positive definite")
+            raise libmogp.NotPositiveDefiniteError("Unable to fit the Gaussian process: matrix not positive definite")
         return res
 
     def done(self, index):
@@ -140,7 +163,10 @@ def _fit_MOGPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", refit=False
     todo = list(range(lo, hi)) if refit else [i for i in gp.get_indices_not_fit() if lo <= i < hi]
     if not todo:
         return gp
+    _check_dims(gp.D)
     priors = {i: gp.priors[i] for i in todo}       # built on the calling thread
+    # start points drawn here, in emulator order: reproducible under np.random.seed (the workers run concurrently)
+    start_points = {i: _start_points(priors[i].sample, gp.n_params[i], n_tries, starts[i]) for i in todo}
     evaluator = _LockstepEvaluator(gp.logpost_and_deriv_batch, todo)
     best = {}
     errors = []
@@ -150,7 +176,7 @@ def _fit_MOGPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", refit=False
             def fun(theta):
                 val, grad = evaluator.evaluate(i, theta)
                 return val, grad
-            best[i] = _minimise_one(fun, True, priors[i].sample, gp.n_params[i], n_tries, starts[i], method, kwargs)
+            best[i] = _minimise_one(fun, True, start_points[i], method, kwargs)
         except BaseException as exc:     # noqa: BLE001 - reported on the calling thread
             errors.append((i, exc))
         finally:
@@ -171,6 +197,7 @@ def _fit_MOGPGPU_MAP(gp, n_tries=15, theta0=None, method="L-BFGS-B", refit=False
     for i in todo:
         if best.get(i) is None:
             gp.reset_emulator(i)
+    gp.sync_fit_status()         # sharded emulators: every rank learns which outputs of the other ranks converged
     gp.map_fit_stats = {"batches": evaluator.n_batches, "mean_batch": float(np.mean(evaluator.batch_sizes or [0]))}
     return gp
 

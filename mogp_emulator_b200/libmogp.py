@@ -71,6 +71,7 @@ SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "mogp_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mogp_comm_allreduce_max": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
+    "mogp_comm_allgather": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int64, _c_double_p]),
     "mogp_peak_dmma": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_double_p]),
     "mogp_peak_i8": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _c_double_p]),
 }
@@ -121,6 +122,15 @@ def last_error():
     return _lib.mogp_last_error().decode("utf-8", "replace") if _lib is not None else (_load_error or "")
 
 
+class NotPositiveDefiniteError(RuntimeError):
+    """The kernel matrix (or the mean function's H^T K^-1 H) could not be factorised (LAPACK info > 0).  A RuntimeError like
+    the reference GPU class raises (densegp_gpu.hpp:556-570); the MAP search skips the restart on exactly this type, so
+    CUDA / argument / NCCL failures are never mistaken for it."""
+
+
+GRAD_MAX_DIMS = 64     # csrc/grad.cu G_MAXD: input dimensions mogp_logpost_grad_list supports
+
+
 def check(status, what=""):
     """Map a status code to the exception type the reference's front-end raises
     (std::runtime_error -> RuntimeError, densegp_gpu.hpp:495,556-570; ValueError for predict-before-fit,
@@ -132,6 +142,8 @@ def check(status, what=""):
         raise ValueError("hyperparameters have not been fit for this Gaussian Process")
     if status == ERR_NOMEM:
         raise MemoryError(msg)
+    if status == ERR_NOT_PD:
+        raise NotPositiveDefiniteError(msg)
     raise RuntimeError(msg)
 
 
@@ -343,6 +355,13 @@ class Comm(object):
         v = ctypes.c_double(float(value))
         check(_lib.mogp_comm_allreduce_max(self._c, ctypes.byref(v)), "mogp_comm_allreduce_max")
         return float(v.value)
+
+    def allgather(self, block):
+        """(count,) float64 per rank -> (world, count): one ncclAllGather between host buffers."""
+        block = as_f64(block).reshape(-1)
+        out = np.empty((self.world, block.size))
+        check(_lib.mogp_comm_allgather(self._c, dptr(block), block.size, dptr(out)), "mogp_comm_allgather")
+        return out
 
     def close(self):
         if getattr(self, "_c", None) is not None and self._c.value and _lib is not None:

@@ -1,15 +1,19 @@
-"""Block partition of the outputs of a multi-output emulator over ranks: rank r owns
-``[r*ceil(E/R), min(E, (r+1)*ceil(E/R)))``; every rank's gather block is padded to ``ceil(E/R)`` rows so the
-all-gather counts are equal.  Pure host logic, shared by the NCCL path and the gloo CPU tests."""
+"""Balanced block partition of the outputs of a multi-output emulator over ranks: with
+``q, rem = divmod(E, R)`` the first ``rem`` ranks own ``q + 1`` consecutive outputs and the others ``q`` (so no rank
+is empty while ``R <= E``; with more ranks than outputs the trailing ranks own none and still join the gather with an
+all-padding block).  Every rank's gather block is padded to ``e_pad = ceil(E/R)`` rows so the all-gather counts are
+equal.  Pure host logic, shared by the NCCL path and the gloo CPU tests."""
 
 
 def shard_bounds(n_outputs, rank, world):
     """-> (lo, hi, e_pad)."""
     if world < 1 or not 0 <= rank < world:
         raise ValueError("bad rank/world")
-    e_pad = -(-int(n_outputs) // int(world))
-    lo = min(n_outputs, rank * e_pad)
-    hi = min(n_outputs, (rank + 1) * e_pad)
+    n_outputs, rank, world = int(n_outputs), int(rank), int(world)
+    q, rem = divmod(n_outputs, world)
+    e_pad = q + (1 if rem else 0)
+    lo = rank * q + min(rank, rem)
+    hi = lo + q + (1 if rank < rem else 0)
     return lo, hi, e_pad
 
 
@@ -45,7 +49,7 @@ def pack_block(mean, var, fitted, e_pad):
 def unpack_gathered(gathered, n_outputs, world, m):
     """(world, e_pad*2*m + e_pad) gathered blocks -> mean (E, m), var (E, m), status (E,) in output order."""
     import numpy as np
-    e_pad = -(-int(n_outputs) // int(world))
+    e_pad = shard_bounds(n_outputs, 0, world)[2]
     gathered = np.asarray(gathered).reshape(world, e_pad * 2 * m + e_pad)
     mean = np.empty((n_outputs, m))
     var = np.empty((n_outputs, m))

@@ -200,8 +200,7 @@ def test_lockstep_evaluator_batches_concurrent_optimisations():
 
     def worker(i):
         try:
-            best[i] = _minimise_one(lambda th: ev.evaluate(i, th), True, lambda: np.zeros(2), 2, 1, np.zeros(2),
-                                    "L-BFGS-B", {})
+            best[i] = _minimise_one(lambda th: ev.evaluate(i, th), True, [np.zeros(2)], "L-BFGS-B", {})
         finally:
             ev.done(i)
 
@@ -219,13 +218,26 @@ def test_lockstep_evaluator_batches_concurrent_optimisations():
     assert max(len(c) for c in calls) == 4 and ev.n_batches < sum(len(c) for c in calls)
 
 
-def test_gathered_rows_are_already_in_output_order():
-    """MultiOutputGP_GPU.predict slices the gathered (world*e_pad, m) block with [:E] instead of copying rows: that is
-    only right because a block partition puts rank r's first output at row r*e_pad."""
+def test_balanced_partition_and_gathered_rows():
+    """The partition is balanced (no rank is empty while world <= E; ADVICE r1: the ceil-block split left trailing ranks
+    without outputs and hung the all-gather), contiguous and ordered; the gathered (world*e_pad, m) block is already in
+    output order exactly when the split is even, otherwise ``gathered_rows`` names the rows to pick."""
     from mogp_emulator_b200 import sharding
-    for E in (1, 2, 5, 8, 31, 32, 33, 256):
+    for E in (1, 2, 5, 8, 9, 14, 31, 32, 33, 256):
         for world in (1, 2, 3, 4, 8):
-            assert sharding.gathered_rows(E, world) == list(range(E))
+            bounds = [sharding.shard_bounds(E, r, world) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == E
+            assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi, _ in bounds]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) == bounds[0][2]
+            if world <= E:
+                assert min(sizes) >= 1
+            rows = sharding.gathered_rows(E, world)
+            assert len(rows) == E and rows == sorted(rows)
+            if E % world == 0:
+                assert rows == list(range(E))
+            e_pad = bounds[0][2]
+            assert rows == [r * e_pad + k for r in range(world) for k in range(sizes[r])]
 
 
 @pytest.mark.parametrize("formula", ["1", "x[0]", "-1 + x[0]*x[1]"])
