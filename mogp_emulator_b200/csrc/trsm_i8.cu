@@ -84,6 +84,14 @@ __host__ __device__ constexpr uint32_t i8_idesc(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(NB >> 4) << 24);
 }
 
+// The issuing thread is chosen with elect.sync: ptxas then knows a single lane is active and moves the operands to uniform
+// registers with plain R2UR; behind `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST / branch loop
+// and the issue thread, not the tensor pipe, set the pace (profiles/r02_i8_timeline.txt).
+__device__ __forceinline__ bool i8_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -122,7 +130,36 @@ __device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// S signed 7-bit digits of x in (-0.5, 0.5):  x = sum_t d_t 2^-7t + O(2^-(7S+1)).  Every step is exact in FP64.
+// S signed 7-bit digits of v 2^-es in [-0.5, 0.5] in INTEGER arithmetic (FP64 instructions share the tensor datapath with the
+// int8 MMAs on this chip -- tools/probe_concurrency.cu -- so the epilogue keeps them to a minimum): q = round(v 2^(7S - es))
+// from the bits of v, then d_t = round(q / 2^(7(S-t))) top down, q -= d_t 2^(7(S-t)).  sum_t d_t 2^-7t = q 2^-7S exactly;
+// |d_t| <= 64 (|d_1| <= 127 for out-of-range input, which degrades instead of wrapping int8).  Differs from the FP64 form
+// below only in how exact ties round.
+template <int S>
+__device__ __forceinline__ void i8_digits_int(double v, int es, int8_t (&dig)[S]) {
+    const long long bits = __double_as_longlong(v);
+    const int e = (int)((bits >> 52) & 0x7FF);
+    const unsigned long long mant = ((unsigned long long)bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+    int sh = 1075 + es - 7 * S - e;                        // v 2^(7S - es) = mant 2^-sh
+    long long q = 0;
+    if (e != 0 && sh < 64) {
+        sh = sh < 1 ? 1 : sh;                              // (never for |v 2^-es| <= 0.5: sh >= 4)
+        q = (long long)((mant + (1ull << (sh - 1))) >> sh);
+        const long long qmax = 127ll << (7 * (S - 1));
+        q = q > qmax ? qmax : q;
+        q = bits < 0 ? -q : q;
+    }
+#pragma unroll
+    for (int t = 1; t < S; t++) {
+        const int shift = 7 * (S - t);
+        const long long d = (q + (1ll << (shift - 1))) >> shift;
+        q -= d << shift;
+        dig[t - 1] = (int8_t)d;
+    }
+    dig[S - 1] = (int8_t)q;
+}
+
+// The same digits in FP64 (the slicing pass of L, a separate kernel):  x = sum_t d_t 2^-7t + O(2^-(7S+1)), every step exact.
 template <int S>
 __device__ __forceinline__ void i8_digits(double x, int8_t (&dig)[S]) {
     x = fmin(fmax(x, -0.99), 0.99);        // in-range data has |x| <= 0.5; out-of-range input degrades instead of wrapping int8
@@ -212,6 +249,24 @@ struct I8TrsmParams {
 
 constexpr int I8_SYNC_HDR = 32;
 
+// -DI8_TRACE: CTA 0 records globaltimer stamps of its pipeline events (tools/i8_timeline.py reads them through
+// mogp_debug_i8_trace); compiled out of the product build
+#ifdef I8_TRACE
+constexpr int I8_TRACE_EV = 16, I8_TRACE_TILES = 2048;
+__device__ unsigned long long i8_trace_buf[I8_TRACE_TILES * I8_TRACE_EV];
+#define I8_STAMP(seq, ev)                                                                                        \
+    do {                                                                                                         \
+        if (blockIdx.x == 0 && (seq) < I8_TRACE_TILES) i8_trace_buf[(seq) * I8_TRACE_EV + (ev)] = globaltimer_ns(); \
+    } while (0)
+#define I8_STAMPV(seq, ev, val)                                                                                  \
+    do {                                                                                                         \
+        if (blockIdx.x == 0 && (seq) < I8_TRACE_TILES) i8_trace_buf[(seq) * I8_TRACE_EV + (ev)] = (unsigned long long)(val); \
+    } while (0)
+#else
+#define I8_STAMP(seq, ev) do { } while (0)
+#define I8_STAMPV(seq, ev, val) do { } while (0)
+#endif
+
 template <int S>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW, const I8TrsmParams p) {
@@ -237,7 +292,10 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
     int* tq = reinterpret_cast<int*>(tq_empty + I8_QN);                              // [QN]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tq + I8_QN);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches and everything
+    // computed inside them from uniform inputs (ring slots, descriptors) on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int T = p.T;
     const int per_row = p.count * p.panels;
     const int total = T * per_row;
@@ -273,7 +331,7 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
 
     if (warp == I8_NCW + 1) {
         // ================================ tickets + operand loader ================================
-        if (lane == 0) {
+        if (i8_elect_one()) {
             int it = 0;
             for (int nq = 0;; nq++) {
                 const int slot = nq % I8_QN;
@@ -283,12 +341,15 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 mbar_arrive(&tq_full[slot]);
                 if (t >= total) break;
                 const int i = t / per_row, tile = t - i * per_row;
+                I8_STAMPV(nq, 0, i);
+                I8_STAMP(nq, 1);
                 if (i == 0) continue;
                 const int o = tile / p.panels;
                 // the panel's block rows 0 .. i-1 are solved and their planes stored (async-proxy writes of another CTA,
                 // published by red.release after the bulk store completed)
                 wait_counter(flags + tile, i);
                 fence_proxy_async();
+                I8_STAMP(nq, 2);
                 const int8_t* a_src = p.Lq + (size_t)p.outs[o] * p.lq_stride + (size_t)(i * (i - 1) / 2) * LBLOCK;
                 const int8_t* b_src = p.Vq + (size_t)tile * T * VBLOCK;
                 for (int st = 0; st < 4 * i; st++, it++) {
@@ -299,11 +360,12 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                     i8_bulk_load(dst, a_src + (size_t)st * ASTAGE, ASTAGE, &full[rs]);
                     i8_bulk_load(dst + ASTAGE, b_src + (size_t)st * BSTAGE, BSTAGE, &full[rs]);
                 }
+                I8_STAMP(nq, 3);
             }
         }
     } else if (warp == I8_NCW + 2) {
         // ================================ K*_i and inv(L_ii) loader ================================
-        if (lane == 0) {
+        if (i8_elect_one()) {
             prefetch_tmap(&tmD);
             prefetch_tmap(&tmW);
             int dc = 0;
@@ -334,8 +396,8 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
             }
         }
     } else if (warp == I8_NCW) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // ================================ MMA issuer (one elected thread) ================================
+        if (i8_elect_one()) {
             int it = 0, k = 0;
             for (int nq = 0;; nq++) {
                 const int slot = nq % I8_QN;
@@ -350,11 +412,13 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                     i8_fence_after();
                 }
                 k++;
+                I8_STAMP(nq, 4);
                 for (int st = 0; st < 4 * i; st++, it++) {
                     const int rs = it % NS;
                     i8_wait(&full[rs], (uint32_t)((it / NS) & 1));
                     i8_fence_after();
                     const uint32_t a0 = smem_u32(base + rs * STAGE), b0 = a0 + ASTAGE;
+                    const uint64_t bd0 = i8_desc(b0), bd1 = i8_desc(b0 + 4 * I8_BPLANE);
 #pragma unroll
                     for (int tt = 1; tt <= S; tt++) {
                         const int ncols = I8_BN * (S + 1 - tt);
@@ -362,12 +426,13 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                         const uint32_t d0 = tmem + (uint32_t)(tt - 1) * I8_BN;
                         const uint64_t ad = i8_desc(a0 + (tt - 1) * I8_APLANE);
                         const int n1 = ncols > 256 ? 256 : ncols;
-                        i8_mma(d0, ad, i8_desc(b0), accum, i8_idesc(n1));
-                        if (ncols > 256) i8_mma(d0 + 256, ad, i8_desc(b0 + 4 * I8_BPLANE), accum, i8_idesc(ncols - 256));
+                        i8_mma(d0, ad, bd0, accum, i8_idesc(n1));
+                        if (ncols > 256) i8_mma(d0 + 256, ad, bd1, accum, i8_idesc(ncols - 256));
                     }
                     i8_commit(&empty[rs]);        // the slot is free once these MMAs have read it
                 }
                 i8_commit(acc_full);              // every MMA of the tile has completed
+                I8_STAMP(nq, 5);
             }
         }
     } else {
@@ -387,26 +452,38 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
             const int o = tile / p.panels, pnl = tile - o * p.panels;
             const bool last = (i + 1 == T);
             const int es = p.eS[o];
+            if (tid == 0) I8_STAMP(nq, 6);
 
             // ---- T_i = K*_i - 2^(2 eS) sum_w 2^-7w acc_w, in place in the K-blocked buffer K*_i was loaded into ----
             if (i > 0) {
-                double acc[32];
+                // sum_w 2^-7(w+2) acc_w in two 64-bit integer halves (accumulators 0..3 and 4..S-1; |acc_w| < 2^30, so the
+                // sums stay below 2^52 and 2^45), converted once each
+                long long hi[32], lo[32];
 #pragma unroll
-                for (int c = 0; c < 32; c++) acc[c] = 0.0;
+                for (int c = 0; c < 32; c++) hi[c] = lo[c] = 0;
                 i8_wait(acc_full, (uint32_t)(k & 1));
                 k++;
                 i8_fence_after();
+                if (tid == 0) I8_STAMP(nq, 7);
 #pragma unroll
                 for (int w = 0; w < S; w++) {
                     uint32_t v[32];
                     i8_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(w * I8_BN + h * 32), v);
-                    const double wgt = __longlong_as_double((long long)(1023 - I8_BITS * (w + 2)) << 52);   // 2^-7(w+2)
 #pragma unroll
-                    for (int c = 0; c < 32; c++) acc[c] = fma((double)(int32_t)v[c], wgt, acc[c]);
+                    for (int c = 0; c < 32; c++) {
+                        if (w < 4) hi[c] += (long long)(int32_t)v[c] << (I8_BITS * (3 - w));
+                        else lo[c] += (long long)(int32_t)v[c] << (I8_BITS * (S - 1 - w));
+                    }
                 }
                 i8_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
+                if (tid == 0) I8_STAMP(nq, 8);
+                double acc[32];
+                {
+                    const double whi = __longlong_as_double((long long)(1023 - I8_BITS * 5) << 52);         // accumulator 3: 2^-35
+                    const double wlo = __longlong_as_double((long long)(1023 - I8_BITS * (S + 1)) << 52);   // accumulator S-1
+#pragma unroll
+                    for (int c = 0; c < 32; c++) acc[c] = fma((double)lo[c], wlo, (double)hi[c] * whi);
+                }
                 i8_wait(ts_full, (uint32_t)(nq & 1));
                 const double nscale = -ldexp(1.0, 2 * es);
                 // element (r, col) at Ts[r / 8][col][r % 8]: the four 8-lane groups of a warp write four slabs 4 KB apart, so the
@@ -425,6 +502,7 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 i8_wait(ts_full, (uint32_t)(nq & 1));
             }
             named_bar_sync(1, I8_NCW * 32);
+            if (tid == 0) I8_STAMP(nq, 9);
 
             // ---- V_i = inv(L_ii) T_i : warp w owns the columns 8 w .. 8 w + 7 and all 128 rows (8 m-tiles) ----
             double vf[8][4];
@@ -453,6 +531,13 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(&d_empty[ds]);
             }
             named_bar_sync(1, I8_NCW * 32);       // every warp is done reading T_i: the buffer becomes the plane image of V_i
+            // FP64 instructions and the int8 MMAs share one datapath, and a saturated MMA stream starves them
+            // (tools/probe_concurrency.cu): releasing the MMA warp right after the drain stretched this tile's diagonal product
+            // over the whole MMA phase of the next tile and left digits + store exposed behind it (profiles/r02_i8_timeline.txt).
+            // So the accumulators are handed back only here: the FP64 part runs at full rate first, the integer / memory part of
+            // the epilogue below overlaps the next tile's MMAs.
+            if (i > 0 && lane == 0) mbar_arrive(acc_empty);
+            if (tid == 0) I8_STAMP(nq, 10);
 
             // ---- column norms (complete inside the warp), digits of V_i ----
             // vf[mt][e]: row 16 mt + g (+ 8 for e >= 2), column 8 warp + 2 t4 (+ 1 for odd e)
@@ -467,7 +552,6 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 if (g == 0) nred[warp * 8 + 2 * t4 + e1] = sq;
             }
             if (!last) {
-                const double vinv = ldexp(1.0, -es);
                 // A lane holds 4 elements of an m-tile (e = 0..3); the four lanes g = 4a .. 4a+3 of one t4 hold 4 consecutive rows of
                 // each.  A 4 x 4 byte transpose over those lanes (two shuffle + permute steps) leaves lane j = g % 4 with the four
                 // row-consecutive digits of element slot e = j: one aligned 32-bit store, and a warp's store covers 128 contiguous
@@ -479,7 +563,7 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 for (int mt = 0; mt < 8; mt++) {
                     int8_t dig[4][S];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) i8_digits<S>(vf[mt][e] * vinv, dig[e]);
+                    for (int e = 0; e < 4; e++) i8_digits_int<S>(vf[mt][e], es, dig[e]);
                     unsigned char* dst = ib + (size_t)(mt >> 1) * BSTAGE + (mt & 1) * 128;
 #pragma unroll
                     for (int tt = 0; tt < S; tt++) {
@@ -495,6 +579,7 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 fence_proxy_async();              // generic-proxy writes of the image -> the bulk store's async-proxy read
             }
             named_bar_sync(1, I8_NCW * 32);
+            if (tid == 0) I8_STAMP(nq, 11);
             if (tid == 0) {
                 if (!last) {
                     i8_bulk_store(p.Vq + ((size_t)tile * T + i) * VBLOCK, img, VBLOCK);
@@ -525,6 +610,7 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 __threadfence();
                 red_release_gpu_add(flags + tile, 1);
             }
+            if (tid == 0) I8_STAMP(nq, 12);
         }
     }
     i8_fence_before();
@@ -605,3 +691,10 @@ int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, cons
 }
 
 }  // namespace mogp
+
+#ifdef I8_TRACE
+extern "C" int mogp_debug_i8_trace(unsigned long long* out, int n_words) {
+    const size_t bytes = sizeof(unsigned long long) * (size_t)(n_words < mogp::I8_TRACE_TILES * mogp::I8_TRACE_EV ? n_words : mogp::I8_TRACE_TILES * mogp::I8_TRACE_EV);
+    return cudaMemcpyFromSymbol(out, mogp::i8_trace_buf, bytes) == cudaSuccess ? 0 : 1;
+}
+#endif
