@@ -153,12 +153,21 @@ def i8_planes():
 
 def ncu_traffic(workload, world):
     """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture
-    of this same command (profiles/r01_traffic.json); None when that workload / GPU count was not captured."""
+    of this same command (profiles/r02_traffic.json); None when that workload / GPU count was not captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f).get("%s@%d" % (workload, world))
     except (OSError, ValueError):
         return None
+
+
+def measured_bf16():
+    """Driver-measured dense bf16 burst TFLOP/s of this pool's B200s (MEASURED_PEAKS.json), for context only."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except (OSError, ValueError, KeyError):
+        return 1590.0
 
 
 def run_c2(args, wl):
@@ -349,29 +358,30 @@ def run_b200(args, wl):
                 "flops_per_launch": trsm_flops * args.steps / tm["n_trsm"] if tm["n_trsm"] else None,
                 "ms_per_launch": trsm_ms, "outputs_per_launch": units_per_launch}
     if tm.get("i8_block_rows", 0) > 0:
-        # the predict TRSM ran on the int8 tcgen05 path (csrc/trsm_i8.cu): the dominant kernel is i8_row_kernel, one launch
-        # per block row.  Algorithmic work of a launch = its kind::i8 MMAs: tiles x (4 K-steps per 128-block of history) x
-        # plane pairs x 2*128*64*32 integer ops; DESIGN.md section 3 states the count.
+        # the predict TRSM ran on the int8 tcgen05 path (csrc/trsm_i8.cu): the dominant kernel is i8_trsm_kernel, ONE persistent
+        # launch per predict call.  Algorithmic work = its kind::i8 MMAs: panels x (4 K-steps per 128-block of history) x plane
+        # pairs x 2*128*64*32 integer ops; DESIGN.md section 3 states the count.
         planes = i8_planes()
         pairs = planes * (planes + 1) // 2
         T = (n + 127) // 128
         panels = (m + 63) // 64
         ops_step = float(e_loc) * panels * (T * (T - 1) // 2) * 4 * pairs * 2.0 * 128 * 64 * 32
         rows_ms = tm["i8_rows_ms"] / args.steps
-        launches = tm["i8_block_rows"] / args.steps
         peak256, peak64 = libmogp.peak_i8_tops(device)
         ach = ops_step / (rows_ms * 1e-3) * 1e-12
-        roofline = {"bound": "tensor", "kernel": "i8_row_kernel<%d> (V_i = K~*_i - sum_j L~_ij V_j, tcgen05.mma kind::i8, "
-                                                 "%d plane pairs per K step)" % (planes, pairs),
+        roofline = {"bound": "tensor", "kernel": "i8_trsm_kernel<%d> (V_i = inv(L_ii)(K*_i - sum_j L_ij V_j): tcgen05.mma kind::i8 on %d "
+                                                 "plane pairs per K step, FP64 DMMA epilogue; one persistent launch)" % (planes, pairs),
                     "achieved": ach, "peak": peak256, "unit": "TOP/s", "frac": ach / peak256,
                     "traffic": ncu_traffic(args.workload + "-i8", world),
                     "peak_source": "int8 tcgen05 issue peak (M128 N256 K32 MMAs from resident operands) measured in this run "
-                                   "(mogp_peak_i8); the M128 N64 K32 shape the kernel is confined to by TMEM capacity issues at "
-                                   "%.0f TOP/s (frac of that: %.3f)" % (peak64, ach / peak64),
-                    "ops_per_launch": ops_step / launches, "ms_per_launch": rows_ms / launches,
-                    "launches_per_step": launches, "outputs_per_launch": float(e_loc),
+                                   "(mogp_peak_i8) at the clock of an otherwise idle chip; the timed kernel runs under the 1 kW power "
+                                   "cap (see clocks).  MEASURED_PEAKS.json has no int8 entry; twice its bf16 burst figure would be "
+                                   "%.0f TOP/s" % (2.0 * measured_bf16()),
+                    "ops_per_launch": ops_step, "ms_per_launch": rows_ms,
+                    "launches_per_step": 1.0, "outputs_per_launch": float(e_loc),
                     "fp64_equivalent_tflops": trsm_flops * (1.0 - 1.0 / T) / (rows_ms * 1e-3) * 1e-12,
                     "fp64_dmma_peak_tflops": peak,
+                    "accuracy_check_ms": tm.get("i8_check_ms", 0.0) / args.steps, "fp64_fallbacks": tm.get("i8_fallbacks", 0.0),
                     "whole_trsm_phase": {"ms": tm["trsm_ms"] / args.steps, "fp64_equivalent_tflops": achieved,
                                          "vs_dmma_peak": achieved / peak if achieved else None}}
     config = workload_config(args.workload, wl, world)
@@ -379,14 +389,17 @@ def run_b200(args, wl):
         config["trsm_path"] = ("int8 tcgen05, %d planes per operand: the O(n^2 m) products of the FP64 forward substitution are "
                                "evaluated exactly on signed 7-bit digits (error-free splitting), everything else -- kernel "
                                "matrices, Cholesky, solves, means, the diagonal-block products, recombination and norms -- is "
-                               "IEEE FP64; variances agree with the all-FP64 path (MOGP_TRSM_I8=0) to 4e-12 on this workload, "
-                               "see parity_vs_cpu_sample" % i8_planes())
+                               "IEEE FP64; every call is checked a posteriori against FP64 solves of sampled test points "
+                               "(accuracy_check_ms) and falls back to the all-FP64 kernel when they disagree; see parity_vs_cpu_sample"
+                               % i8_planes())
+        dtype = "f64 (predict TRSM: %d x int8 planes on tcgen05, exact s32 accumulation, FP64 epilogue)" % i8_planes()
     else:
         config["trsm_path"] = "FP64 DMMA"
+        dtype = "f64"
     line = {
         "metric": "gp_fit_predict_seconds", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": config,
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "s",
@@ -400,23 +413,30 @@ def run_b200(args, wl):
                                "kstar_and_mean": tm["kstar_ms"] / args.steps,
                                "predict_trsm": tm["trsm_ms"] / args.steps,
                                "trsm_i8_planes_of_L": tm.get("i8_prep_ms", 0.0) / args.steps,
-                               "trsm_i8_ktilde": tm.get("i8_ktilde_ms", 0.0) / args.steps,
-                               "trsm_i8_block_rows": tm.get("i8_rows_ms", 0.0) / args.steps},
+                               "trsm_i8_accuracy_check": tm.get("i8_check_ms", 0.0) / args.steps,
+                               "trsm_i8_kernel": tm.get("i8_rows_ms", 0.0) / args.steps},
         "phases_ms_per_step_max_over_ranks": phase_max,
         "host_wall_ms_per_step": dict(wall_ms, predict_device_part=tm["predict_device_wall_ms"] / args.steps,
                                       predict_copy_out=tm["predict_d2h_wall_ms"] / args.steps),
         "cholesky_tflops": (e_loc * (n ** 3) / 3.0) / (tm["chol_ms"] / args.steps * 1e-3) * 1e-12 if tm["chol_ms"] else None,
         "fit_tflops": (e_loc * (n ** 3) / 3.0) / (tm["fit_ms"] / args.steps * 1e-3) * 1e-12 if tm["fit_ms"] else None,
     }
-    if world == 1 and not args.no_cpu:
-        # bounded CPU sample on the same box: one output of the job with the oracle port of the reference
-        dt, cmean, cvar = oracle_step(X, Y[0], Xs, thetas[0], kernel, nugget)
-        line["cpu_baseline"] = {"value": dt * E, "unit": "s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "fit+predict of output 0 only (%.2f s on %d host cores), scaled x%d outputs"
-                                          % (dt, os.cpu_count(), E)}
-        gmean, gvar = res.mean[0], res.unc[0]
-        line["parity_vs_cpu_sample"] = {"mean_max_rel": float(np.max(np.abs(gmean - cmean)) / np.max(np.abs(cmean))),
-                                        "var_max_abs": float(np.max(np.abs(gvar - cvar)))}
+    if not args.no_cpu:
+        # bounded CPU sample on the same box: ONE output of the job with the oracle port of the reference.  At N > 1 it is the
+        # LAST output -- owned by the last rank, so the row rank 0 checks arrived through the all-gather.
+        o_chk = E - 1 if world > 1 else 0
+        dt, cmean, cvar = oracle_step(X, Y[o_chk], Xs, thetas[o_chk], kernel, nugget)
+        if world == 1:
+            line["cpu_baseline"] = {"value": dt * E, "unit": "s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "fit+predict of output 0 only (%.2f s on %d host cores), scaled x%d outputs"
+                                              % (dt, os.cpu_count(), E)}
+        gmean, gvar = res.mean[o_chk], res.unc[o_chk]
+        nug = float(nugget) if not isinstance(nugget, str) else 0.0
+        line["parity_vs_cpu_sample"] = {"output": o_chk, "owner_rank": world - 1 if world > 1 else 0,
+                                        "mean_max_rel": float(np.max(np.abs(gmean - cmean)) / np.max(np.abs(cmean))),
+                                        "var_max_abs": float(np.max(np.abs(gvar - cvar))),
+                                        "var_worst_vs_tolerance": float(np.max(np.abs(gvar - cvar) / (1e-4 * np.abs(cvar) + 1e-4 * nug + 1e-300))),
+                                        "all_outputs_finite": bool(np.all(np.isfinite(res.mean)) and np.all(np.isfinite(res.unc)))}
     print(json.dumps(line))
 
 

@@ -27,7 +27,8 @@ enum {
     MOGP_ERR_NOT_PD = 3,   /* factorisation failed (densegp_gpu.hpp:556-570, cholesky.py:219,281)  */
     MOGP_ERR_NOT_FIT = 4,  /* predict/get on an output whose hyperparameters are not set           */
     MOGP_ERR_NCCL = 5,
-    MOGP_ERR_NOMEM = 6
+    MOGP_ERR_NOMEM = 6,
+    MOGP_ERR_FPE = 7       /* infinite squared distance in the kernel (Kernel.py:482-483 raises FloatingPointError) */
 };
 
 /* mogp_gpu/src/types.hpp:29-33 -- the numeric values are part of the reference's Python contract
@@ -142,8 +143,9 @@ int mogp_kstar_dot(mogp_handle* h, const double* Xs, int64_t m, const double* ve
 /* accumulated device time per phase in ms since the last call with reset != 0:
  * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),
  *              predict host wall up to the last kernel's completion, predict result copy-out host wall;
- * out[11..14] = int8 path of the predict TRSM (inside predict_trsm): slicing L into planes (ms), unused (0), the
- *               persistent integer TRSM kernel (ms), block rows solved by it */
+ * out[11..15] = int8 path of the predict TRSM (inside predict_trsm): slicing L into planes (ms), the FP64 solve of the
+ *               sampled test points for the a-posteriori accuracy check (ms), the persistent integer TRSM kernel (ms), block
+ *               rows solved by it, number of groups the check sent back to the FP64 kernel */
 int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset);
 
 /* NCCL plumbing (no reference equivalent: the reference is single-device, multioutputgp_gpu.hpp:183). */

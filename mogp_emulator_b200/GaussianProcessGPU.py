@@ -246,7 +246,14 @@ class GaussianProcessGPU(object):
         theta = libmogp.as_f64(theta).reshape(-1)
         if theta.shape != (self.n_params,):
             raise RuntimeError("bad shape for hyperparameters: expected %d values, got %d" % (self.n_params, theta.size))
-        quad, logdet, nug, status = self._handle.fit(0, theta)
+        try:
+            quad, logdet, nug, status = self._handle.fit(0, theta)
+        except FloatingPointError:
+            # infinite squared distance (calc_r2, Kernel.py:482-483): the emulator is left "not fit"
+            self._theta.unset_data()
+            self._logpost_data = None
+            self._meanfit = None
+            raise
         self.n_fit_calls = getattr(self, "n_fit_calls", 0) + 1
         self._meanfit = None
         if status[0] != libmogp.OK:

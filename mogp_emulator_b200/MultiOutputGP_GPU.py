@@ -217,7 +217,13 @@ class MultiOutputGP_GPU(object):
         if thetas.shape[1] != self.n_params[0]:
             raise RuntimeError("bad shape for hyperparameters")
         if self._handle is not None:
-            quad, logdet, nug, status = self._handle.fit(0, thetas[self._lo:self._hi])
+            try:
+                quad, logdet, nug, status = self._handle.fit(0, thetas[self._lo:self._hi])
+            except FloatingPointError:
+                # infinite squared distance (calc_r2, Kernel.py:482-483): the call's emulators are left "not fit"
+                for i in range(self._lo, self._hi):
+                    self._record(i, None, 0.0, 0.0, 0.0, libmogp.ERR_FPE)
+                raise
             for k, i in enumerate(range(self._lo, self._hi)):
                 self._record(i, thetas[i], quad[k], logdet[k], nug[k], status[k])
             ok = [k for k in range(self._hi - self._lo) if status[k] == libmogp.OK]
@@ -246,7 +252,11 @@ class MultiOutputGP_GPU(object):
         if theta.shape[0] != self.n_params[index]:
             raise RuntimeError("bad shape for hyperparameters")
         if self._lo <= index < self._hi:
-            quad, logdet, nug, status = self._handle.fit(index - self._lo, theta)
+            try:
+                quad, logdet, nug, status = self._handle.fit(index - self._lo, theta)
+            except FloatingPointError:
+                self._record(index, None, 0.0, 0.0, 0.0, libmogp.ERR_FPE)
+                raise
             self._record(index, theta, quad[0], logdet[0], nug[0], status[0])
             if status[0] == libmogp.OK:
                 self._apply_mean([index], quad, logdet)
@@ -279,7 +289,12 @@ class MultiOutputGP_GPU(object):
             if not self._lo <= i < self._hi:
                 raise RuntimeError("emulator %d is not held by this rank" % i)
         local = [i - self._lo for i in indices]
-        quad, logdet, nug, status = self._handle.fit_list(local, thetas)
+        try:
+            quad, logdet, nug, status = self._handle.fit_list(local, thetas)
+        except FloatingPointError:
+            for i in indices:
+                self._record(i, None, 0.0, 0.0, 0.0, libmogp.ERR_FPE)
+            raise
         ok = []
         for k, i in enumerate(indices):
             self._record(i, thetas[k], quad[k], logdet[k], nug[k], status[k])

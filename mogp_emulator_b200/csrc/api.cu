@@ -100,7 +100,7 @@ using namespace mogp;
 constexpr int MAXM = 32;  // mean-function vectors per output (grad_max_mean())
 constexpr int I8_DEFAULT_PLANES = 7;   // default of MOGP_TRSM_I8 (see mogp_create)
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H,
-       T_I8_PREP, T_I8_KT, T_I8_ROWS, T_I8_NROWS, T_COUNT };
+       T_I8_PREP, T_I8_CHECK, T_I8_ROWS, T_I8_NROWS, T_I8_NFALLBACK, T_COUNT };
 
 struct mogp_handle {
     int device = 0, n_sms = 148;
@@ -128,7 +128,12 @@ struct mogp_handle {
     double* Vq = nullptr;                          // (bytes; typed double for grow())
     size_t Vq_cap = 0;
     std::vector<char> lq_valid;
+    std::vector<char> i8_bad;                      // output failed the a-posteriori accuracy check since its last fit: FP64 path
     int use_i8 = 0;                                // planes per operand of the tcgen05 path (6 or 7), 0 = FP64 DMMA path only
+    int i8_check = 1;                              // MOGP_I8_CHECK=0 skips the a-posteriori check (diagnostic: to time it)
+    // a-posteriori check of the int8 path: sampled K* rows, their FP64 variances, ticket words / norms of that solve, ratios
+    double *chk_W = nullptr, *chk_var = nullptr, *chk_sync = nullptr, *chk_norm = nullptr, *chk_ratio = nullptr, *h_chk_ratio = nullptr;
+    size_t chk_W_cap = 0, chk_var_cap = 0, chk_sync_cap = 0, chk_norm_cap = 0, chk_ratio_cap = 0, h_chk_ratio_cap = 0;
     size_t csync_cap = 0;
     // analytic mean function (set by the host front-end after a fit, cleared by every fit of that output)
     double* U = nullptr;                           // [E][MAXM][n_pad]: u_q with K^-1 H A^-1 H^T K^-1 = sum_q u_q u_q^T
@@ -236,7 +241,7 @@ int mogp_destroy(mogp_handle* h) {
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
-                    h->sync, h->normacc, h->csync, h->U, h->aux, h->Lq, h->Vq, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
+                    h->sync, h->normacc, h->csync, h->U, h->aux, h->Lq, h->Vq, h->chk_W, h->chk_var, h->chk_sync, h->chk_norm, h->chk_ratio, h->h_chk_ratio, h->info, h->h_hyper, h->h_scal, h->h_res, h->h_XsT, h->h_info, h->h_grad};
     for (auto p : bufs) pool_free(p);
     cudaGetLastError();
     delete h;
@@ -298,6 +303,11 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     h->fitted.assign(n_out, 0);
     h->n_u.assign(n_out, 0);
     h->lq_valid.assign(n_out, 0);
+    h->i8_bad.assign(n_out, 0);
+    {
+        const char* e = getenv("MOGP_I8_CHECK");
+        h->i8_check = (e && e[0] == '0') ? 0 : 1;
+    }
     {
         // MOGP_TRSM_I8 = 0: FP64 DMMA path only; 6 / 7: planes per operand of the int8 tcgen05 path
         const char* e = getenv("MOGP_TRSM_I8");
@@ -345,10 +355,10 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
     CREATE_ALLOC(h->z, double, sizeof(double) * n_out * np, device);
     CREATE_ALLOC(h->hyper, double, sizeof(double) * n_out * (d + 2), device);
     CREATE_ALLOC(h->scal, double, sizeof(double) * n_out * 2, device);
-    CREATE_ALLOC(h->info, int, sizeof(int) * n_out, device);
+    CREATE_ALLOC(h->info, int, sizeof(int) * (n_out + 1), device);      // [n_out] = infinite-distance flag of the kernel-matrix kernels
     CREATE_ALLOC(h->h_hyper, double, sizeof(double) * n_out * (d + 2), -1);
     CREATE_ALLOC(h->h_scal, double, sizeof(double) * n_out * 2, -1);
-    CREATE_ALLOC(h->h_info, int, sizeof(int) * n_out, -1);
+    CREATE_ALLOC(h->h_info, int, sizeof(int) * (n_out + 1), -1);
 #undef CREATE_ALLOC
     tc.mark("allocations");
     {
@@ -397,8 +407,9 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
             API_CUDA(cudaMemsetAsync(h->info + og[i], 0, sizeof(int), h->main));
             API_CUDA(cudaMemsetAsync(h->scal + 2 * og[i], 0, 2 * sizeof(double), h->main));
         }
+        API_CUDA(cudaMemsetAsync(h->info + h->E, 0, sizeof(int), h->main));
         API_CUDA(cudaEventRecord(h->ev_a, h->main));
-        if (kmat_sym(h->tmXT, h->kernel, h->n, np, h->d, h->hyper, og, cnt, 1, h->A, np, h->main)) {
+        if (kmat_sym(h->tmXT, h->kernel, h->n, np, h->d, h->hyper, og, cnt, 1, h->A, np, h->main, h->info + h->E)) {
             set_error("kmat launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return MOGP_ERR_CUDA;
         }
@@ -423,7 +434,12 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
             API_CUDA(cudaMemcpyAsync(h->h_scal + 2 * og[i], h->scal + 2 * og[i], 2 * sizeof(double), cudaMemcpyDeviceToHost,
                                      h->main));
         }
+        API_CUDA(cudaMemcpyAsync(h->h_info + h->E, h->info + h->E, sizeof(int), cudaMemcpyDeviceToHost, h->main));
         API_CUDA(cudaStreamSynchronize(h->main));
+        if (h->h_info[h->E]) {
+            set_error("Inf enountered in kernel distance computation");      // (sic) the reference's message, Kernel.py:483
+            return MOGP_ERR_FPE;
+        }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
         h->timings[T_KMAT] += ms;
@@ -488,6 +504,7 @@ int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const doubl
         h->fitted[o] = 0;
         h->n_u[o] = 0;
         h->lq_valid[o] = 0;
+        h->i8_bad[o] = 0;
         todo[i] = o;
         pos[o] = i;
     }
@@ -608,26 +625,25 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 set_error("tensor map (XsT) failed");
                 return MOGP_ERR_CUDA;
             }
+            API_CUDA(cudaMemsetAsync(h->info + h->E, 0, sizeof(int), h->main));
             API_CUDA(cudaEventRecord(h->ev_a, h->main));
             if (kmat_cross(tmXsT, h->tmXT, h->kernel, h->n, np, w_stride, d, outs, cnt, h->hyper, h->W, w_stride, want_var,
-                           h->alpha, np, h->part, h->main) ||
+                           h->alpha, np, h->part, h->main, h->info + h->E) ||
                 mean_reduce(h->part, outs, cnt, n_tiles, w_stride, mc, h->res + m0, 2 * m, h->main)) {
                 set_error("kstar launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return MOGP_ERR_CUDA;
             }
             API_CUDA(cudaEventRecord(h->ev_b, h->main));
-            // many right-hand sides (every block row keeps >= 2 tiles per SM busy): the int8 / tcgen05 path
+            // many right-hand sides (at least one panel chain per SM): the int8 / tcgen05 path.  There is no a-priori accuracy
+            // gate: worst-case bounds of the fixed-point error (n 2^(2 es - 7 S) amplified by ||L^-1||) are orders of magnitude
+            // above what is observed, so every call is checked a posteriori instead -- I8_NCHECK test points per output are also
+            // solved by the FP64 kernel and must agree to 1 % of the parity bar; an output that fails sends its group back to the
+            // FP64 path now and until it is fitted again.
             int i8_prep_launches = 0;
             bool i8 = want_var && h->use_i8 && n_tiles >= 2 &&
-                      (int64_t)cnt * ((mc + i8_panel_width() - 1) / i8_panel_width()) >= 2 * (int64_t)h->n_sms;
-            // the fixed-point scheme resolves V to 2^-50 of sqrt(sigma2), amplified by ||inv(L_ii)||; the parity bar on the
-            // variance is relative to the nugget (atol 1e-4 nugget), so emulators with a (relatively) small or zero nugget keep the
-            // FP64 DMMA path.  At nugget = 1e-7 sigma2 the exact emulation of this arithmetic (oracle/i8_emulation.py) stays 100 x
-            // inside the bar on smooth low-dimensional kernels (cond(K) ~ 5e9); at 1e-9 sigma2 it would exceed it.
-            for (int k = 0; k < cnt && i8; k++) {
-                const double* hy = h->h_hyper + (size_t)outs[k] * (d + 2);
-                if (!(hy[d + 1] >= 1.0e-7 * hy[d])) i8 = false;
-            }
+                      (int64_t)cnt * ((mc + i8_panel_width() - 1) / i8_panel_width()) >= (int64_t)h->n_sms;
+            for (int k = 0; k < cnt && i8; k++)
+                if (h->i8_bad[outs[k]]) i8 = false;
             if (i8) {
                 // planes of L (all outputs of the handle, allocated once) and of V (this call); if the device cannot hold them the
                 // call stays on the FP64 path
@@ -674,6 +690,29 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                         i8_prep_launches = 1;
                     }
                     API_CUDA(cudaEventRecord(h->ev_e, h->main));
+                    const int npt = i8_check_points();
+                    const TrsmPlan cplan{npt, 1};
+                    if (h->i8_check) {
+                        // FP64 reference variances of the sampled test points (a copy of their K* rows: the FP64 kernel solves in place)
+                        CUtensorMap tmWc;
+                        if ((rc = grow(&h->chk_W, &h->chk_W_cap, sizeof(double) * (size_t)cnt * npt * np, h->device))) return rc;
+                        if ((rc = grow(&h->chk_var, &h->chk_var_cap, sizeof(double) * (size_t)h->E * npt, h->device))) return rc;
+                        if ((rc = grow(&h->chk_sync, &h->chk_sync_cap, predict_sync_bytes(cplan, cnt, n_tiles), h->device))) return rc;
+                        if ((rc = grow(&h->chk_norm, &h->chk_norm_cap, sizeof(double) * (size_t)cnt * npt, h->device))) return rc;
+                        if ((rc = grow(&h->chk_ratio, &h->chk_ratio_cap, sizeof(double) * MAXG, h->device))) return rc;
+                        if ((rc = grow(&h->h_chk_ratio, &h->h_chk_ratio_cap, sizeof(double) * MAXG, -1))) return rc;
+                        if (make_kblocked_tmap(&tmWc, h->chk_W, (int64_t)cnt * npt, np, npt)) {
+                            set_error("tensor map (check workspace) failed");
+                            return MOGP_ERR_CUDA;
+                        }
+                        if (i8_check_gather(outs, cnt, h->W, w_stride, np, mc, h->chk_W, h->main) ||
+                            predict_trsm(cplan, outs, cnt, h->maps.a128, h->maps.d128, tmWc, h->chk_W, npt, h->hyper, d, include_nugget, np,
+                                         npt, h->chk_var, npt, 0, (int*)h->chk_sync, h->chk_norm, h->n_sms, h->main, 0,
+                                         want_var == 2 ? 1 : 0)) {
+                            set_error("i8 check launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                            return MOGP_ERR_CUDA;
+                        }
+                    }
                     API_CUDA(cudaEventRecord(h->ev_f, h->main));
                     // the integer forward substitution with its FP64 epilogue (K* in W is only read)
                     if (i8_trsm(S8, outs, exps.data(), cnt, plan.panels, h->Lq, (int64_t)lq_stride, (int8_t*)h->Vq, h->maps.d128, tmW, h->W,
@@ -681,6 +720,13 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                                 h->normacc, (int*)h->sync, h->n_sms, h->main)) {
                         set_error("i8 predict launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                         return MOGP_ERR_CUDA;
+                    }
+                    if (h->i8_check) {
+                        if (i8_check_compare(outs, cnt, mc, h->res + m + m0, 2 * m, h->chk_var, h->hyper, d, h->chk_ratio, h->main)) {
+                            set_error("i8 check launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                            return MOGP_ERR_CUDA;
+                        }
+                        API_CUDA(cudaMemcpyAsync(h->h_chk_ratio, h->chk_ratio, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->main));
                     }
                 } else if (predict_trsm(plan, outs, cnt, h->maps.a128, h->maps.d128, tmW, h->W, w_stride, h->hyper, d,
                                  include_nugget, np, mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms,
@@ -693,7 +739,12 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
             API_CUDA(cudaEventRecord(h->ev_c, h->main));
             h->timings[T_NLAUNCH] += 2 + (want_var ? 1 : 0);
             // per-phase device times (the sync also protects the reused workspace and the pinned XsT buffer)
+            API_CUDA(cudaMemcpyAsync(h->h_info + h->E, h->info + h->E, sizeof(int), cudaMemcpyDeviceToHost, h->main));
             API_CUDA(cudaStreamSynchronize(h->main));
+            if (h->h_info[h->E]) {
+                set_error("Inf enountered in kernel distance computation");
+                return MOGP_ERR_FPE;
+            }
             float ms1 = 0.f, ms2 = 0.f;
             cudaEventElapsedTime(&ms1, h->ev_a, h->ev_b);
             cudaEventElapsedTime(&ms2, h->ev_b, h->ev_c);
@@ -705,10 +756,36 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                 cudaEventElapsedTime(&b, h->ev_e, h->ev_f);
                 cudaEventElapsedTime(&c, h->ev_f, h->ev_c);
                 h->timings[T_I8_PREP] += a;
-                h->timings[T_I8_KT] += b;
+                h->timings[T_I8_CHECK] += b;
                 h->timings[T_I8_ROWS] += c;
                 h->timings[T_I8_NROWS] += n_tiles;          // block rows solved by the (single) int8 launch
-                h->timings[T_NLAUNCH] += i8_prep_launches;
+                h->timings[T_NLAUNCH] += i8_prep_launches + (h->i8_check ? 3 : 0);
+                bool failed = false;
+                for (int k = 0; k < cnt && h->i8_check; k++)
+                    if (!(h->h_chk_ratio[k] <= 1.0)) {
+                        h->i8_bad[outs[k]] = 1;
+                        failed = true;
+                    }
+                if (failed) {
+                    // the fixed-point solve missed the bar on a sampled test point: redo the group in FP64 (K* in W is intact)
+                    if (trace_on()) fprintf(stderr, "[mogp trace] int8 predict path failed its accuracy check: group redone in FP64\n");
+                    const TrsmPlan fplan = predict_plan(mc, cnt, (int)np, h->n_sms);
+                    CUtensorMap tmWf;
+                    if (make_kblocked_tmap(&tmWf, h->W, (int64_t)cnt * w_stride, np, fplan.nw)) {
+                        set_error("tensor map (W) failed");
+                        return MOGP_ERR_CUDA;
+                    }
+                    if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(fplan, cnt, n_tiles), h->device))) return rc;
+                    if (predict_trsm(fplan, outs, cnt, h->maps.a128, h->maps.d128, tmWf, h->W, w_stride, h->hyper, d, include_nugget, np,
+                                     mc, h->res + m + m0, 2 * m, 0, (int*)h->sync, h->normacc, h->n_sms, h->main, 0,
+                                     want_var == 2 ? 1 : 0)) {
+                        set_error("predict_trsm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                        return MOGP_ERR_CUDA;
+                    }
+                    API_CUDA(cudaStreamSynchronize(h->main));
+                    h->timings[T_I8_NFALLBACK] += 1;
+                    h->timings[T_NLAUNCH] += 1;
+                }
             }
         }
     }

@@ -30,10 +30,11 @@ int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, c
 int kmat_init();
 int kmat_dbox(int d);
 int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, const int* outs,
-             int count, int add_nugget, double* A_slab, int64_t slab_rows_per_output, cudaStream_t st);
+             int count, int add_nugget, double* A_slab, int64_t slab_rows_per_output, cudaStream_t st, int* inf_flag = nullptr);
 int kmat_cross(const CUtensorMap& tmXsT, const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int64_t m_pad,
                int d, const int* outs, int count, const double* hyper, double* W_slab, int64_t w_stride, int store,
-               const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st);
+               const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st, int* inf_flag = nullptr);
+// inf_flag (device, optional): set to 1 when any squared distance is +inf -- the reference raises FloatingPointError there
 int mean_reduce(const double* part, const int* outs, int count, int n_tiles, int64_t m_pad, int64_t m, double* mean,
                 int64_t mean_stride, cudaStream_t st);
 
@@ -80,6 +81,15 @@ int i8_trsm(int S, const int* outs, const int* exps, int count, int panels, cons
             const CUtensorMap& tmD, const CUtensorMap& tmW, const double* W, int64_t w_stride, const double* hyper, int d,
             int include_nugget, int no_clip, int64_t n_pad, int64_t m, double* var, int64_t var_stride, double* normacc, int* sync,
             int n_sms, cudaStream_t st);
+
+// a-posteriori accuracy check of the int8 path: i8_check_points() test points per output (spread evenly over the m of the
+// call) are gathered from K* into Wc [count][points][n_pad] for an FP64 solve (predict_trsm), then compared:
+// ratio[k] = max over the samples of |var - var_ref| / (1 % of the parity bar + FP64 rounding floor); > 1 fails
+int i8_check_points();
+int i8_check_gather(const int* outs, int count, const double* W, int64_t w_stride, int64_t n_pad, int64_t m, double* Wc,
+                    cudaStream_t st);
+int i8_check_compare(const int* outs, int count, int64_t m, const double* var, int64_t var_stride, const double* var_ref,
+                     const double* hyper, int d, double* ratio, cudaStream_t st);
 
 // ---- grad.cu ----
 int grad_init();

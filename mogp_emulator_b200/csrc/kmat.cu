@@ -44,6 +44,7 @@ struct KmatParams {
     int outs[MAXG];         // global output index handled by blockIdx.z (hyper/alpha rows)
     int store;              // CROSS: write the matrix (0 when only the mean is wanted)
     int add_nugget;         // SYM: add hyper[d+1] (the nugget) on the diagonal
+    int* inf_flag;          // set to 1 when a squared distance is +inf (Kernel.py:482-483 raises FloatingPointError); may be null
 };
 
 template <int KT, int CROSS>
@@ -113,6 +114,17 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
         __syncthreads();  // single smem buffer: everyone done before the next box lands
     }
 
+    if (p.inf_flag) {
+        // the reference refuses infinite distances (calc_r2, Kernel.py:482-483); integer test of the bit pattern: the kernel
+        // is bound by the FP64 pipe
+        bool inf = false;
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 8; b++)
+                inf |= (__double2hiint(r2[a][b]) == 0x7ff00000) && (__double2loint(r2[a][b]) == 0);
+        if (inf) atomicOr(p.inf_flag, 1);
+    }
     const double sigma2 = hyp[p.d];
     if (!CROSS) {
         const double nugget = p.add_nugget ? hyp[p.d + 1] : 0.0;
@@ -176,11 +188,11 @@ int kmat_dbox(int d) { return d < DCH ? d : DCH; }
 // K + nugget*I (lower 128x128 tiles) of `count` outputs in one launch.  Output k uses hyper row outs[k] and is
 // written at slab rows slab_idx[k]*n_pad.. of A_slab (slab_idx == nullptr: same as outs).
 int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int d, const double* hyper, const int* outs,
-             int count, int add_nugget, double* A_slab, int64_t slab_rows_per_output, cudaStream_t st) {
+             int count, int add_nugget, double* A_slab, int64_t slab_rows_per_output, cudaStream_t st, int* inf_flag) {
     if (count < 1 || count > MAXG) return 1;
     KmatParams p{};
     p.n = n; p.n_pad = n_pad; p.rows_pad = n_pad; p.d = d; p.dbox = kmat_dbox(d); p.hyper_stride = d + 2;
-    p.hyper = hyper; p.out = A_slab; p.out_stride = slab_rows_per_output; p.add_nugget = add_nugget;
+    p.hyper = hyper; p.out = A_slab; p.out_stride = slab_rows_per_output; p.add_nugget = add_nugget; p.inf_flag = inf_flag;
     for (int i = 0; i < count; i++) p.outs[i] = outs[i];
     const int T = (int)(n_pad / 128);
     const int tiles = T * (T + 1) / 2;
@@ -194,8 +206,9 @@ int kmat_sym(const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int 
 
 int kmat_cross(const CUtensorMap& tmXsT, const CUtensorMap& tmXT, int kernel, int64_t n, int64_t n_pad, int64_t m_pad,
                int d, const int* outs, int count, const double* hyper, double* W_slab, int64_t w_stride, int store,
-               const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st) {
+               const double* alpha, int64_t alpha_stride, double* part, cudaStream_t st, int* inf_flag) {
     KmatParams p{};
+    p.inf_flag = inf_flag;
     p.n = n; p.n_pad = n_pad; p.rows_pad = m_pad; p.d = d; p.dbox = kmat_dbox(d); p.hyper_stride = d + 2;
     p.hyper = hyper; p.out = W_slab; p.out_stride = w_stride; p.alpha = alpha; p.alpha_stride = alpha_stride;
     p.part = part; p.store = store;

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmogp_b200.so")
 
-OK, ERR_CUDA, ERR_ARG, ERR_NOT_PD, ERR_NOT_FIT, ERR_NCCL, ERR_NOMEM = range(7)
+OK, ERR_CUDA, ERR_ARG, ERR_NOT_PD, ERR_NOT_FIT, ERR_NCCL, ERR_NOMEM, ERR_FPE = range(8)
 GET_K, GET_L, GET_ALPHA, GET_KINV = range(4)
 
 
@@ -144,6 +144,8 @@ def check(status, what=""):
         raise MemoryError(msg)
     if status == ERR_NOT_PD:
         raise NotPositiveDefiniteError(msg)
+    if status == ERR_FPE:
+        raise FloatingPointError(last_error())      # calc_r2, Kernel.py:482-483
     raise RuntimeError(msg)
 
 
@@ -330,10 +332,11 @@ class Handle(object):
         return out
 
     def timings(self, reset=False):
-        out = np.zeros(15)
-        check(_lib.mogp_timings(self._h, dptr(out), 15, int(reset)))
+        out = np.zeros(16)
+        check(_lib.mogp_timings(self._h, dptr(out), 16, int(reset)))
         keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms",
-                "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_ktilde_ms", "i8_rows_ms", "i8_block_rows"]
+                "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_check_ms", "i8_rows_ms", "i8_block_rows",
+                "i8_fallbacks"]
         return dict(zip(keys, out.tolist()))
 
 

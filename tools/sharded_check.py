@@ -33,4 +33,30 @@ except ValueError:
 r2 = mo.predict(Xs, deriv=False, allow_not_fit=True)
 assert np.all(np.isnan(r2.mean[E - 1])) and np.array_equal(r2.mean[:E - 1], r1.mean[:E - 1])
 assert mo.get_indices_not_fit() == [E - 1]
+mo.close()
+
+# derivatives and a mean function are gathered too (the reference returns deriv (E, m, D) by default,
+# MultiOutputGP_GPU.py:185-297); again against a single-GPU emulator on the same inputs
+Ym = Y + 1.5 - 0.7 * X[:, 0]
+mm = MultiOutputGP_GPU(X, Ym, mean="x[0]", nugget=1e-6, device=local_rank, comm=comm)
+mm.fit(thetas)
+rm = mm.predict(Xs)                       # deriv=True, the default
+om = MultiOutputGP_GPU(X, Ym, mean="x[0]", nugget=1e-6, device=local_rank)
+om.fit(thetas)
+r1m = om.predict(Xs)
+assert rm.deriv.shape == (E, 77, 3)
+assert np.array_equal(rm.mean, r1m.mean) and np.array_equal(rm.unc, r1m.unc) and np.array_equal(rm.deriv, r1m.deriv), "sharded (mean function, deriv) != single"
+assert mm.get_indices_not_fit() == [] and mm.get_indices_fit() == list(range(E))      # status exchange at the end of fit
+mm.close()
+om.close()
+
+# more ranks than outputs: the ranks without outputs still join the collective
+if world > 1:
+    Es = world - 1
+    ms = MultiOutputGP_GPU(X, Y[:Es], nugget=1e-6, device=local_rank, comm=comm)
+    ms.fit(thetas[:Es])
+    rs = ms.predict(Xs, deriv=False)
+    assert rs.mean.shape == (Es, 77) and np.array_equal(rs.mean, r1.mean[:Es]) and np.array_equal(rs.unc, r1.unc[:Es]), "empty rank"
+    ms.close()
+one.close()
 print("rank %d/%d: sharded predict OK (local outputs %s)" % (rank, world, mo.local_range))
