@@ -230,6 +230,14 @@ class GaussianProcessGPU(object):
             return None
         return self._logpost_data - self.priors.logp(self._theta)
 
+    @property
+    def invQ(self):
+        """(K + nugget I)^-1 as a dense (n, n) array -- ``DenseGP_GPU::get_invQ`` of the reference's native class
+        (mogp_gpu/src/densegp_gpu.hpp:629).  Computed on demand from the Cholesky factor; nothing else in this library forms it."""
+        if not self._theta.data_has_been_set():
+            return None
+        return self._handle.get(0, libmogp.GET_KINV)
+
     def get_K_matrix(self):
         """sigma^2 * k(X, X) without the nugget (GaussianProcess.get_K_matrix, GaussianProcess.py:545-558)."""
         if not self._theta.data_has_been_set():

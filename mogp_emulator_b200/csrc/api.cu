@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges are no-ops unless a profiler injects its library
+
 #include "../../include/mogp_b200.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -91,6 +93,15 @@ struct TraceClock {
         fprintf(stderr, "[mogp trace] %s: %s +%.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     }
+};
+
+// NVTX range over an API call or one of its phases (the reference has no tracing of its own; nsys / ncu --nvtx attribute the
+// kernels of a fit or predict to these names)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 }  // namespace mogp
@@ -400,6 +411,7 @@ int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out) {
 static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
     const int64_t np = h->n_pad;
     const int T = (int)(np / NB);
+    NvtxRange nvtx_range("mogp fit attempt: kmat + cholesky + solves");
     for (int g0 = 0; g0 < count; g0 += MAXG) {
         const int cnt = std::min(MAXG, count - g0);
         const int* og = outs + g0;
@@ -487,6 +499,7 @@ int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const doubl
         return MOGP_ERR_ARG;
     }
     API_CUDA(cudaSetDevice(h->device));
+    NvtxRange nvtx_range("mogp_fit");
     const int hs = d + 2;
     std::vector<double> nug(count, 0.0);
     std::vector<int> todo(count);
@@ -572,6 +585,7 @@ int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas,
 // Runs predict for all fitted outputs; results land in h->res as [E][2][m] (mean row, variance row),
 // rows of unfitted outputs are NaN.  Enqueued on h->main, not synchronised.
 static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_var, int include_nugget) {
+    NvtxRange nvtx_range("mogp predict: kstar + mean + trsm");
     const int64_t np = h->n_pad;
     const int d = h->d;
     std::vector<int> fit_idx;
@@ -1092,6 +1106,44 @@ int mogp_get(mogp_handle* h, int32_t idx, int32_t which, double* out) {
             for (int64_t j = i + 1; j < n; j++) out[i * n + j] = out[j * n + i];
         return MOGP_OK;
     }
+    if (which == MOGP_GET_KINV) {
+        // K^-1 = (L^-1)^T L^-1 (DenseGP_GPU::get_invQ, densegp_gpu.hpp:629, the reference's stored explicit inverse): L^-1 by the
+        // dataflow TRSM on an identity right-hand side (as for the gradient), then one DMMA SYRK.  Nothing in the library keeps
+        // or uses an explicit inverse; this getter exists for the reference's interface.
+        const int T = (int)(np / NB);
+        int rc;
+        if ((rc = grow(&h->G, &h->G_cap, sizeof(double) * 2 * (size_t)np * np, h->device))) return rc;
+        TrsmPlan plan = predict_plan_square(np, h->n_sms);
+        if ((rc = grow(&h->sync, &h->sync_cap, predict_sync_bytes(plan, 1, T), h->device))) return rc;
+        double* Wt = h->G;
+        double* C = h->G + (size_t)np * np;
+        CUtensorMap tmW, tmW128, tmW64;
+        if (make_kblocked_tmap(&tmW, Wt, np, np, plan.nw) || make_kblocked_tmap(&tmW128, Wt, np, np, 128) ||
+            make_kblocked_tmap(&tmW64, Wt, np, np, 64)) {
+            set_error("tensor map (inverse workspace) failed");
+            return MOGP_ERR_CUDA;
+        }
+        const int one[1] = {idx};
+        API_CUDA(cudaMemsetAsync(C, 0, sizeof(double) * (size_t)np * np, h->main));
+        if (grad_set_identity(Wt, np, h->main) ||
+            predict_trsm(plan, one, 1, h->maps.a128, h->maps.d128, tmW, Wt, np, h->hyper, h->d, 0, np, np, nullptr, 0, 1,
+                         (int*)h->sync, nullptr, h->n_sms, h->main) ||
+            cov_syrk_sub(tmW128, tmW64, 0, np, np, C, h->main)) {
+            set_error("get K^-1 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MOGP_ERR_CUDA;
+        }
+        API_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n, C, sizeof(double) * np, sizeof(double) * n, n, cudaMemcpyDeviceToHost,
+                                   h->main));
+        API_CUDA(cudaStreamSynchronize(h->main));
+        h->timings[T_NLAUNCH] += 3;
+        for (int64_t i = 0; i < n; i++)
+            for (int64_t j = 0; j <= i; j++) {
+                const double v = -out[i * n + j];           // the SYRK subtracts from a zero matrix (lower tiles)
+                out[i * n + j] = v;
+                out[j * n + i] = v;
+            }
+        return MOGP_OK;
+    }
     set_error("mogp_get: selector %d not available", which);
     return MOGP_ERR_ARG;
 }
@@ -1116,6 +1168,7 @@ int mogp_logpost_grad_list(mogp_handle* h, const int32_t* idx, int32_t count, do
         return MOGP_ERR_ARG;
     }
     API_CUDA(cudaSetDevice(h->device));
+    NvtxRange nvtx_range("mogp_logpost_grad");
     const int64_t np = h->n_pad;
     const int T = (int)(np / NB);
     const size_t tiles = (size_t)T * (T + 1);
@@ -1346,6 +1399,7 @@ int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, in
     }
     const NcclApi* api = nccl_api();
     API_CUDA(cudaSetDevice(h->device));
+    NvtxRange nvtx_range("mogp_predict_allgather");
     int rc = predict_device(h, Xs, m, 1, include_nugget);
     if (rc) return rc;
     const size_t blk = (size_t)e_pad * 2 * m;  // doubles per rank; one extra row-pair block carries the status words

@@ -36,7 +36,7 @@ def test_bench_line_contract(monkeypatch, capsys, i8):
     monkeypatch.setattr(libmogp, "peak_i8_tops", lambda device=0, iters=0: (4500.0, 3000.0))
     for var in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(var, raising=False)
-    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", workload="c1", no_cpu=False, no_e2e=False)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", workload="c1", no_cpu=False, no_e2e=False, no_other=True)
     bench.run_b200(args, bench.WORKLOADS["c1"])
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",

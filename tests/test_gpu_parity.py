@@ -772,6 +772,69 @@ def test_full_size_c3_takes_the_int8_path(mogp, monkeypatch):
         assert_allclose(res.unc[o], rv, rtol=1e-4, atol=1e-4 * nugget)
 
 
+def test_integration_route_b_stub_against_reference_golden(mogp):
+    """INTEGRATION.md route B: the ctypes stand-in for the reference's pybind ``DenseGP_GPU`` is executed VERBATIM from the
+    document (only the library path is made absolute) and driven the way the reference front-end drives the native object
+    (GaussianProcessGPU.py:515-524, 582-629), against an output of the unmodified reference."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if "class DenseGP_GPU" in b]
+    assert len(stub) == 1
+    from mogp_emulator_b200 import libmogp
+    code = stub[0].replace('ctypes.CDLL("libmogp_b200.so")', "ctypes.CDLL(%r)" % libmogp.LIB_PATH)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md:route-B", "exec"), ns)
+    assert ns["have_compatible_device"]()
+    g = _load("sqexp_fixed_n150_d3")
+    X, y, Xs, theta = (np.ascontiguousarray(g[k], dtype=np.float64) for k in ("X", "y", "Xs", "theta"))
+    n, m = X.shape[0], Xs.shape[0]
+    dg = ns["DenseGP_GPU"](X, y.reshape(1, -1), 2000, None, ns["kernel_type"].SquaredExponential, ns["nugget_type"].fixed,
+                           float(g["nugget_in"]))
+    dg.fit(theta)
+    mean, var = np.zeros(m), np.zeros(m)
+    dg.predict_variance_batch(Xs, mean, var)
+    assert_allclose(mean, g["mean"], rtol=1e-6, atol=1e-9)
+    assert_allclose(var + float(g["nugget_in"]), g["var"], rtol=1e-4, atol=1e-4 * float(g["nugget_in"]))   # front-end adds the nugget (:613)
+    mean2 = np.zeros(m)
+    dg.predict_batch(Xs, mean2)
+    assert np.array_equal(mean2, mean)
+    L, K, a = np.zeros((n, n)), np.zeros((n, n)), np.zeros(n)
+    dg.get_cholesky_lower(L)
+    dg.get_K(K)
+    dg.get_invQt(a)
+    assert_allclose(K, g["K"], rtol=1e-13, atol=1e-300)
+    assert_allclose(L, g["L"], rtol=1e-7, atol=1e-9)
+    assert_allclose(a, g["Kinv_t"], rtol=1e-6, atol=1e-6 * np.abs(g["Kinv_t"]).max())
+    assert dg.get_nugget_size() == float(g["nugget_in"])
+    grad = np.zeros(theta.size)
+    dg.logpost_deriv(grad)
+    ref = orc.OracleGP(X, y, nugget=float(g["nugget_in"]), priors="weak")
+    ref.fit(theta)
+    assert_allclose(grad, ref.logpost_deriv(theta), rtol=1e-6, atol=1e-8)      # weak priors: the data term is the whole gradient
+    assert_allclose(dg.get_logpost(theta), ref.logposterior(theta), rtol=1e-9)
+    del dg
+
+
+def test_explicit_inverse_getter(mogp):
+    """MOGP_GET_KINV / ``invQ`` (DenseGP_GPU::get_invQ, densegp_gpu.hpp:629): (K + nugget I)^-1 against the oracle's factor,
+    at a size that is not a multiple of the tile (padding must not leak in)."""
+    X, Y, _ = orc.make_workload(333, 4, 1, 5, seed=44)
+    theta = np.array([0.3, 0.6, 0.9, 1.2, 0.2])
+    gp = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-4)
+    assert gp.invQ is None
+    gp.fit(theta)
+    Kinv = gp.invQ
+    ref = orc.OracleGP(X, Y[0], nugget=1e-4, priors="weak").fit(theta)
+    Kn = ref.get_K_matrix() + 1e-4 * np.eye(333)
+    assert_allclose(Kinv, Kinv.T, rtol=0, atol=0)
+    assert_allclose(Kinv @ Kn, np.eye(333), atol=1e-7)
+    assert_allclose(Kinv, np.linalg.inv(Kn), rtol=1e-6, atol=1e-6 * np.abs(Kinv).max())
+    assert_allclose(Kinv @ Y[0], gp.Kinv_t, rtol=1e-7, atol=1e-7 * np.abs(gp.Kinv_t).max())
+    gp.close()
+
+
 def test_infinite_distance_raises_floating_point_error(mogp):
     """calc_r2 refuses infinite squared distances (Kernel.py:482-483: FloatingPointError, which the MAP search skips as a
     failed restart, fitting.py:250-252); the device kernels flag them and the front-end raises the same exception."""
