@@ -118,8 +118,9 @@ struct mogp_handle {
     int64_t n = 0, n_pad = 0;
     int d = 0, E = 0, kernel = 0, nug_type = 0;
     double nug_fixed = 0.0;
-    cudaStream_t main = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr, ev_f = nullptr;
+    cudaStream_t main = nullptr, side = nullptr;   // side: the FP64 accuracy check of the int8 predict path runs beside the integer kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_d2 = nullptr, ev_e = nullptr, ev_f = nullptr;
     // device slabs
     double *XT = nullptr, *Y = nullptr, *A = nullptr, *Dinv = nullptr, *alpha = nullptr, *z = nullptr;
     double *hyper = nullptr, *scal = nullptr;  // scal: [E][2] = logdet, quad
@@ -248,7 +249,8 @@ int mogp_destroy(mogp_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->main) cudaStreamDestroy(h->main);
-    cudaEvent_t evs[6] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_e, h->ev_f};
+    if (h->side) cudaStreamDestroy(h->side);
+    cudaEvent_t evs[9] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_d2, h->ev_e, h->ev_f, h->ev_fork, h->ev_join};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     void* bufs[] = {h->XT, h->Y, h->A, h->Dinv, h->alpha, h->z, h->hyper, h->scal, h->XsT, h->W, h->part, h->res, h->G,
@@ -342,10 +344,14 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         }                                                                                            \
     } while (0)
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->main, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreate(&h->ev_a));
     CREATE_CUDA(cudaEventCreate(&h->ev_b));
     CREATE_CUDA(cudaEventCreate(&h->ev_c));
     CREATE_CUDA(cudaEventCreate(&h->ev_d));
+    CREATE_CUDA(cudaEventCreate(&h->ev_d2));
     CREATE_CUDA(cudaEventCreate(&h->ev_e));
     CREATE_CUDA(cudaEventCreate(&h->ev_f));
     tc.mark("streams + events");
@@ -508,7 +514,16 @@ int mogp_fit_list(mogp_handle* h, const int32_t* idx, int32_t count, const doubl
         const int o = idx[i];
         const double* th = thetas + (size_t)i * n_params;
         double* hy = h->h_hyper + (size_t)o * hs;
-        for (int k = 0; k < d; k++) hy[k] = exp(th[k]);       // CorrTransform: l = exp(-theta/2) <=> weight exp(theta)
+        for (int k = 0; k < d; k++) {
+            hy[k] = exp(th[k]);                               // CorrTransform: l = exp(-theta/2) <=> weight exp(theta)
+            if (std::isinf(hy[k])) {
+                // exp(theta) overflows: every squared distance between points that differ in this dimension is +inf and calc_r2
+                // raises (Kernel.py:482-483).  Caught here because the device kernels work with sqrt(exp(theta)) (inf - inf = NaN).
+                for (int q = 0; q < count; q++) h->fitted[idx[q]] = 0;
+                set_error("Inf enountered in kernel distance computation");
+                return MOGP_ERR_FPE;
+            }
+        }
         hy[d] = exp(th[d]);                                   // CovTransform
         if (h->nug_type == MOGP_NUG_FIT) nug[i] = exp(th[d + 1]);
         else if (h->nug_type == MOGP_NUG_FIXED) nug[i] = h->nug_fixed;
@@ -694,20 +709,15 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                             stale_exp.push_back(exps[k]);
                         }
                     }
-                    API_CUDA(cudaEventRecord(h->ev_d, h->main));
-                    if (!stale.empty()) {
-                        if (i8_slice_L(S8, h->A, np, stale.data(), stale_exp.data(), (int)stale.size(), h->Lq, (int64_t)lq_stride, h->main)) {
-                            set_error("i8_slice_L launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-                            return MOGP_ERR_CUDA;
-                        }
-                        for (int o : stale) h->lq_valid[o] = 1;
-                        i8_prep_launches = 1;
-                    }
-                    API_CUDA(cudaEventRecord(h->ev_e, h->main));
                     const int npt = i8_check_points();
                     const TrsmPlan cplan{npt, 1};
                     if (h->i8_check) {
-                        // FP64 reference variances of the sampled test points (a copy of their K* rows: the FP64 kernel solves in place)
+                        // FP64 reference variances of the sampled test points (a copy of their K* rows: the FP64 kernel solves in
+                        // place) on the side stream: launched first, they take one SM per output while the persistent integer kernel
+                        // starts on the others and its remaining CTAs join the ticket queue as those SMs free up
+                        API_CUDA(cudaEventRecord(h->ev_fork, h->main));
+                        API_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                        API_CUDA(cudaEventRecord(h->ev_e, h->side));
                         CUtensorMap tmWc;
                         if ((rc = grow(&h->chk_W, &h->chk_W_cap, sizeof(double) * (size_t)cnt * npt * np, h->device))) return rc;
                         if ((rc = grow(&h->chk_var, &h->chk_var_cap, sizeof(double) * (size_t)h->E * npt, h->device))) return rc;
@@ -719,15 +729,26 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                             set_error("tensor map (check workspace) failed");
                             return MOGP_ERR_CUDA;
                         }
-                        if (i8_check_gather(outs, cnt, h->W, w_stride, np, mc, h->chk_W, h->main) ||
+                        if (i8_check_gather(outs, cnt, h->W, w_stride, np, mc, h->chk_W, h->side) ||
                             predict_trsm(cplan, outs, cnt, h->maps.a128, h->maps.d128, tmWc, h->chk_W, npt, h->hyper, d, include_nugget, np,
-                                         npt, h->chk_var, npt, 0, (int*)h->chk_sync, h->chk_norm, h->n_sms, h->main, 0,
+                                         npt, h->chk_var, npt, 0, (int*)h->chk_sync, h->chk_norm, h->n_sms, h->side, 0,
                                          want_var == 2 ? 1 : 0)) {
                             set_error("i8 check launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                             return MOGP_ERR_CUDA;
                         }
+                        API_CUDA(cudaEventRecord(h->ev_f, h->side));
+                        API_CUDA(cudaEventRecord(h->ev_join, h->side));
                     }
-                    API_CUDA(cudaEventRecord(h->ev_f, h->main));
+                    API_CUDA(cudaEventRecord(h->ev_d, h->main));
+                    if (!stale.empty()) {
+                        if (i8_slice_L(S8, h->A, np, stale.data(), stale_exp.data(), (int)stale.size(), h->Lq, (int64_t)lq_stride, h->main)) {
+                            set_error("i8_slice_L launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                            return MOGP_ERR_CUDA;
+                        }
+                        for (int o : stale) h->lq_valid[o] = 1;
+                        i8_prep_launches = 1;
+                    }
+                    API_CUDA(cudaEventRecord(h->ev_d2, h->main));
                     // the integer forward substitution with its FP64 epilogue (K* in W is only read)
                     if (i8_trsm(S8, outs, exps.data(), cnt, plan.panels, h->Lq, (int64_t)lq_stride, (int8_t*)h->Vq, h->maps.d128, tmW, h->W,
                                 w_stride, h->hyper, d, include_nugget, want_var == 2 ? 1 : 0, np, mc, h->res + m + m0, 2 * m,
@@ -736,6 +757,7 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                         return MOGP_ERR_CUDA;
                     }
                     if (h->i8_check) {
+                        API_CUDA(cudaStreamWaitEvent(h->main, h->ev_join, 0));
                         if (i8_check_compare(outs, cnt, mc, h->res + m + m0, 2 * m, h->chk_var, h->hyper, d, h->chk_ratio, h->main)) {
                             set_error("i8 check launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                             return MOGP_ERR_CUDA;
@@ -766,9 +788,9 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
             h->timings[T_TRSM] += ms2;
             if (i8) {
                 float a = 0.f, b = 0.f, c = 0.f;
-                cudaEventElapsedTime(&a, h->ev_d, h->ev_e);
-                cudaEventElapsedTime(&b, h->ev_e, h->ev_f);
-                cudaEventElapsedTime(&c, h->ev_f, h->ev_c);
+                cudaEventElapsedTime(&a, h->ev_d, h->ev_d2);
+                if (h->i8_check) cudaEventElapsedTime(&b, h->ev_e, h->ev_f);      // on the side stream, concurrent with the integer kernel
+                cudaEventElapsedTime(&c, h->ev_d2, h->ev_c);
                 h->timings[T_I8_PREP] += a;
                 h->timings[T_I8_CHECK] += b;
                 h->timings[T_I8_ROWS] += c;

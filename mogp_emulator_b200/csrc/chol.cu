@@ -26,6 +26,16 @@
 
 namespace mogp {
 
+// -DCHOL_TRACE: globaltimer stamps of the diagonal (D) tiles for tools/chol_dtile_timeline.py; compiled out of the product
+#ifdef CHOL_TRACE
+constexpr int CH_TRACE_EV = 8, CH_TRACE_N = 4096;
+__device__ unsigned long long chol_trace_buf[CH_TRACE_N * CH_TRACE_EV];
+__device__ int chol_trace_count;
+#define CH_STAMP(slot, ev) do { if ((slot) >= 0 && (slot) < CH_TRACE_N) chol_trace_buf[(slot) * CH_TRACE_EV + (ev)] = globaltimer_ns(); } while (0)
+#else
+#define CH_STAMP(slot, ev) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // diagonal block: factor + invert, cooperatively by NTHR threads of one CTA (device function)
 // ------------------------------------------------------------------------------------------
@@ -44,6 +54,22 @@ struct Potf2Smem {
     int fail;
 };
 
+// pv = sqrt(d), ri = 1 / pv for a pivot d > 0.  FP64 latency is what bounds the diagonal tile (tools/chol_dtile_timeline.py:
+// sqrt() followed by 1.0 / pv cost ~800 cycles per pivot, 128 pivots per tile on the critical path of every block column), so
+// both come from ONE reciprocal-square-root seed: y = rsqrt(d), then the FMA-corrected square root (pv0 = d y,
+// pv = pv0 + (d - pv0^2) y/2: correctly rounded for a seed accurate to an ulp) and two residual corrections of the reciprocal
+// against that pv (r += r (1 - pv r)): the results of sqrt() and of the IEEE division up to rounding ties.
+__device__ __forceinline__ void sqrt_and_reciprocal(double d, double& pv, double& ri) {
+    const double y = rsqrt(d);
+    const double pv0 = d * y;
+    const double e = fma(-pv0, pv0, d);
+    pv = fma(e, 0.5 * y, pv0);
+    double r = y;
+    r = fma(fma(-pv, r, 1.0), r, r);
+    r = fma(fma(-pv, r, 1.0), r, r);
+    ri = r;
+}
+
 // (a1) of potf2_inv_block: Cholesky of the 16x16 diagonal sub-block at (j0, j0) by ONE warp.  Lane r (mod 16) owns
 // row j0+r in registers; pivots and multipliers travel by shuffle, so the 16-step dependency chain has no barrier.
 // Writes L11 back to sm.S and sm.Lr, the reciprocal pivots to sm.rd, or sets sm.fail (1-based failing column).
@@ -59,8 +85,8 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
         // also catches NaN (LAPACK: ajj <= 0 or isnan); warp-uniform.  No early exit: the loop stays fully
         // unrolled (register-resident a[]); what follows a failed pivot is never stored.
         if (fail == 0 && !(d > 0.0)) fail = j0 + j + 1;
-        const double pv = sqrt(d);
-        const double ri = 1.0 / pv;
+        double pv, ri;
+        sqrt_and_reciprocal(d, pv, ri);
         a[j] = (r == j) ? pv : a[j] * ri;   // LAPACK scales the column by the reciprocal pivot (entries above the diagonal are 0)
         if (lane == 0) sm.rd[j0 + j] = ri;
 #pragma unroll
@@ -89,6 +115,16 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
 // blocks of sm.S hold inv(L)'s diagonal blocks and its upper blocks (J, b) the off-diagonal blocks X_bJ, Lout (global, row stride ld) has received L with a zero upper part, and *logdet_add is
 // 2*sum(log L_ii) on thread 0.  On failure returns the 1-based index of the failing pivot (LAPACK info).
 // BAR_ALL: named barrier id for the NTHR participating threads.
+#ifdef CHOL_TRACE
+__device__ int chol_trace_cur[256];     // per SM: slot of the D tile in flight (trace build only)
+#define CH_STAMP_IN(ev) do { if (tid == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); CH_STAMP(chol_trace_cur[sm_ & 255], ev); } } while (0)
+__device__ unsigned long long chol_trace_buf2[CH_TRACE_N * 32];
+#define CH_STAMP2(cond, ev) do { if (cond) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); const int sl_ = chol_trace_cur[sm_ & 255]; if (sl_ >= 0 && sl_ < CH_TRACE_N) chol_trace_buf2[sl_ * 32 + (ev)] = globaltimer_ns(); } } while (0)
+#else
+#define CH_STAMP_IN(ev) do { } while (0)
+#define CH_STAMP2(cond, ev) do { } while (0)
+#endif
+
 template <int NTHR, int BAR_ALL>
 __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* __restrict__ Lout, int64_t ld,
                                                double* logdet_add) {
@@ -125,6 +161,20 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
         for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
         const int cmax = (r < c_hi) ? r : c_hi;
         int c = c_lo + q;
+        // eight dot products at a time: a dependent DFMA costs ~50 cycles on this chip, the chains of one dot are 16 long
+        for (; c + 7 * nq <= cmax; c += 8 * nq) {
+            double dd[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) dd[u] = 0.0;
+            const double* s0 = sm.S + c * PS + j0;
+#pragma unroll
+            for (int kk = 0; kk < SB; kk++)
+#pragma unroll
+                for (int u = 0; u < 8; u++) dd[u] = fma(a[kk], s0[u * nq * PS + kk], dd[u]);
+            double* dst = sm.S + r * PS + c;
+#pragma unroll
+            for (int u = 0; u < 8; u++) dst[u * nq] -= dd[u];
+        }
         for (; c + 3 * nq <= cmax; c += 4 * nq) {
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
             const double* s0 = sm.S + c * PS + j0;
@@ -149,11 +199,14 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
         }
     };
 
+    CH_STAMP2(tid == 0, 0);
     if (tid < 32) potf2_diag16(sm, 0, tid);
+    CH_STAMP2(tid == 0, 1);
     named_bar_sync(BAR_ALL, NTHR);
     if (sm.fail) return sm.fail;
     rows_below(0);
     named_bar_sync(BAR_ALL, NTHR);
+    CH_STAMP2(tid == 0, 2);
     for (int s = 0; s + 1 < NB / SB; s++) {
         const int j0 = s * SB;
         const int nrow = NB - j0 - SB;   // rows below panel s
@@ -164,8 +217,10 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
             if (t < nrow) update_row(j0, j0 + SB + t, j0 + SB, j0 + 2 * SB - 1, q, NQ1);
         }
         named_bar_sync(BAR_ALL, NTHR);
+        CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 3 : 10);      // after b1
         if (tid < 32) {
             potf2_diag16(sm, j0 + SB, tid);                         // (a1) of panel s+1
+            CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 4 : 11);  // a1 done
         } else {
             // (b2) the remaining columns (>= j0+32); rows folded in pairs (short + long) so that every thread gets
             // the same number of columns
@@ -177,13 +232,17 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
                 update_row(j0, j0 + 2 * SB + t, j0 + 2 * SB, NB - 1, q, NQ2);
                 update_row(j0, NB - 1 - t, j0 + 2 * SB, NB - 1, q, NQ2);
             }
+            CH_STAMP2(tid == 32 && (s == 0 || s == 3), s == 0 ? 5 : 12); // b2 done (one of its warps)
         }
         named_bar_sync(BAR_ALL, NTHR);
+        CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 6 : 13);      // after the a1 / b2 barrier
         if (sm.fail) return sm.fail;
         rows_below(j0 + SB);                                        // (a2) of panel s+1
+        CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 7 : 14);      // a2 done (this thread)
         named_bar_sync(BAR_ALL, NTHR);
     }
     if (sm.fail) return sm.fail;
+    CH_STAMP_IN(2);
 
     // ---- write L_kk back (upper part of the block zeroed) and accumulate log det -------------
     for (int idx = tid; idx < NB * NB; idx += NTHR) {
@@ -199,6 +258,7 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
         if (tid == 0) *logdet_add = 2.0 * ((sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]));
     }
 
+    CH_STAMP_IN(3);
     // ---- in-place inverse of the lower-triangular block --------------------------------------
     // (i) the eight 16x16 diagonal sub-blocks: thread (b, c) solves L_bb x = e_c
     {
@@ -224,6 +284,7 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
         }
         named_bar_sync(BAR_ALL, NTHR);
     }
+    CH_STAMP_IN(4);
     // (ii) off-diagonal blocks by distance from the diagonal:  X_bJ = -Inv_bb * sum_{b'=J}^{b-1} L_bb' X_b'J  (X_JJ = Inv_JJ).
     //      All pairs (b, J = b - dist) of one distance are independent: one warp per pair, every lane a 2x4 micro-tile
     //      (rows ti, ti+8; columns 4tc..4tc+3) so each shared-memory operand feeds several FMAs -- with one element
@@ -238,11 +299,15 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
             if (b < NSB) {
                 const double* L0 = sm.S + (b * SB + ti) * PS;
                 const double* L1 = L0 + 8 * PS;
-                double t[2][4];
+                // four independent accumulator sets over k % 4 (a dependent DFMA costs ~50 cycles; one set made every 16 x 16
+                // block product a 16-deep chain)
+                double t[4][2][4];
 #pragma unroll
-                for (int a = 0; a < 2; a++)
+                for (int z = 0; z < 4; z++)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) t[a][q] = 0.0;
+                    for (int a = 0; a < 2; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) t[z][a][q] = 0.0;
                 for (int bp = J; bp < b; bp++) {
                     // X_b'J[k][c]: the inverted diagonal block (b' == J, zero above its diagonal) or the parked block (J, b')
                     const double* xs = sm.S + (J * SB) * PS + bp * SB + 4 * tc;
@@ -254,40 +319,42 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
                         const double* x = xs + k * PS;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            t[0][q] = fma(a0, x[q], t[0][q]);
-                            t[1][q] = fma(a1, x[q], t[1][q]);
+                            t[k & 3][0][q] = fma(a0, x[q], t[k & 3][0][q]);
+                            t[k & 3][1][q] = fma(a1, x[q], t[k & 3][1][q]);
                         }
                     }
                 }
                 double* tp = sm.Tmp + w * SB * (SB + 1);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    tp[ti * (SB + 1) + 4 * tc + q] = t[0][q];
-                    tp[(ti + 8) * (SB + 1) + 4 * tc + q] = t[1][q];
+                    tp[ti * (SB + 1) + 4 * tc + q] = (t[0][0][q] + t[1][0][q]) + (t[2][0][q] + t[3][0][q]);
+                    tp[(ti + 8) * (SB + 1) + 4 * tc + q] = (t[0][1][q] + t[1][1][q]) + (t[2][1][q] + t[3][1][q]);
                 }
                 __syncwarp();
                 const double* i0 = sm.S + (b * SB + ti) * PS + b * SB;     // rows ti, ti+8 of Inv_bb (lower triangular)
                 const double* i1 = i0 + 8 * PS;
-                double y[2][4];
+                double y[4][2][4];
 #pragma unroll
-                for (int a = 0; a < 2; a++)
+                for (int z = 0; z < 4; z++)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) y[a][q] = 0.0;
+                    for (int a = 0; a < 2; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) y[z][a][q] = 0.0;
 #pragma unroll
                 for (int k = 0; k < SB; k++) {
                     const double a0 = i0[k], a1 = i1[k];                   // zero for k beyond the row index
                     const double* x = tp + k * (SB + 1) + 4 * tc;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        y[0][q] = fma(a0, x[q], y[0][q]);
-                        y[1][q] = fma(a1, x[q], y[1][q]);
+                        y[k & 3][0][q] = fma(a0, x[q], y[k & 3][0][q]);
+                        y[k & 3][1][q] = fma(a1, x[q], y[k & 3][1][q]);
                     }
                 }
                 double* xo = sm.S + (J * SB) * PS + b * SB + 4 * tc;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    xo[ti * PS + q] = -y[0][q];
-                    xo[(ti + 8) * PS + q] = -y[1][q];
+                    xo[ti * PS + q] = -((y[0][0][q] + y[1][0][q]) + (y[2][0][q] + y[3][0][q]));
+                    xo[(ti + 8) * PS + q] = -((y[0][1][q] + y[1][1][q]) + (y[2][1][q] + y[3][1][q]));
                 }
                 __syncwarp();   // block column J = w of the inverse is produced and consumed by this warp alone
             }
@@ -526,15 +593,48 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
             // the factorisation borrows the ring and the staging buffer: every consumer warp must be done reading them
             // for the previous tile (its last MMA stage, a DIAG tile's write-back) before the first store lands there
             named_bar_sync(1, Cfg::NCW * 32);
+#ifdef CHOL_TRACE
+            __shared__ int tr_slot;
+            if (ctid == 0) tr_slot = atomicAdd(&chol_trace_count, 1);
+            named_bar_sync(1, Cfg::NCW * 32);
+            const int trs = tr_slot;
+            if (ctid == 0) { CH_STAMP(trs, 0); if (trs < CH_TRACE_N) chol_trace_buf[trs * CH_TRACE_EV + 7] = (unsigned long long)j;
+                             unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); chol_trace_cur[sm_ & 255] = trs; }
+            named_bar_sync(1, Cfg::NCW * 32);
+#endif
             if (!skip) {
                 Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(base);
                 double* Ablk = p.A + (rb + (int64_t)j * NB) * p.n_pad + (int64_t)j * NB;
-                for (int idx = ctid; idx < NB * NB; idx += Cfg::NCW * 32) {
-                    const int r = idx >> 7, c = idx & 127;
-                    sm.S[r * PS + c] = (c <= r) ? __ldcg(Ablk + (int64_t)r * p.n_pad + c) : 0.0;
+                // R_jj (written by the two DIAG tiles on other SMs) -> shared memory: 16-byte loads, eight in flight per thread
+                // (a single 8-byte load per iteration left the 128 KB block waiting on 64 sequential L2 round trips: 16 us)
+                {
+                    const int cp = ctid & 63, r0 = ctid >> 6;          // column pair, first row; rows r0, r0 + 4, ...
+#pragma unroll
+                    for (int it = 0; it < 32; it += 8) {
+                        double2 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int r = r0 + 4 * (it + u);
+                            v[u] = (2 * cp <= r) ? __ldcg(reinterpret_cast<const double2*>(Ablk + (int64_t)r * p.n_pad) + cp)
+                                                 : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int r = r0 + 4 * (it + u);
+                            sm.S[r * PS + 2 * cp] = (2 * cp <= r) ? v[u].x : 0.0;
+                            sm.S[r * PS + 2 * cp + 1] = (2 * cp + 1 <= r) ? v[u].y : 0.0;
+                        }
+                    }
                 }
                 double ld_add = 0.0;
+#ifdef CHOL_TRACE
+                named_bar_sync(1, Cfg::NCW * 32);
+                if (ctid == 0) CH_STAMP(trs, 1);
+#endif
                 const int fail = potf2_inv_block<Cfg::NCW * 32, 2>(sm, ctid, Ablk, p.n_pad, &ld_add);
+#ifdef CHOL_TRACE
+                if (ctid == 0) CH_STAMP(trs, 5);
+#endif
                 if (fail) {
                     if (ctid == 0) p.info[o] = j * NB + fail;
                 } else {
@@ -554,6 +654,9 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
             __threadfence();
             fence_proxy_async();
             named_bar_sync(1, Cfg::NCW * 32);   // everyone is done with the borrowed shared memory
+#ifdef CHOL_TRACE
+            if (ctid == 0) CH_STAMP(trs, 6);
+#endif
             if (lane == 0) {
                 red_release_gpu_add(dprog, 1);
                 mbar_arrive(d_done);
@@ -682,3 +785,17 @@ int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, c
 }
 
 }  // namespace mogp
+
+#ifdef CHOL_TRACE
+extern "C" int mogp_debug_chol_trace(unsigned long long* out, int n_words, int reset) {
+    int cnt = 0;
+    cudaMemcpyFromSymbol(&cnt, mogp::chol_trace_count, sizeof(int));
+    const int words = mogp::CH_TRACE_N * mogp::CH_TRACE_EV;
+    if (out) cudaMemcpyFromSymbol(out, mogp::chol_trace_buf, sizeof(unsigned long long) * (size_t)(n_words < words ? n_words : words));
+    if (reset) { int z = 0; cudaMemcpyToSymbol(mogp::chol_trace_count, &z, sizeof(int)); }
+    return cnt;
+}
+extern "C" int mogp_debug_chol_trace2(unsigned long long* out, int n_words) {
+    return cudaMemcpyFromSymbol(out, mogp::chol_trace_buf2, sizeof(unsigned long long) * (size_t)n_words) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -1,0 +1,47 @@
+"""Phases of the diagonal (D) tiles of chol_dataflow_kernel (debug build: ./build.sh -DCHOL_TRACE) for one n = 4096 matrix:
+load R_jj -> factor -> write L_jj -> invert 16x16 diagonal sub-blocks -> off-diagonal inverse blocks -> write inv(L_jj) + publish.
+usage (under gpurun): python tools/chol_dtile_timeline.py > gpurun_out/chol_dtile.txt"""
+import ctypes, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import make_workload, make_thetas
+import mogp_emulator_b200 as mogp
+from mogp_emulator_b200 import libmogp
+
+n, d = 4096, 10
+X, Y, Xs = make_workload(n, d, 1, 16, 1)
+gp = mogp.GaussianProcessGPU(X, Y[0], nugget=1e-6)
+theta = make_thetas(1, d)[0]
+lib = libmogp._lib
+lib.mogp_debug_chol_trace.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int, ctypes.c_int]
+gp.fit(theta)
+gp.fit(theta)
+lib.mogp_debug_chol_trace(None, 0, 1)
+gp.fit(theta)
+EV, N = 8, 4096
+buf = (ctypes.c_ulonglong * (EV * N))()
+cnt = lib.mogp_debug_chol_trace(buf, EV * N, 0)
+a = np.array(buf[:], dtype=np.int64).reshape(N, EV)[:cnt]
+a = a[np.argsort(a[:, 7])]
+names = ["load", "factor", "write_L+logdet", "inv_diag16", "inv_offdiag", "write_Dinv+publish"]
+print("# j start_us " + " ".join(names) + " total   (us)")
+for r in a:
+    t = r[:7]
+    print(int(r[7]), "%.1f" % ((t[0] - a[0, 0]) / 1e3), " ".join("%.1f" % ((t[k + 1] - t[k]) / 1e3) for k in range(6)), "%.1f" % ((t[6] - t[0]) / 1e3))
+d_ = np.diff(a[:, :7], axis=1) / 1e3
+print("# medians (us):", " ".join("%s %.1f" % (nm, np.median(d_[:, k])) for k, nm in enumerate(names)), " total %.1f" % np.median((a[:, 6] - a[:, 0]) / 1e3),
+      " column period %.1f" % np.median(np.diff(a[:, 0]) / 1e3))
+lib.mogp_debug_chol_trace2.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+buf2 = (ctypes.c_ulonglong * (32 * cnt))()
+lib.mogp_debug_chol_trace2(buf2, 32 * cnt)
+b = np.array(buf2[:], dtype=np.int64).reshape(cnt, 32)
+ev = ["start", "a1(0) done", "a2(0)+barriers", "after b1(0)", "a1(1) done", "b2(0) done (warp 1)", "after barrier", "a2(1) done",
+      None, None, "after b1(3)", "a1(4) done", "b2(3) done (warp 1)", "after barrier", "a2(4) done"]
+for k in range(1, 15):
+    if ev[k] is None or k == 10:
+        continue
+    print("# factor phases, median over D tiles (us): %-24s +%.2f" % (ev[k], np.median((b[:, k] - b[:, k - 1]) / 1e3)))
+print("# (b2 done is measured from 'after b1')", "b2(0): %.2f" % np.median((b[:, 5] - b[:, 3]) / 1e3), "b2(3): %.2f" % np.median((b[:, 12] - b[:, 10]) / 1e3),
+      " a1(1): %.2f" % np.median((b[:, 4] - b[:, 3]) / 1e3), " a1(4): %.2f" % np.median((b[:, 11] - b[:, 10]) / 1e3))
+print(gp._handle.timings())
