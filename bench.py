@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (outputs, n, d, m, kernel, nugget, seed)      SURVEY.md section 8d
     "c1": (1, 256, 4, 1000, "SquaredExponential", 1.0e-6, 0),
     "c3": (32, 4096, 10, 10000, "SquaredExponential", 1.0e-6, 2),
+    "c3a": (32, 4096, 10, 10000, "SquaredExponential", "adaptive", 2),  # C3 with the API-default nugget (adaptive -> 0.0 here)
     "c4": (1, 16384, 20, 1000, "Matern52", "adaptive", 3),
     "c5": (256, 8192, 15, 10000, "SquaredExponential", 1.0e-6, 4),
     "c2": (1, 4096, 10, 10000, "SquaredExponential", 1.0e-6, 1),       # fit_GP_MAP (run_c2)

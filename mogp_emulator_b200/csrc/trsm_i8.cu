@@ -336,7 +336,7 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
             int it = 0;
             for (int nq = 0;; nq++) {
                 const int slot = nq % I8_QN;
-                if (nq >= I8_QN) i8_wait(&tq_empty[slot], (uint32_t)(((nq / I8_QN) - 1) & 1));
+                i8_wait(&tq_empty[slot], (uint32_t)(((nq / I8_QN) & 1) ^ 1));      // (a fresh barrier passes the wait on parity 1)
                 const int t = atomicAdd(p.sync, 1);
                 tq[slot] = (t < total) ? t : -1;
                 mbar_arrive(&tq_full[slot]);
@@ -536,7 +536,9 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
             // (tools/probe_concurrency.cu): releasing the MMA warp right after the drain stretched this tile's diagonal product
             // over the whole MMA phase of the next tile and left digits + store exposed behind it (profiles/r02_i8_timeline.txt).
             // So the accumulators are handed back only here: the FP64 part runs at full rate first, the integer / memory part of
-            // the epilogue below overlaps the next tile's MMAs.
+            // the epilogue below overlaps the next tile's MMAs.  (Handing them back right after the drain and pausing the issuer
+            // only for the diagonal product was tried: the few FP64 instructions of the T_i update then starve instead, same
+            // tile period -- profiles/r02_i8_timeline.txt.)
             if (i > 0 && lane == 0) mbar_arrive(acc_empty);
             if (tid == 0) I8_STAMP(nq, 10);
 

@@ -18,7 +18,14 @@ gp.fit(thetas[0])
 c = gp.predict(Xs, full_cov=True)
 gp.logpost_deriv(thetas[0])
 gp.close()
-print("case done", float(r.mean[0, 0]), float(c.unc[0, 0]))
+# many right-hand sides: the persistent int8 tcgen05 TRSM (csrc/trsm_i8.cu) with its a-posteriori FP64 check on the side stream
+X, Y, Xs = orc.make_workload(300, 3, 40, 600, seed=1)
+mo = MultiOutputGP_GPU(X, Y, nugget=1e-6)
+mo.fit(np.tile(np.array([1.0, 0.9, 1.1, 0.0]), (40, 1)))
+r8 = mo.predict(Xs, deriv=False)
+assert mo.timings()["i8_block_rows"] == 3, mo.timings()
+mo.close()
+print("case done", float(r.mean[0, 0]), float(c.unc[0, 0]), float(r8.unc[0, 0]))
 PY
 for tool in memcheck synccheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 200 python /tmp/san_case.py > gpurun_out/sanitizer_$tool.log 2>&1
