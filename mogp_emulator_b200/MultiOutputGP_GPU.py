@@ -14,7 +14,7 @@ from .GaussianProcessGPU import PredictResult, GPUUnavailableError, _check_mean
 from .hyper import GPParams, GPPriors, make_priors
 from .kernels import interpret_kernel
 from .meanfunc import design_matrix, design_matrix_inputderiv, MeanFit
-from .sharding import shard_bounds
+from .sharding import shard_bounds, gathered_rows, pack_block, unpack_gathered
 
 
 class MultiOutputGP_GPU(object):
@@ -342,54 +342,37 @@ class MultiOutputGP_GPU(object):
         if unc and full_cov:
             raise GPUUnavailableError("full predictive covariances are not gathered across ranks: predict them on the "
                                       "rank that holds the output (local_range)")
-        world, rank, e_pad, e_loc = self._comm.world, self._comm.rank, self._e_pad, self._hi - self._lo
-        rows = np.array([r * e_pad + k for r in range(world) for k in range(shard_bounds(E, r, world)[1] - shard_bounds(E, r, world)[0])])
-        in_order = bool(np.array_equal(rows, np.arange(E)))
+        world, e_pad, e_loc = self._comm.world, self._e_pad, self._hi - self._lo
         dmean_all = None
-        if not deriv and self._dm.shape[1] == 0:
+        if not deriv and self._dm.shape[1] == 0 and self._handle is not None:
             # the path of the BASELINE metric: device-resident results, ONE ncclAllGather of the packed [e_pad][2][m] blocks
-            if self._handle is not None:
-                mean_all, var_all, status_all = self._handle.predict_allgather(self._comm, testing, include_nugget, e_pad)
+            mean_all, var_all, status_all = self._handle.predict_allgather(self._comm, testing, include_nugget, e_pad)
+            # rank r's block starts at row r*e_pad; when the partition is even that is its first global output index and the
+            # gathered rows are already in output order (slice, no copy); otherwise pick the rows
+            rows = gathered_rows(E, world)
+            if rows == list(range(E)):
+                mean_all, var_all, status = mean_all[:E], var_all[:E], status_all[:E]
             else:
-                # this rank holds no outputs (more ranks than outputs): an all-padding block of the same length
-                block = np.full(e_pad * 2 * m + e_pad, np.nan)
-                block[e_pad * 2 * m:] = float(libmogp.ERR_ARG)
-                got = self._comm.allgather(block)
-                mean_all = got[:, :e_pad * 2 * m].reshape(world * e_pad, 2, m)[:, 0]
-                var_all = got[:, :e_pad * 2 * m].reshape(world * e_pad, 2, m)[:, 1]
-                status_all = got[:, e_pad * 2 * m:].reshape(-1).astype(np.int32)
+                mean_all, var_all, status = mean_all[rows], var_all[rows], status_all[rows]
         else:
-            # mean function and / or derivatives: each rank finishes its own posteriors on the host, then one all-gather of
-            # [e_pad][(2 + D) m] + status
-            width = (2 + (self.D if deriv else 0)) * m
-            block = np.full(e_pad * width + e_pad, np.nan)
-            block[e_pad * width:] = float(libmogp.ERR_ARG)
+            # mean function and / or derivatives (or a rank without outputs, which joins the same collective with an all-padding
+            # block): each rank finishes its own posteriors on the host, then one all-gather of the packed block (sharding.py)
+            D = self.D if deriv else 0
             if e_loc:
                 mean, var, dmean = self._local_predict(testing, True, deriv, include_nugget, False)
-                body = block[:e_pad * width].reshape(e_pad, width)
-                body[:e_loc, :m] = mean
-                body[:e_loc, m:2 * m] = var
-                if deriv:
-                    body[:e_loc, 2 * m:] = dmean.reshape(e_loc, m * self.D)
-                block[e_pad * width:e_pad * width + e_loc] = [float(libmogp.OK if f else libmogp.ERR_NOT_FIT)
-                                                              for f in self._fit[self._lo:self._hi]]
-            got = self._comm.allgather(block)
-            body = got[:, :e_pad * width].reshape(world * e_pad, width)
-            mean_all, var_all = body[:, :m], body[:, m:2 * m]
+            else:
+                mean, var, dmean = np.empty((0, m)), np.empty((0, m)), (np.empty((0, m, self.D)) if deriv else None)
+            block = pack_block(mean, var, self._fit[self._lo:self._hi], e_pad, deriv=dmean if deriv else None)
+            got = unpack_gathered(self._comm.allgather(block), E, world, m, d=D)
+            mean_all, var_all, status = got[0], got[1], got[2]
             if deriv:
-                dmean_all = body[:, 2 * m:].reshape(world * e_pad, m, self.D)
-            status_all = got[:, e_pad * width:].reshape(-1).astype(np.int32)
-        # rank r's block starts at row r*e_pad; when the partition is even that is its first global output index and the
-        # gathered rows are already in output order (slice, no copy); otherwise pick the rows
-        pick = (lambda a: a[:E]) if in_order else (lambda a: a[rows])
-        status = pick(status_all)
+                dmean_all = got[3]
         for i in range(E):
             if not self._lo <= i < self._hi:
                 self._fit[i] = bool(status[i] == libmogp.OK)
         if not allow_not_fit and np.any(status != libmogp.OK):
             raise ValueError("Hyperparameters have not been fit for this Gaussian Process")
-        return PredictResult(mean=pick(mean_all), unc=pick(var_all) if unc else None,
-                             deriv=pick(dmean_all) if deriv else None)
+        return PredictResult(mean=mean_all, unc=var_all if unc else None, deriv=dmean_all if deriv else None)
 
     def _local_predict(self, testing, unc, deriv, include_nugget, full_cov):
         """Posterior of the outputs this rank holds (local index k <-> output lo + k): mean (e, m), var (e, m) or

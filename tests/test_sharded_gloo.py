@@ -21,7 +21,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, E, unfit, out_dir):
+def _worker(rank, world, port, E, unfit, out_dir, with_deriv=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "oracle")):
@@ -35,26 +35,37 @@ def _worker(rank, world, port, E, unfit, out_dir):
     X, Y, Xs = orc.make_workload(60, 2, E, 11, seed=1)
     thetas = np.tile(np.array([1.0, 0.5, 0.1]), (E, 1)) + 0.05 * np.arange(E)[:, None]
     lo, hi, e_pad = sharding.shard_bounds(E, rank, world)
-    gp = orc.OracleMultiOutputGP(X, Y[lo:hi], nugget=1e-6, priors="weak")
+    gp = orc.OracleMultiOutputGP(X, Y[lo:hi], nugget=1e-6, priors="weak") if hi > lo else None
     fitted = []
     for k, i in enumerate(range(lo, hi)):
         if i not in unfit:
             gp.fit_emulator(k, thetas[i])
         fitted.append(i not in unfit)
-    mean, var = gp.predict(Xs, allow_not_fit=True)
-    block = torch.from_numpy(sharding.pack_block(mean, var, fitted, e_pad))
+    m, D = Xs.shape
+    if hi > lo:
+        mean, var = gp.predict(Xs, allow_not_fit=True)
+    else:
+        mean, var = np.empty((0, m)), np.empty((0, m))           # a rank without outputs still joins the collective
+    deriv = None
+    if with_deriv:
+        deriv = np.full((hi - lo, m, D), np.nan)
+        for k in range(hi - lo):
+            if fitted[k]:
+                deriv[k] = gp.emulators[k].predict_deriv(Xs)
+    block = torch.from_numpy(sharding.pack_block(mean, var, fitted, e_pad, deriv=deriv))
     gathered = [torch.empty_like(block) for _ in range(world)]
     dist.all_gather(gathered, block)                      # the one collective of the path
-    gm, gv, st = sharding.unpack_gathered(torch.stack(gathered).numpy(), E, world, Xs.shape[0])
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mean=gm, var=gv, status=st)
+    got = sharding.unpack_gathered(torch.stack(gathered).numpy(), E, world, m, d=D if with_deriv else 0)
+    extra = {"deriv": got[3]} if with_deriv else {}
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mean=got[0], var=got[1], status=got[2], **extra)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("E,unfit", [(4, ()), (5, (3,))])
-def test_two_rank_gather_reassembles_all_outputs(tmp_path, E, unfit):
+@pytest.mark.parametrize("E,unfit,world,with_deriv", [(4, (), 2, False), (5, (3,), 2, False), (5, (1,), 2, True), (2, (), 3, True)])
+def test_gather_reassembles_all_outputs(tmp_path, E, unfit, world, with_deriv):
+    """Even and uneven (balanced) partitions, an unfit emulator, gathered derivatives, more ranks than outputs."""
     import gp_oracle as orc
-    world = 2
-    mp.spawn(_worker, args=(world, _free_port(), E, tuple(unfit), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), E, tuple(unfit), str(tmp_path), with_deriv), nprocs=world, join=True)
     X, Y, Xs = orc.make_workload(60, 2, E, 11, seed=1)
     thetas = np.tile(np.array([1.0, 0.5, 0.1]), (E, 1)) + 0.05 * np.arange(E)[:, None]
     full = orc.OracleMultiOutputGP(X, Y, nugget=1e-6, priors="weak")
@@ -67,3 +78,9 @@ def test_two_rank_gather_reassembles_all_outputs(tmp_path, E, unfit):
         np.testing.assert_allclose(z["mean"], want_mean, rtol=1e-12, equal_nan=True)
         np.testing.assert_allclose(z["var"], want_var, rtol=1e-12, atol=1e-18, equal_nan=True)
         assert list(z["status"]) == [4 if i in unfit else 0 for i in range(E)]
+        if with_deriv:
+            for i in range(E):
+                if i in unfit:
+                    assert np.all(np.isnan(z["deriv"][i]))
+                else:
+                    np.testing.assert_allclose(z["deriv"][i], full.emulators[i].predict_deriv(Xs), rtol=1e-12, atol=1e-15)
