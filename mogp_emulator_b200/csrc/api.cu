@@ -1422,8 +1422,10 @@ int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, in
     const NcclApi* api = nccl_api();
     API_CUDA(cudaSetDevice(h->device));
     NvtxRange nvtx_range("mogp_predict_allgather");
+    TraceClock tc("mogp_predict_allgather");
     int rc = predict_device(h, Xs, m, 1, include_nugget);
     if (rc) return rc;
+    tc.mark("predict_device (kernels + sync)");
     const size_t blk = (size_t)e_pad * 2 * m;  // doubles per rank; one extra row-pair block carries the status words
     const size_t send_n = blk + e_pad;
     if ((rc = grow(&comm->sendbuf, &comm->send_cap, sizeof(double) * send_n, comm->device))) return rc;
@@ -1442,7 +1444,9 @@ int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, in
         return MOGP_ERR_NCCL;
     }
     API_CUDA(cudaMemcpyAsync(comm->h_recv, comm->recvbuf, sizeof(double) * send_n * comm->world, cudaMemcpyDeviceToHost, h->main));
+    tc.mark("pack + enqueue all-gather + D2H");
     API_CUDA(cudaStreamSynchronize(h->main));
+    tc.mark("all-gather + D2H complete");
     for (int rk = 0; rk < comm->world; rk++) {
         const double* src = comm->h_recv + (size_t)rk * send_n;
         for (int o = 0; o < e_pad; o++) {
@@ -1452,6 +1456,7 @@ int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, in
             if (status_all) status_all[row] = (int32_t)src[blk + o];
         }
     }
+    tc.mark("host unpack");
     return MOGP_OK;
 }
 

@@ -2,11 +2,15 @@
 
 Digits are held in float64 and multiplied with BLAS: every product and partial sum is an integer far below 2^53, so the
 result is what tcgen05.mma.kind::i8 with s32 accumulation produces.  Conventions are the kernel's: block 128, signed 7-bit
-digits by round-to-nearest, scaled values clamped to +-0.99, row scale of L~ = 2^(frexp exponent of the row maximum + 1),
-scale of V = 2^(frexp exponent of sqrt(sigma2 + nugget) + 1), digit pairs (t, u) with t + u <= S + 1, V re-sliced after
-every block row, FP64 for blockdiag(L_ii)^-1 L, blockdiag(L_ii)^-1 K* and the final subtraction.
-Used to check that the error the GPU path shows against the FP64 path (profiles/r01_i8_check.txt) is the error of the
-designed arithmetic, not of its implementation, and as the debugging reference for changes to that kernel.
+digits by round-to-nearest, digit pairs (t, u) with t + u <= S + 1, V re-sliced after every block row.
+
+``trsm_variance`` is the kernel of round 2 (rows-of-L form): the strictly lower blocks of L and every solved block row V_i are
+sliced with ONE scale 2^e per output, sqrt(sigma2 + nugget) <= 2^(e-1); T_i = K*_i - sum_j L_ij V_j from the integer
+products; V_i = inv(L_ii) T_i in FP64.  ``trsm_variance_ltilde`` is the kernel of round 1 (L~ = blockdiag(L_ii)^-1 L sliced
+with one scale per row, K* pre-multiplied), kept because profiles/r01_i8_check.txt was measured with it.
+Used to check that the error the GPU path shows against the FP64 path is the error of the designed arithmetic, not of its
+implementation, as the debugging reference for changes to that kernel, and for the study behind the a-posteriori accuracy
+check (tools/i8_gate_study.py).
 """
 import numpy as np
 
@@ -39,9 +43,38 @@ def sliced_product(A, eA, Vd, S):
     return acc
 
 
+def scale_exponent(sigma2, nugget):
+    """csrc/trsm_i8.cu i8_scale_exponent: e with sqrt(sigma2 + nugget) <= 2^(e-1)."""
+    return int(np.frexp(np.sqrt(sigma2 + nugget))[1]) + 1
+
+
 def trsm_variance(L, Ks, sigma2, nugget, S, include_nugget=True):
     """L (n, n) lower Cholesky factor of sigma2 k(X, X) + nugget I, Ks (n, m) = sigma2 k(X, X*): predictive variances as
-    the int8 path computes them (un-clipped)."""
+    i8_trsm_kernel computes them (un-clipped)."""
+    n, m = Ks.shape
+    n_pad = (n + NB - 1) // NB * NB
+    Lp = np.eye(n_pad)
+    Lp[:n, :n] = L
+    Kp = np.zeros((n_pad, m))
+    Kp[:n] = Ks
+    e = scale_exponent(sigma2, nugget)
+    Vd = [np.zeros((n_pad, m)) for _ in range(S)]
+    norms = np.zeros(m)
+    for i0 in range(0, n_pad, NB):
+        blk = slice(i0, i0 + NB)
+        T = Kp[blk].copy()
+        if i0 > 0:
+            acc = sliced_product(Lp[blk, :i0], np.full(NB, e), [d[:i0] for d in Vd], S)
+            T -= acc * 2.0 ** (2 * e)
+        V = np.linalg.solve(Lp[blk, blk], T)               # the kernel multiplies by the stored inverse of L_ii (DMMA)
+        norms += np.sum(V * V, axis=0)
+        for t, d in enumerate(digits(V * 2.0 ** -e, S)):
+            Vd[t][blk] = d
+    return sigma2 + (nugget if include_nugget else 0.0) - norms
+
+
+def trsm_variance_ltilde(L, Ks, sigma2, nugget, S, include_nugget=True):
+    """The round-1 kernel (L~ form, one scale per row of L~): predictive variances (un-clipped)."""
     n, m = Ks.shape
     n_pad = (n + NB - 1) // NB * NB
     Lp = np.eye(n_pad)
