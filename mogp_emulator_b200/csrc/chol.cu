@@ -473,7 +473,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     if (warp >= Cfg::NCW) {
         // =========================== ticket + TMA producer ===========================
         reg_dealloc<56>();
-        if (warp == Cfg::NCW && lane == 0) {
+        if (warp == Cfg::NCW && elect_one_sync()) {
             prefetch_tmap(&tmL);
             prefetch_tmap(&tmW);
             prefetch_tmap(&tmD);

@@ -91,6 +91,15 @@ __device__ __forceinline__ void reg_alloc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
 }
 
+// One lane of a converged warp, chosen by elect.sync: ptxas then knows a single thread runs the branch and feeds the uniform
+// datapath of TMA / tcgen05 instructions with plain R2UR (behind `if (lane == 0)` every such instruction is wrapped in an
+// ELECT / R2UR.BROADCAST / branch loop -- profiles/r02_sass_evidence.txt).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

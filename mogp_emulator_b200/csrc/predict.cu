@@ -116,7 +116,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
     if (warp >= Cfg::NCW) {
         // =========================== ticket + TMA producer ===========================
         reg_dealloc<56>();
-        if (warp == Cfg::NCW && lane == 0) {
+        if (warp == Cfg::NCW && elect_one_sync()) {
             prefetch_tmap(&tmL);
             prefetch_tmap(&tmD);
             prefetch_tmap(&tmW);

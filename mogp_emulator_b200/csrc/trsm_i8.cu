@@ -85,14 +85,10 @@ __host__ __device__ constexpr uint32_t i8_idesc(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(NB >> 4) << 24);
 }
 
-// The issuing thread is chosen with elect.sync: ptxas then knows a single lane is active and moves the operands to uniform
-// registers with plain R2UR; behind `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST / branch loop
-// and the issue thread, not the tensor pipe, set the pace (profiles/r02_i8_timeline.txt).
-__device__ __forceinline__ bool i8_elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
+// The issuing thread is chosen with elect.sync (common.cuh elect_one_sync): ptxas then knows a single lane is active and
+// moves the operands to uniform registers with plain R2UR; behind `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT /
+// R2UR.BROADCAST / branch loop and the issue thread, not the tensor pipe, set the pace (profiles/r02_i8_timeline_before.txt).
+__device__ __forceinline__ bool i8_elect_one() { return elect_one_sync(); }
 __device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -212,7 +208,7 @@ __global__ void __launch_bounds__(256) i8_slice_kernel(const I8SliceParams p) {
             for (int q = 0; q < 4; q++) w[t][q] = 0u;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            const double2 v = __ldcs(src + q);
+            const double2 v = src[q];      // (default caching: the eight loads of a thread walk one 128-byte line)
             int8_t d0[S], d1[S];
             i8_digits<S>(v.x * sc, d0);
             i8_digits<S>(v.y * sc, d1);
