@@ -669,7 +669,8 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
             // solved by the FP64 kernel and must agree to 1 % of the parity bar; an output that fails sends its group back to the
             // FP64 path now and until it is fitted again.
             int i8_prep_launches = 0;
-            bool i8 = want_var && h->use_i8 && n_tiles >= 2 &&
+            // (n_pad <= 65536: a column of n_pad products of 7-bit digits times S pairs must stay below 2^31 in the s32 accumulators)
+            bool i8 = want_var && h->use_i8 && n_tiles >= 2 && np <= 65536 &&
                       (int64_t)cnt * ((mc + i8_panel_width() - 1) / i8_panel_width()) >= (int64_t)h->n_sms;
             for (int k = 0; k < cnt && i8; k++)
                 if (h->i8_bad[outs[k]]) i8 = false;

@@ -405,27 +405,45 @@ struct TileId {
     int kind, lo, i, p, j;
 };
 
-// ticket -> tile.  Column j holds count*(2T+1-2j) tickets: [2*count DIAG][count D][count*2*(T-1-j) ROW, i ascending]
+// ticket -> tile, with look-ahead on the critical chain.  The first 3*count tickets are [2*count DIAG(0)][count D(0)]; then
+// block j = 0 .. T-2 holds count*(2T+1-2j) tickets:
+//     [2*count ROW(j+1, p, j)] [2*count DIAG(j+1, p)] [count D(j+1)] [count * 2*(T-2-j) ROW(i, p, j), i = j+2 .. T-1]
+// i.e. the tiles the NEXT column's diagonal block waits for, that diagonal block and its factorisation are drawn before the
+// bulk of column j's row tiles.  (In plain column order DIAG(j+1) sat behind every ROW tile of column j: with a few matrices
+// per launch -- C3 on 8 GPUs: 4 -- that is more tiles than SMs, and the chain DIAG -> D -> ROW stalled for a wave of row
+// tiles in every column.)  Still a topological order: DIAG(j+1, p) needs ROW(j+1, p, k <= j), all drawn before it.
 __device__ __forceinline__ TileId decode_ticket(int t, int T, int count) {
     TileId id;
+    if (t < 3 * count) {
+        id.j = 0; id.i = 0;
+        if (t < 2 * count) {
+            id.kind = TK_DIAG; id.lo = t >> 1; id.p = t & 1;
+        } else {
+            id.kind = TK_D; id.lo = t - 2 * count; id.p = 0;
+        }
+        return id;
+    }
+    t -= 3 * count;
     const int x = t / count;
     int j = (int)((double)(T + 1) - sqrt((double)(T + 1) * (double)(T + 1) - (double)x));
     if (j < 0) j = 0;
-    if (j > T - 1) j = T - 1;
+    if (j > T - 2) j = T - 2;
     while (j > 0 && j * (2 * T + 2 - j) > x) j--;
-    while (j < T - 1 && (j + 1) * (2 * T + 2 - (j + 1)) <= x) j++;
+    while (j < T - 2 && (j + 1) * (2 * T + 2 - (j + 1)) <= x) j++;
     int u = t - count * j * (2 * T + 2 - j);
-    id.j = j;
     if (u < 2 * count) {
-        id.kind = TK_DIAG; id.lo = u >> 1; id.p = u & 1; id.i = j;
-    } else if (u < 3 * count) {
-        id.kind = TK_D; id.lo = u - 2 * count; id.p = 0; id.i = j;
+        id.kind = TK_ROW; id.lo = u >> 1; id.p = u & 1; id.i = j + 1; id.j = j;
+    } else if (u < 4 * count) {
+        u -= 2 * count;
+        id.kind = TK_DIAG; id.lo = u >> 1; id.p = u & 1; id.i = j + 1; id.j = j + 1;
+    } else if (u < 5 * count) {
+        id.kind = TK_D; id.lo = u - 4 * count; id.p = 0; id.i = j + 1; id.j = j + 1;
     } else {
-        u -= 3 * count;
-        const int per = 2 * (T - 1 - j);
+        u -= 5 * count;
+        const int per = 2 * (T - 2 - j);
         id.kind = TK_ROW; id.lo = u / per;
         const int w = u - id.lo * per;
-        id.i = j + 1 + (w >> 1); id.p = w & 1;
+        id.i = j + 2 + (w >> 1); id.p = w & 1; id.j = j;
     }
     return id;
 }
