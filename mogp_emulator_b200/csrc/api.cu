@@ -622,6 +622,12 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
         API_CUDA(cudaMemGetInfo(&free_b, &total_b));
         budget = (size_t)((free_b + h->W_cap + pool_cached_bytes()) * 0.6);
     }
+    {
+        // MOGP_WORKSPACE_MB caps the predict workspace (tests: forces the grouping of outputs / chunking of test points that a
+        // full device would cause)
+        const char* e = getenv("MOGP_WORKSPACE_MB");
+        if (e && atof(e) > 0.0) budget = std::min(budget, (size_t)(atof(e) * 1048576.0));
+    }
     int64_t mc_max = m;
     while ((size_t)(round_up(mc_max, 128) + 128) * np * 8 > budget && mc_max > 128) mc_max = (mc_max + 1) / 2;
     for (int64_t m0 = 0; m0 < m; m0 += mc_max) {

@@ -882,6 +882,31 @@ def test_sharded_predict_two_ranks(mogp):
         assert p.returncode == 0 and "sharded predict OK" in out, "rank %d:\n%s" % (r, out)
 
 
+def test_predict_under_a_workspace_cap_groups_and_chunks(mogp, monkeypatch):
+    """A workspace smaller than the job (MOGP_WORKSPACE_MB, what a nearly full device causes): outputs are predicted in groups
+    and, when not even one output fits, the test points in chunks -- each piece on the int8 path with its own accuracy check.
+    Every test point is solved independently of its neighbours, so the results equal the one-piece run bit for bit."""
+    X, Y, Xs = orc.make_workload(300, 3, 24, 20000, seed=12)
+    thetas = np.tile(np.array([1.0, 0.9, 1.1, 0.0]), (24, 1)) + 0.03 * np.arange(24)[:, None]
+    _with_planes(monkeypatch, 7)
+    gp = mogp.MultiOutputGP_GPU(X, Y, nugget=1e-6)
+    gp.fit(thetas)
+    gp.timings(reset=True)
+    ref = gp.predict(Xs, deriv=False)
+    assert gp.timings(reset=True)["n_trsm"] == 1
+    monkeypatch.setenv("MOGP_WORKSPACE_MB", "400")          # one output's slab is 62 MB: groups of 6
+    grouped = gp.predict(Xs, deriv=False)
+    t = gp.timings(reset=True)
+    assert t["n_trsm"] == 4 and t["i8_block_rows"] == 4 * 3 and t["i8_fallbacks"] == 0
+    monkeypatch.setenv("MOGP_WORKSPACE_MB", "40")           # not even one output: two chunks of 10000 test points each
+    chunked = gp.predict(Xs, deriv=False)
+    t = gp.timings(reset=True)
+    assert t["n_trsm"] == 2 * 24 and t["i8_block_rows"] == 2 * 24 * 3 and t["i8_fallbacks"] == 0
+    gp.close()
+    for res in (grouped, chunked):
+        assert np.array_equal(res.mean, ref.mean) and np.array_equal(res.unc, ref.unc)
+
+
 def test_i8_trsm_with_mean_function(mogp, monkeypatch):
     """Un-clipped variances (the mean-function term is added on the host before the clip) through the int8 path."""
     X, Y, Xs = orc.make_workload(280, 3, 40, 640, seed=9)
