@@ -45,8 +45,9 @@ constexpr int SB = 16;      // sub-block width inside the diagonal block
 constexpr int NSB = NB / SB;                  // 8 sub-blocks per side
 
 struct Potf2Smem {
-    double S[NB * PS];                         // lower: L, then its diagonal-block inverses; upper blocks: inv(L) blocks (see (ii))
-    double Tmp[(NSB - 1) * SB * (SB + 1)];     // per (b, J) pair of a step: sum_b' L_bb' X_b'J
+    double S[NB * PS];                         // lower: L; upper blocks (J, b): the off-diagonal blocks X_bJ of inv(L)
+    double InvD[NSB * SB * (SB + 1)];          // inverses of the eight 16x16 diagonal sub-blocks of L (zero above the diagonal)
+    double Tmp[(NSB - 1) * SB * (SB + 1)];     // per (b, J) pair: sum_b' L_bb' X_b'J
     double Lr[SB * (SB + 1)];
     double rd[NB];
     double red[32];
@@ -199,6 +200,94 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
         }
     };
 
+    // ---- inverse of the block, one 16-row block row at a time -------------------------------------------------------
+    // inv_diag16(b): Inv_bb by one warp, lane c (< 16) solves L_bb x = e_c with the stored reciprocal pivots.
+    // inv_offdiag(b, J): X_bJ = -Inv_bb * sum_{b'=J}^{b-1} L_bb' X_b'J (X_JJ = Inv_JJ) by one warp, every lane a 2x4 micro-tile
+    // (rows ti, ti+8; columns 4tc..4tc+3) with four independent accumulator sets over k % 4 (a dependent DFMA costs ~50
+    // cycles); X_bJ is parked in the unused UPPER block (J, b) of sm.S (element [i][c] at S[J*16+i][b*16+c]).
+    // Block row b needs only the finished panels <= b of L and the block rows < b of the inverse, so it is computed by the
+    // warps 1..7 in the shadow of warp 0's pivot block b+1 (the long pole of the factorisation) instead of after it.
+    auto inv_diag16 = [&](int b, int lane) {
+        if (lane < SB) {
+            const int c = lane;
+            const double* Lb = sm.S + (b * SB) * PS + b * SB;
+            double* Ib = sm.InvD + b * SB * (SB + 1);
+            double x[SB];
+#pragma unroll
+            for (int i = 0; i < SB; i++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < i; kk++) sacc = fma(Lb[i * PS + kk], x[kk], sacc);
+                const double rdi = sm.rd[b * SB + i];
+                x[i] = (i == c) ? rdi : ((i > c) ? -sacc * rdi : 0.0);
+            }
+#pragma unroll
+            for (int i = 0; i < SB; i++) Ib[i * (SB + 1) + c] = x[i];
+        }
+    };
+    auto inv_offdiag = [&](int b, int J, int lane) {
+        if (J >= b) return;
+        const int ti = lane >> 2, tc = lane & 3;
+        const double* L0 = sm.S + (b * SB + ti) * PS;
+        const double* L1 = L0 + 8 * PS;
+        double t[4][2][4];
+#pragma unroll
+        for (int z = 0; z < 4; z++)
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) t[z][a][q] = 0.0;
+        for (int bp = J; bp < b; bp++) {
+            // X_b'J[k][c]: the inverted diagonal block (b' == J) or the parked block (J, b')
+            const double* xs = (bp == J) ? (sm.InvD + J * SB * (SB + 1) + 4 * tc) : (sm.S + (J * SB) * PS + bp * SB + 4 * tc);
+            const int xstride = (bp == J) ? (SB + 1) : PS;
+            const double* l0 = L0 + bp * SB;
+            const double* l1 = L1 + bp * SB;
+#pragma unroll
+            for (int k = 0; k < SB; k++) {
+                const double a0 = l0[k], a1 = l1[k];
+                const double* x = xs + k * xstride;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    t[k & 3][0][q] = fma(a0, x[q], t[k & 3][0][q]);
+                    t[k & 3][1][q] = fma(a1, x[q], t[k & 3][1][q]);
+                }
+            }
+        }
+        double* tp = sm.Tmp + J * SB * (SB + 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            tp[ti * (SB + 1) + 4 * tc + q] = (t[0][0][q] + t[1][0][q]) + (t[2][0][q] + t[3][0][q]);
+            tp[(ti + 8) * (SB + 1) + 4 * tc + q] = (t[0][1][q] + t[1][1][q]) + (t[2][1][q] + t[3][1][q]);
+        }
+        __syncwarp();
+        const double* i0 = sm.InvD + b * SB * (SB + 1) + ti * (SB + 1);      // rows ti, ti+8 of Inv_bb (zero above the diagonal)
+        const double* i1 = i0 + 8 * (SB + 1);
+        double y[4][2][4];
+#pragma unroll
+        for (int z = 0; z < 4; z++)
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) y[z][a][q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < SB; k++) {
+            const double a0 = i0[k], a1 = i1[k];
+            const double* x = tp + k * (SB + 1) + 4 * tc;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                y[k & 3][0][q] = fma(a0, x[q], y[k & 3][0][q]);
+                y[k & 3][1][q] = fma(a1, x[q], y[k & 3][1][q]);
+            }
+        }
+        double* xo = sm.S + (J * SB) * PS + b * SB + 4 * tc;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            xo[ti * PS + q] = -((y[0][0][q] + y[1][0][q]) + (y[2][0][q] + y[3][0][q]));
+            xo[(ti + 8) * PS + q] = -((y[0][1][q] + y[1][1][q]) + (y[2][1][q] + y[3][1][q]));
+        }
+    };
+
     CH_STAMP2(tid == 0, 0);
     if (tid < 32) potf2_diag16(sm, 0, tid);
     CH_STAMP2(tid == 0, 1);
@@ -233,6 +322,10 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
                 update_row(j0, NB - 1 - t, j0 + 2 * SB, NB - 1, q, NQ2);
             }
             CH_STAMP2(tid == 32 && (s == 0 || s == 3), s == 0 ? 5 : 12); // b2 done (one of its warps)
+            // block row s of the inverse (panel s of L is final): Inv_ss by warp 1, then X_sJ for J < s by the warps 1..7
+            if (tid < 64) inv_diag16(s, tid & 31);
+            named_bar_sync(BAR_ALL + 1, NTHR - 32);
+            inv_offdiag(s, (tid >> 5) - 1, tid & 31);
         }
         named_bar_sync(BAR_ALL, NTHR);
         CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 6 : 13);      // after the a1 / b2 barrier
@@ -259,108 +352,12 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
     }
 
     CH_STAMP_IN(3);
-    // ---- in-place inverse of the lower-triangular block --------------------------------------
-    // (i) the eight 16x16 diagonal sub-blocks: thread (b, c) solves L_bb x = e_c
-    {
-        double x[SB];
-        const int b = tid >> 4, c = tid & 15;
-        if (tid < NB) {
-            const double* Lb = sm.S + (b * SB) * PS + b * SB;
-#pragma unroll
-            for (int i = 0; i < SB; i++) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < i; kk++) sacc = fma(Lb[i * PS + kk], x[kk], sacc);
-                const double rdi = sm.rd[b * SB + i];
-                x[i] = (i == c) ? rdi : ((i > c) ? -sacc * rdi : 0.0);
-            }
-        }
-        named_bar_sync(BAR_ALL, NTHR);
-        if (tid < NB) {
-            double* Lb = sm.S + (b * SB) * PS + b * SB;
-#pragma unroll
-            for (int i = 0; i < SB; i++)
-                if (i >= c) Lb[i * PS + c] = x[i];
-        }
-        named_bar_sync(BAR_ALL, NTHR);
-    }
+    // ---- last block row of the inverse (the others were computed in the shadow of the pivot blocks, see the loop above) ----
+    if (tid >= 32 && tid < 64) inv_diag16(NSB - 1, tid & 31);
+    named_bar_sync(BAR_ALL, NTHR);
     CH_STAMP_IN(4);
-    // (ii) off-diagonal blocks by distance from the diagonal:  X_bJ = -Inv_bb * sum_{b'=J}^{b-1} L_bb' X_b'J  (X_JJ = Inv_JJ).
-    //      All pairs (b, J = b - dist) of one distance are independent: one warp per pair, every lane a 2x4 micro-tile
-    //      (rows ti, ti+8; columns 4tc..4tc+3) so each shared-memory operand feeds several FMAs -- with one element
-    //      per thread this phase was bound by shared-memory bandwidth.  X_bJ is parked in the unused UPPER block
-    //      (J, b) of sm.S (element [i][c] at S[J*16+i][b*16+c]); the L blocks stay intact for the larger distances.
-    {
-        static_assert(NTHR / 32 >= NSB - 1, "one warp per (b, J) pair");
-        const int w = tid >> 5, lane = tid & 31;
-        const int ti = lane >> 2, tc = lane & 3;
-        for (int dist = 1; dist < NSB; dist++) {
-            const int b = dist + w, J = w;          // pair handled by this warp
-            if (b < NSB) {
-                const double* L0 = sm.S + (b * SB + ti) * PS;
-                const double* L1 = L0 + 8 * PS;
-                // four independent accumulator sets over k % 4 (a dependent DFMA costs ~50 cycles; one set made every 16 x 16
-                // block product a 16-deep chain)
-                double t[4][2][4];
-#pragma unroll
-                for (int z = 0; z < 4; z++)
-#pragma unroll
-                    for (int a = 0; a < 2; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) t[z][a][q] = 0.0;
-                for (int bp = J; bp < b; bp++) {
-                    // X_b'J[k][c]: the inverted diagonal block (b' == J, zero above its diagonal) or the parked block (J, b')
-                    const double* xs = sm.S + (J * SB) * PS + bp * SB + 4 * tc;
-                    const double* l0 = L0 + bp * SB;
-                    const double* l1 = L1 + bp * SB;
-#pragma unroll
-                    for (int k = 0; k < SB; k++) {
-                        const double a0 = l0[k], a1 = l1[k];
-                        const double* x = xs + k * PS;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            t[k & 3][0][q] = fma(a0, x[q], t[k & 3][0][q]);
-                            t[k & 3][1][q] = fma(a1, x[q], t[k & 3][1][q]);
-                        }
-                    }
-                }
-                double* tp = sm.Tmp + w * SB * (SB + 1);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    tp[ti * (SB + 1) + 4 * tc + q] = (t[0][0][q] + t[1][0][q]) + (t[2][0][q] + t[3][0][q]);
-                    tp[(ti + 8) * (SB + 1) + 4 * tc + q] = (t[0][1][q] + t[1][1][q]) + (t[2][1][q] + t[3][1][q]);
-                }
-                __syncwarp();
-                const double* i0 = sm.S + (b * SB + ti) * PS + b * SB;     // rows ti, ti+8 of Inv_bb (lower triangular)
-                const double* i1 = i0 + 8 * PS;
-                double y[4][2][4];
-#pragma unroll
-                for (int z = 0; z < 4; z++)
-#pragma unroll
-                    for (int a = 0; a < 2; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) y[z][a][q] = 0.0;
-#pragma unroll
-                for (int k = 0; k < SB; k++) {
-                    const double a0 = i0[k], a1 = i1[k];                   // zero for k beyond the row index
-                    const double* x = tp + k * (SB + 1) + 4 * tc;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        y[k & 3][0][q] = fma(a0, x[q], y[k & 3][0][q]);
-                        y[k & 3][1][q] = fma(a1, x[q], y[k & 3][1][q]);
-                    }
-                }
-                double* xo = sm.S + (J * SB) * PS + b * SB + 4 * tc;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    xo[ti * PS + q] = -((y[0][0][q] + y[1][0][q]) + (y[2][0][q] + y[3][0][q]));
-                    xo[(ti + 8) * PS + q] = -((y[0][1][q] + y[1][1][q]) + (y[2][1][q] + y[3][1][q]));
-                }
-                __syncwarp();   // block column J = w of the inverse is produced and consumed by this warp alone
-            }
-        }
-        named_bar_sync(BAR_ALL, NTHR);
-    }
+    if (tid >= 32) inv_offdiag(NSB - 1, (tid >> 5) - 1, tid & 31);
+    named_bar_sync(BAR_ALL, NTHR);
     return 0;
 }
 
@@ -661,7 +658,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                         const int r = idx >> 7, c = idx & 127;
                         const int b = r >> 4, J = c >> 4;
                         double v = 0.0;
-                        if (b == J) v = (c <= r) ? sm.S[r * PS + c] : 0.0;
+                        if (b == J) v = sm.InvD[(b * SB + (r & 15)) * (SB + 1) + (c & 15)];      // (zero above the diagonal)
                         else if (b > J) v = sm.S[(J * SB + (r & 15)) * PS + b * SB + (c & 15)];   // parked in the upper block (J, b)
                         Dblk[idx] = v;
                     }
