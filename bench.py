@@ -563,6 +563,31 @@ def run_b200(args, wl):
                                         "var_max_abs": float(np.max(np.abs(gvar - cvar))),
                                         "var_worst_vs_tolerance": float(np.max(np.abs(gvar - cvar) / (1e-4 * np.abs(cvar) + 1e-4 * nug + 1e-300))),
                                         "all_outputs_finite": bool(np.all(np.isfinite(res.mean)) and np.all(np.isfinite(res.unc)))}
+    if world == 1 and tm.get("i8_block_rows", 0) > 0 and not args.no_other:
+        # the same step on the all-FP64 path (MOGP_TRSM_I8=0 is read when an emulator is constructed), in the same run on the
+        # same box: the number the int8 figures stand beside.  One warm-up step, two timed.
+        saved = os.environ.get("MOGP_TRSM_I8")
+        os.environ["MOGP_TRSM_I8"] = "0"
+        try:
+            gpf = MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget, device=device)
+            step(gpf)
+            gpf.timings(reset=True)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                rf = step(gpf)
+            dtf = (time.perf_counter() - t0) / 2
+            tf = gpf.timings(reset=True)
+            gpf.close()
+            line["all_fp64_path"] = {"value": dtf, "unit": "s", "predict_trsm_ms": tf["trsm_ms"] / 2, "cholesky_ms": tf["chol_ms"] / 2,
+                                     "trsm_tflops": trsm_flops / (tf["trsm_ms"] / 2 * 1e-3) * 1e-12,
+                                     "var_max_abs_int8_vs_fp64": float(np.max(np.abs(rf.unc - res.unc))),
+                                     "mean_identical": bool(np.array_equal(rf.mean, res.mean)),
+                                     "note": "MOGP_TRSM_I8=0: predict_trsm_kernel (DMMA) instead of i8_trsm_kernel; everything else identical"}
+        finally:
+            if saved is None:
+                os.environ.pop("MOGP_TRSM_I8", None)
+            else:
+                os.environ["MOGP_TRSM_I8"] = saved
     if world == 1 and args.workload == "c3" and not args.no_other:
         line["other_configs"] = other_configs(device, peak)
     print(json.dumps(line))

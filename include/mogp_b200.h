@@ -140,6 +140,13 @@ int mogp_set_mean_vectors_list(mogp_handle* h, const int32_t* idx, int32_t count
  * m), NaN rows for unfit outputs) -- H^T K^-1 K* of calc_R, without materialising K*. */
 int mogp_kstar_dot(mogp_handle* h, const double* Xs, int64_t m, const double* vecs, int32_t n_vec, double* out);
 
+/* Introspection of the factorisation's tile schedule (no device needed): ticket -> out5 = {kind (0 = DIAG accumulation of a
+ * diagonal block half, 1 = D factor + invert the diagonal block, 2 = ROW panel tile), output, block row i, half p, block column j}
+ * for a launch over n_outputs matrices of n_block_rows x n_block_rows 128-blocks; tickets run 0 .. n_outputs * T * (T + 2) - 1.
+ * The persistent kernel draws tickets in this order and spin-waits on the tiles a tile depends on, so the order must be
+ * topological; tests/test_host.py checks that on the CPU. */
+int mogp_chol_schedule(int32_t ticket, int32_t n_block_rows, int32_t n_outputs, int32_t* out5);
+
 /* accumulated device time per phase in ms since the last call with reset != 0:
  * out[0..10] = kmat, cholesky, solves, kstar, predict_trsm, grad, n_trsm_launches, n_kernel_launches, fit (device),
  *              predict host wall up to the last kernel's completion, predict result copy-out host wall;

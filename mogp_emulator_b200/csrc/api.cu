@@ -1310,6 +1310,15 @@ int mogp_logpost_grad(mogp_handle* h, int32_t idx, double* grad, int32_t n_param
     return mogp_logpost_grad_list(h, &idx, 1, grad, n_params);
 }
 
+int mogp_chol_schedule(int32_t ticket, int32_t n_block_rows, int32_t n_outputs, int32_t* out5) {
+    if (!out5 || n_block_rows < 1 || n_outputs < 1 || ticket < 0 || (int64_t)ticket >= (int64_t)n_outputs * n_block_rows * (n_block_rows + 2))
+        return MOGP_ERR_ARG;
+    int tmp[5];
+    chol_ticket(ticket, n_block_rows, n_outputs, tmp);
+    for (int k = 0; k < 5; k++) out5[k] = tmp[k];
+    return MOGP_OK;
+}
+
 int mogp_trim(void) {
     pool_trim();
     return MOGP_OK;

@@ -409,7 +409,7 @@ struct TileId {
 // bulk of column j's row tiles.  (In plain column order DIAG(j+1) sat behind every ROW tile of column j: with a few matrices
 // per launch -- C3 on 8 GPUs: 4 -- that is more tiles than SMs, and the chain DIAG -> D -> ROW stalled for a wave of row
 // tiles in every column.)  Still a topological order: DIAG(j+1, p) needs ROW(j+1, p, k <= j), all drawn before it.
-__device__ __forceinline__ TileId decode_ticket(int t, int T, int count) {
+__host__ __device__ __forceinline__ TileId decode_ticket(int t, int T, int count) {
     TileId id;
     if (t < 3 * count) {
         id.j = 0; id.i = 0;
@@ -763,6 +763,13 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         __syncwarp();
         if (lane == 0) red_release_gpu_add(prog + 2 * id.i + id.p, 1);
     }
+}
+
+// the schedule, for the host (tests check that it is a permutation of the tiles in a topological order of their dependencies:
+// that order is what makes the spin-waits of the persistent kernel deadlock-free)
+void chol_ticket(int t, int T, int count, int out[5]) {
+    const TileId id = decode_ticket(t, T, count);
+    out[0] = id.kind; out[1] = id.lo; out[2] = id.i; out[3] = id.p; out[4] = id.j;
 }
 
 // kernel attributes are per device: called once per device by mogp_create (api.cu keeps the per-device flag)

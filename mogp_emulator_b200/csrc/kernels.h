@@ -26,6 +26,9 @@ size_t chol_sync_bytes(int count, int T);
 int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, const int* outs, int count,
                       int64_t n_pad, int* info, double* scal, int* sync, int n_sms, cudaStream_t st);
 
+// ticket t of a launch over `count` outputs with T block rows -> {kind (0 DIAG, 1 D, 2 ROW), output, block row i, half p, column j}
+void chol_ticket(int t, int T, int count, int out[5]);
+
 // ---- kmat.cu ----
 int kmat_init();
 int kmat_dbox(int d);

@@ -39,10 +39,11 @@ __device__ const double kExp2Table[32] = {
 
 // exp(x) for x <= 0 to ~1.5 ulp:  x = (32 e + j) ln2/32 + r, |r| <= ln2/64;  exp(x) = 2^e 2^(j/32) (1 + expm1(r)) with a
 // degree-6 expm1 and the 32-entry table above -- 11 FP64 instructions instead of the ~23 DFMA-equivalents of exp()
-// (profiles/r01_probe_fp64.txt; the kernel is bound by the FP64 pipe).  Results below the normal range (x < -708) are flushed
-// to zero (the reference's numpy exp returns denormals there: below 1e-300 either way).
+// (profiles/r01_probe_fp64.txt; the kernel is bound by the FP64 pipe).  x is clamped at -708 (the smallest normal results):
+// below that the reference's numpy exp returns denormals or 0, this returns 3e-308 -- both below 1e-300.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
     const double magic = 6755399441055744.0;                // 1.5 * 2^52
+    x = fmax(x, -708.0);
     const double t = fma(x, 46.16624130844683 /* 32 / ln2 */, magic);
     const int ni = __double2loint(t);                       // round(32 x / ln2), |ni| < 2^16
     const double nd = t - magic;
@@ -56,8 +57,7 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
     const double tj = tab[ni & 31];
     const double v = fma(tj, pm1, tj);                      // in [1, 2)
     const int e = ni >> 5;
-    const double scaled = __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
-    return (x < -708.0) ? 0.0 : scaled;
+    return __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
 }
 
 template <int KT>
@@ -231,6 +231,7 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
                     }
                 }
             } else {
+                const int nvalid = (int)min((int64_t)128, p.n - (int64_t)J * 128);     // training points of this tile
 #pragma unroll
                 for (int a = 0; a < KM_RA; a++) {
                     const int64_t row = (int64_t)I * KM_ROWS + ty + (KM_THREADS / 16) * a;  // test point
@@ -243,7 +244,7 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
                         for (int e = 0; e < 2; e++) {
                             const int c = 2 * tx + 32 * b + e;           // training point inside the tile
                             double w = sigma2 * kfun<KT>(r2[a][2 * b + e], tab_s);
-                            if ((int64_t)J * 128 + c >= p.n) w = 0.0;
+                            if (c >= nvalid) w = 0.0;
                             sdot = fma(w, al_s[c], sdot);
                             v[e] = w;
                         }

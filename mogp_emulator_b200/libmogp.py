@@ -66,6 +66,7 @@ SIGNATURES = {
     "mogp_logpost_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int32]),
     "mogp_loo_variance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _c_double_p]),
     "mogp_timings": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int32]),
+    "mogp_chol_schedule": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _c_int_p]),
     "mogp_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "mogp_comm_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.POINTER(ctypes.c_void_p)]),
@@ -161,6 +162,17 @@ def dptr(a):
 
 def iptr(a):
     return a.ctypes.data_as(_c_int_p)
+
+
+def chol_schedule(n_block_rows, n_outputs):
+    """The tile schedule of the factorisation kernel as a list of (kind, output, i, p, j), kind in ("DIAG", "D", "ROW")."""
+    names = ("DIAG", "D", "ROW")
+    out = np.zeros(5, dtype=np.int32)
+    tiles = []
+    for t in range(n_outputs * n_block_rows * (n_block_rows + 2)):
+        check(_lib.mogp_chol_schedule(t, int(n_block_rows), int(n_outputs), iptr(out)), "mogp_chol_schedule")
+        tiles.append((names[out[0]], int(out[1]), int(out[2]), int(out[3]), int(out[4])))
+    return tiles
 
 
 def trim():

@@ -324,3 +324,30 @@ def test_formula_input_derivatives():
     assert_allclose(d[:, :2], want[:, :2], rtol=1e-13, atol=1e-13)          # complex step: exact to rounding
     assert_allclose(d[:, 2], want[:, 2], rtol=1e-8, atol=1e-8)
     assert MeanFormula("1").input_deriv(X).shape == (11, 3, 1) and not MeanFormula("1").input_deriv(X).any()
+
+
+@pytest.mark.parametrize("T,count", [(1, 1), (1, 5), (2, 3), (3, 1), (8, 4), (32, 4), (33, 1), (64, 2)])
+def test_cholesky_tile_schedule_is_a_topological_permutation(T, count):
+    """chol_dataflow_kernel draws its tiles from a ticket counter and spin-waits on their dependencies: that cannot deadlock
+    only if every dependency of a tile has a SMALLER ticket (it is then held by a running CTA).  The look-ahead order (next
+    column's DIAG / D ahead of the bulk of this column's ROW tiles) is checked here on the CPU through the library's own
+    decode function (mogp_chol_schedule needs no device)."""
+    from mogp_emulator_b200 import libmogp
+    if not libmogp.HAVE_LIBMOGP:
+        pytest.skip("libmogp_b200.so not built")
+    tiles = libmogp.chol_schedule(T, count)
+    assert len(tiles) == count * T * (T + 2) == len(set(tiles))
+    at = {tile: t for t, tile in enumerate(tiles)}
+    n_kind = {"DIAG": 0, "D": 0, "ROW": 0}
+    for t, (kind, lo, i, p, j) in enumerate(tiles):
+        n_kind[kind] += 1
+        assert 0 <= lo < count and 0 <= j <= i < T and p in (0, 1)
+        if kind == "D":
+            assert i == j and at[("DIAG", lo, j, 0, j)] < t and at[("DIAG", lo, j, 1, j)] < t
+        elif kind == "DIAG":
+            assert i == j and all(at[("ROW", lo, j, p, k)] < t for k in range(j))
+        else:
+            assert i > j and at[("D", lo, j, 0, j)] < t
+            for k in range(j):      # own history and both halves of block row j
+                assert at[("ROW", lo, i, p, k)] < t and at[("ROW", lo, j, 0, k)] < t and at[("ROW", lo, j, 1, k)] < t
+    assert n_kind == {"DIAG": 2 * count * T, "D": count * T, "ROW": count * T * (T - 1)}
