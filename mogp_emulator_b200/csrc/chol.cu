@@ -55,20 +55,22 @@ struct Potf2Smem {
     int fail;
 };
 
-// pv = sqrt(d), ri = 1 / pv for a pivot d > 0.  FP64 latency is what bounds the diagonal tile (tools/chol_dtile_timeline.py:
-// sqrt() followed by 1.0 / pv cost ~800 cycles per pivot, 128 pivots per tile on the critical path of every block column), so
-// both come from ONE reciprocal-square-root seed: y = rsqrt(d), then the FMA-corrected square root (pv0 = d y,
-// pv = pv0 + (d - pv0^2) y/2: correctly rounded for a seed accurate to an ulp) and two residual corrections of the reciprocal
-// against that pv (r += r (1 - pv r)): the results of sqrt() and of the IEEE division up to rounding ties.
+// pv = sqrt(d) and ri = 1 / sqrt(d) for a pivot d > 0.  A dependent FP64 instruction costs ~55 cycles on this chip and the
+// pivots of a factorisation are one dependency chain (tools/chol_dtile_timeline.py: sqrt() followed by 1.0 / pv is ~17 dependent
+// operations, 860 cycles per pivot, 128 pivots per diagonal tile on the critical path of every block column).  Only the
+// reciprocal is on that chain (the next pivot needs l = a * ri), so it is taken straight from the refined reciprocal square
+// root -- hardware seed (MUFU.RSQ64H, what sqrt() starts from too) + one third-order step: 4 dependent operations, error
+// below an ulp -- and the square root itself (FMA-corrected d * y, correctly rounded) is computed off the chain.  LAPACK
+// scales by fl(1 / fl(sqrt(d))); this reciprocal differs from that by at most an ulp or two.
 __device__ __forceinline__ void sqrt_and_reciprocal(double d, double& pv, double& ri) {
-    const double y = rsqrt(d);
-    const double pv0 = d * y;
-    const double e = fma(-pv0, pv0, d);
-    pv = fma(e, 0.5 * y, pv0);
-    double r = y;
-    r = fma(fma(-pv, r, 1.0), r, r);
-    r = fma(fma(-pv, r, 1.0), r, r);
-    ri = r;
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+    const double t = y0 * y0;
+    const double e = fma(-d, t, 1.0);                 // 1 - d y0^2
+    const double y1 = fma(fma(e, 0.375, 0.5), y0 * e, y0);      // y0 (1 + e/2 + 3 e^2/8)
+    ri = y1;
+    const double s0 = d * y1;
+    pv = fma(fma(-s0, s0, d), 0.5 * y1, s0);
 }
 
 // (a1) of potf2_inv_block: Cholesky of the 16x16 diagonal sub-block at (j0, j0) by ONE warp.  Lane r (mod 16) owns

@@ -36,20 +36,10 @@
 // error table, oracle/i8_emulation.py the exact CPU emulation of this arithmetic, tools/probe_i8*.cu the instruction probes.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "i8_common.cuh"
 #include "kernels.h"
 
 namespace mogp {
-
-constexpr int I8_BITS = 7;                    // bits per plane (signed digit in [-64, 64])
-constexpr int I8_BN = 64;                     // test points per tile (MMA N per accumulator)
-constexpr int I8_APLANE = NB * 32;            // bytes of one plane of a K = 32 step of L (128 rows)
-constexpr int I8_BPLANE = I8_BN * 32;         // ... of V (64 columns)
-constexpr int I8_NCW = 8;                     // consumer warps
-constexpr int I8_THREADS = (I8_NCW + 3) * 32; // + MMA warp + loader warp + inv(L_ii) loader warp
-constexpr int I8_QN = 4;                      // ticket queue depth
-constexpr int I8_DCHUNK = NB * KC * 8;        // one K chunk (16 columns) of inv(L_ii): 16 KB, K-blocked
-constexpr int I8_NCHECK = 32;                 // test points per output re-solved in FP64 by the a-posteriori accuracy check
 
 // S planes per operand: S = 6 keeps the pairs t + u <= 7 (products resolved to 2^-49 of the two scales), S = 7 the pairs
 // t + u <= 8 (2^-56): the accurate default, see the error table in DESIGN.md
@@ -59,7 +49,6 @@ struct I8Cfg {
     static constexpr int ASTAGE = S * I8_APLANE;
     static constexpr int BSTAGE = S * I8_BPLANE;
     static constexpr int STAGE = ASTAGE + BSTAGE;
-    static constexpr int LBLOCK = 4 * ASTAGE;               // one 128 x 128 block of L: 4 K steps
     static constexpr int VBLOCK = 4 * BSTAGE;               // one 128-row block of V for one panel
     static constexpr int OFF_T = NS * STAGE;                // T_i (FP64, K-blocked, 64 KB); later the plane image of V_i
     static constexpr int OFF_D = OFF_T + NB * I8_BN * 8;    // two chunks of inv(L_ii)
@@ -70,105 +59,6 @@ struct I8Cfg {
     static_assert(SMEM <= 232448, "shared memory per CTA");
     static_assert(VBLOCK <= NB * I8_BN * 8, "the plane image reuses the T buffer");
 };
-
-// byte offset of element (row r, k in [0, 32)) inside a plane of a K = 32 step: K-major, no swizzle, 8 x 16-byte core
-// matrices; leading (K half) byte offset 128, stride (8-row group) byte offset 256 (checked by tools/probe_i8.cu)
-__host__ __device__ __forceinline__ int i8_plane_off(int r, int kk) {
-    return (r >> 3) * 256 + ((kk >> 4) & 1) * 128 + (r & 7) * 16 + (kk & 15);
-}
-
-__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
-}
-// D = s32, A = B = signed 8 bit, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t i8_idesc(int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(NB >> 4) << 24);
-}
-
-// The issuing thread is chosen with elect.sync (common.cuh elect_one_sync): ptxas then knows a single lane is active and
-// moves the operands to uniform registers with plain R2UR; behind `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT /
-// R2UR.BROADCAST / branch loop and the issue thread, not the tensor pipe, set the pace (profiles/r02_i8_timeline_before.txt).
-__device__ __forceinline__ bool i8_elect_one() { return elect_one_sync(); }
-__device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void i8_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void i8_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void i8_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void i8_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void i8_bulk_store(void* dst_global, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void i8_bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// mbarrier wait that traps instead of hanging the GPU if the pipeline protocol is ever violated
-__device__ __forceinline__ void i8_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = globaltimer_ns();
-    while (!mbar_try_wait(bar, parity))
-        if (globaltimer_ns() - t0 > 10000000000ull) __trap();   // 10 s: never in a correct run
-}
-__device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
-        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// S signed 7-bit digits of v 2^-es in [-0.5, 0.5] in INTEGER arithmetic (FP64 instructions share the tensor datapath with the
-// int8 MMAs on this chip -- tools/probe_concurrency.cu -- so the epilogue keeps them to a minimum): q = round(v 2^(7S - es))
-// from the bits of v, then d_t = round(q / 2^(7(S-t))) top down, q -= d_t 2^(7(S-t)).  sum_t d_t 2^-7t = q 2^-7S exactly;
-// |d_t| <= 64 (|d_1| <= 127 for out-of-range input, which degrades instead of wrapping int8).  Differs from the FP64 form
-// below only in how exact ties round.
-template <int S>
-__device__ __forceinline__ void i8_digits_int(double v, int es, int8_t (&dig)[S]) {
-    const long long bits = __double_as_longlong(v);
-    const int e = (int)((bits >> 52) & 0x7FF);
-    const unsigned long long mant = ((unsigned long long)bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
-    int sh = 1075 + es - 7 * S - e;                        // v 2^(7S - es) = mant 2^-sh
-    long long q = 0;
-    if (e != 0 && sh < 64) {
-        sh = sh < 1 ? 1 : sh;                              // (never for |v 2^-es| <= 0.5: sh >= 4)
-        q = (long long)((mant + (1ull << (sh - 1))) >> sh);
-        const long long qmax = 127ll << (7 * (S - 1));
-        q = q > qmax ? qmax : q;
-        q = bits < 0 ? -q : q;
-    }
-#pragma unroll
-    for (int t = 1; t < S; t++) {
-        const int shift = 7 * (S - t);
-        const long long d = (q + (1ll << (shift - 1))) >> shift;
-        q -= d << shift;
-        dig[t - 1] = (int8_t)d;
-    }
-    dig[S - 1] = (int8_t)q;
-}
-
-// The same digits in FP64 (the slicing pass of L, a separate kernel):  x = sum_t d_t 2^-7t + O(2^-(7S+1)), every step exact.
-template <int S>
-__device__ __forceinline__ void i8_digits(double x, int8_t (&dig)[S]) {
-    x = fmin(fmax(x, -0.99), 0.99);        // in-range data has |x| <= 0.5; out-of-range input degrades instead of wrapping int8
-    double y = x;
-#pragma unroll
-    for (int t = 0; t < S; t++) {
-        y *= 128.0;
-        const double dd = rint(y);
-        y -= dd;
-        dig[t] = (int8_t)(int)dd;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // planes of the strictly lower blocks of L (one pass, no arithmetic besides the slicing)
@@ -186,7 +76,6 @@ struct I8SliceParams {
 // run per plane in the K-major core-matrix order tcgen05.mma reads without swizzle
 template <int S>
 __global__ void __launch_bounds__(256) i8_slice_kernel(const I8SliceParams p) {
-    using Cfg = I8Cfg<S>;
     const int b = blockIdx.x;
     int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)b)) * 0.5f);
     while (i * (i - 1) / 2 > b) i--;
@@ -195,7 +84,7 @@ __global__ void __launch_bounds__(256) i8_slice_kernel(const I8SliceParams p) {
     const int o = p.outs[blockIdx.y];
     const double sc = ldexp(1.0, -p.eL[blockIdx.y]);
     const double* Lb = p.A + ((size_t)o * p.n_pad + (size_t)i * NB) * p.n_pad + (size_t)j * NB;
-    int8_t* blk = p.Lq + (size_t)o * p.lq_stride + (size_t)b * Cfg::LBLOCK;
+    int8_t* blk = p.Lq + (size_t)o * p.lq_stride + (size_t)b * I8_LBLOCK;
     const int tid = threadIdx.x, cg = tid & 7;
 #pragma unroll 1
     for (int it = 0; it < 4; it++) {
@@ -217,7 +106,7 @@ __global__ void __launch_bounds__(256) i8_slice_kernel(const I8SliceParams p) {
                 w[t][q >> 1] |= ((uint32_t)(uint8_t)d0[t] | ((uint32_t)(uint8_t)d1[t] << 8)) << (16 * (q & 1));
         }
         // columns cg*16 .. +15: K step cg >> 1, K half cg & 1
-        int8_t* dst = blk + (size_t)(cg >> 1) * Cfg::ASTAGE + (r >> 3) * 256 + (cg & 1) * 128 + (r & 7) * 16;
+        int8_t* dst = blk + (size_t)(cg >> 1) * I8_LSTAGE + (r >> 3) * 256 + (cg & 1) * 128 + (r & 7) * 16;
 #pragma unroll
         for (int t = 0; t < S; t++)
             *reinterpret_cast<uint4*>(dst + (size_t)t * I8_APLANE) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
@@ -269,7 +158,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW, const I8TrsmParams p) {
     using Cfg = I8Cfg<S>;
     constexpr int NS = Cfg::NS, STAGE = Cfg::STAGE, ASTAGE = Cfg::ASTAGE, BSTAGE = Cfg::BSTAGE;
-    constexpr int LBLOCK = Cfg::LBLOCK, VBLOCK = Cfg::VBLOCK;
+    constexpr int VBLOCK = Cfg::VBLOCK;
     extern __shared__ __align__(128) unsigned char i8_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 127) & ~uintptr_t(127));
     double* Ts = reinterpret_cast<double*>(base + Cfg::OFF_T);                       // [16 slabs][64 columns][8]
@@ -347,14 +236,14 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                 wait_counter(flags + tile, i);
                 fence_proxy_async();
                 I8_STAMP(nq, 2);
-                const int8_t* a_src = p.Lq + (size_t)p.outs[o] * p.lq_stride + (size_t)(i * (i - 1) / 2) * LBLOCK;
+                const int8_t* a_src = p.Lq + (size_t)p.outs[o] * p.lq_stride + (size_t)(i * (i - 1) / 2) * I8_LBLOCK;
                 const int8_t* b_src = p.Vq + (size_t)tile * T * VBLOCK;
                 for (int st = 0; st < 4 * i; st++, it++) {
                     const int rs = it % NS;
                     if (it >= NS) i8_wait(&empty[rs], (uint32_t)(((it / NS) - 1) & 1));
                     unsigned char* dst = base + rs * STAGE;
                     mbar_arrive_expect_tx(&full[rs], STAGE);
-                    i8_bulk_load(dst, a_src + (size_t)st * ASTAGE, ASTAGE, &full[rs]);
+                    i8_bulk_load(dst, a_src + (size_t)st * I8_LSTAGE, ASTAGE, &full[rs]);      // the leading S of the stored planes
                     i8_bulk_load(dst + ASTAGE, b_src + (size_t)st * BSTAGE, BSTAGE, &full[rs]);
                 }
                 I8_STAMP(nq, 3);
@@ -694,9 +583,8 @@ int i8_init() {
     return 0;
 }
 
-static size_t lblock(int S) { return S == 6 ? I8Cfg<6>::LBLOCK : I8Cfg<7>::LBLOCK; }
 static size_t vblock(int S) { return S == 6 ? I8Cfg<6>::VBLOCK : I8Cfg<7>::VBLOCK; }
-size_t i8_lq_bytes(int T, int S) { return (size_t)T * (T - 1) / 2 * lblock(S); }
+size_t i8_lq_bytes(int T, int S) { (void)S; return (size_t)T * (T - 1) / 2 * I8_LBLOCK; }
 size_t i8_vq_bytes(int count, int panels, int T, int S) { return (size_t)count * panels * T * vblock(S); }
 int i8_panel_width() { return I8_BN; }
 size_t i8_sync_bytes(int count, int panels) { return sizeof(int) * ((size_t)I8_SYNC_HDR + (size_t)count * panels); }
