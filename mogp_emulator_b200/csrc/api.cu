@@ -45,12 +45,12 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int make_kblocked_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t ld, int box_rows) {
+int make_kblocked_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t ld, int box_rows, int box_kslabs) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 1;
     cuuint64_t gdim[3] = {8, (cuuint64_t)rows, (cuuint64_t)(ld / 8)};
     cuuint64_t gstr[2] = {(cuuint64_t)ld * 8, 64};
-    cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)(KC / 8)};
+    cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_kslabs};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -110,8 +110,13 @@ using namespace mogp;
 
 constexpr int MAXM = 32;  // mean-function vectors per output (grad_max_mean())
 constexpr int I8_DEFAULT_PLANES = 7;   // default of MOGP_TRSM_I8 (see mogp_create)
+// MOGP_CHOL_I8 unset: the Cholesky takes the tcgen05 path when outputs x (block rows)^2 of the launch reaches this.  The
+// history products are ~2 x faster there (profiles/r02_chol_i8_check.txt: 32 x n=4096 24.7 -> 11.9 ms, one n=16384 43.5 -> 23.0 ms),
+// but a launch of a few small matrices is bound by the chain D(j) -> ROW(j+1, ., j) -> DIAG(j+1) -> D(j+1), whose tiles have the
+// longer epilogue on that path (4 x n=4096: 4.05 -> 4.71 ms, one: 3.65 -> 3.92 ms).  Work / chain ~ outputs x T^3 / T.
+constexpr int64_t CHOL_I8_MIN_WORK = 6144;
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H,
-       T_I8_PREP, T_I8_CHECK, T_I8_ROWS, T_I8_NROWS, T_I8_NFALLBACK, T_COUNT };
+       T_I8_PREP, T_I8_CHECK, T_I8_ROWS, T_I8_NROWS, T_I8_NFALLBACK, T_CHOL_I8_N, T_COUNT };
 
 struct mogp_handle {
     int device = 0, n_sms = 148;
@@ -143,6 +148,7 @@ struct mogp_handle {
     std::vector<char> i8_bad;                      // output failed the a-posteriori accuracy check since its last fit: FP64 path
     int use_i8 = 0;                                // planes per operand of the tcgen05 path (6 or 7), 0 = FP64 DMMA path only
     int i8_check = 1;                              // MOGP_I8_CHECK=0 skips the a-posteriori check (diagnostic: to time it)
+    int chol_i8 = 2;                               // Cholesky history products on tcgen05: 0 never, 1 whenever possible, 2 auto (MOGP_CHOL_I8)
     // a-posteriori check of the int8 path: sampled K* rows, their FP64 variances, ticket words / norms of that solve, ratios
     double *chk_W = nullptr, *chk_var = nullptr, *chk_sync = nullptr, *chk_norm = nullptr, *chk_ratio = nullptr, *h_chk_ratio = nullptr;
     size_t chk_W_cap = 0, chk_var_cap = 0, chk_sync_cap = 0, chk_norm_cap = 0, chk_ratio_cap = 0, h_chk_ratio_cap = 0;
@@ -329,6 +335,12 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         else if (e && e[0] == '6') h->use_i8 = 6;
         else if (e && (e[0] == '7' || e[0] == '1')) h->use_i8 = 7;
     }
+    {
+        // MOGP_CHOL_I8 = 0: FP64 DMMA Cholesky only; 1: int8 tcgen05 history products whenever there is a history (n > 128);
+        // default: when the launch is bound by its arithmetic rather than by the chain of diagonal tiles (enqueue_attempt)
+        const char* e = getenv("MOGP_CHOL_I8");
+        h->chol_i8 = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 2);
+    }
     const int64_t np = h->n_pad;
     (void)n_streams;   // kept in the ABI: every phase is one batched launch on the handle's stream, there is nothing to tune
     int rc = MOGP_OK;
@@ -344,7 +356,11 @@ int mogp_create(const double* X, int64_t n, int32_t d, const double* Y, int32_t 
         }                                                                                            \
     } while (0)
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->main, cudaStreamNonBlocking));
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CREATE_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi));
+    }
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreate(&h->ev_a));
@@ -434,7 +450,29 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
         API_CUDA(cudaEventRecord(h->ev_b, h->main));
         int rc;
         if ((rc = grow(&h->csync, &h->csync_cap, chol_sync_bytes(cnt, T), h->device))) return rc;
-        int nl = chol_factor_batch(h->maps, h->A, h->Dinv, og, cnt, np, h->info, h->scal, (int*)h->csync, h->n_sms, h->main);
+        // Many or large factorisations are bound by their O(n^3) history products: those run as exact integer GEMM on the
+        // tcgen05 tensor cores (chol_i8_kernel, 8 signed 7-bit planes per operand), which also leaves the planes of L the predict
+        // TRSM needs.  A few small ones are bound by the chain of diagonal tiles, which is FP64 either way: DMMA kernel.
+        bool ci8 = h->chol_i8 != 0 && T >= 2 && np <= 32768 && (h->chol_i8 == 1 || (int64_t)cnt * T * T >= CHOL_I8_MIN_WORK);
+        if (ci8 && !h->Lq) {
+            h->Lq = (int8_t*)pool_alloc(i8_lq_bytes(T, chol_i8_planes()) * (size_t)h->E, h->device);
+            if (!h->Lq) {
+                cudaGetLastError();
+                ci8 = false;      // no room for the planes: FP64 path
+            }
+        }
+        int nl;
+        if (ci8) {
+            std::vector<int> exps(cnt);
+            for (int i = 0; i < cnt; i++) {
+                const double* hy = h->h_hyper + (size_t)og[i] * (h->d + 2);
+                exps[i] = i8_scale_exponent(hy[h->d], hy[h->d + 1]);
+            }
+            nl = chol_i8_factor_batch(h->maps, h->A, h->Dinv, og, exps.data(), cnt, np, h->Lq, (int64_t)i8_lq_bytes(T, chol_i8_planes()),
+                                      h->info, h->scal, (int*)h->csync, h->n_sms, h->main);
+        } else {
+            nl = chol_factor_batch(h->maps, h->A, h->Dinv, og, cnt, np, h->info, h->scal, (int*)h->csync, h->n_sms, h->main);
+        }
         if (nl < 0) {
             set_error("cholesky launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return MOGP_ERR_CUDA;
@@ -457,6 +495,10 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
         if (h->h_info[h->E]) {
             set_error("Inf enountered in kernel distance computation");      // (sic) the reference's message, Kernel.py:483
             return MOGP_ERR_FPE;
+        }
+        if (ci8) {
+            for (int i = 0; i < cnt; i++) h->lq_valid[og[i]] = (h->h_info[og[i]] == 0) ? 1 : 0;   // the planes of L came with the factor
+            h->timings[T_CHOL_I8_N] += cnt;
         }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
@@ -720,11 +762,10 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     const TrsmPlan cplan{npt, 1};
                     if (h->i8_check) {
                         // FP64 reference variances of the sampled test points (a copy of their K* rows: the FP64 kernel solves in
-                        // place) on the side stream: launched first, they take one SM per output while the persistent integer kernel
-                        // starts on the others and its remaining CTAs join the ticket queue as those SMs free up
-                        API_CUDA(cudaEventRecord(h->ev_fork, h->main));
-                        API_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-                        API_CUDA(cudaEventRecord(h->ev_e, h->side));
+                        // place) on the side stream: they take one SM per output while the persistent integer kernel starts on the
+                        // others and its remaining CTAs join the ticket queue as those SMs free up.  The side stream has the higher
+                        // priority and its kernel is enqueued first, the gather runs on the main stream before the fork: the check
+                        // must reach the SMs before the persistent kernel fills them all (it would otherwise run after it, serially).
                         CUtensorMap tmWc;
                         if ((rc = grow(&h->chk_W, &h->chk_W_cap, sizeof(double) * (size_t)cnt * npt * np, h->device))) return rc;
                         if ((rc = grow(&h->chk_var, &h->chk_var_cap, sizeof(double) * (size_t)h->E * npt, h->device))) return rc;
@@ -736,8 +777,14 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                             set_error("tensor map (check workspace) failed");
                             return MOGP_ERR_CUDA;
                         }
-                        if (i8_check_gather(outs, cnt, h->W, w_stride, np, mc, h->chk_W, h->side) ||
-                            predict_trsm(cplan, outs, cnt, h->maps.a128, h->maps.d128, tmWc, h->chk_W, npt, h->hyper, d, include_nugget, np,
+                        if (i8_check_gather(outs, cnt, h->W, w_stride, np, mc, h->chk_W, h->main)) {
+                            set_error("i8 check launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                            return MOGP_ERR_CUDA;
+                        }
+                        API_CUDA(cudaEventRecord(h->ev_fork, h->main));
+                        API_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                        API_CUDA(cudaEventRecord(h->ev_e, h->side));
+                        if (predict_trsm(cplan, outs, cnt, h->maps.a128, h->maps.d128, tmWc, h->chk_W, npt, h->hyper, d, include_nugget, np,
                                          npt, h->chk_var, npt, 0, (int*)h->chk_sync, h->chk_norm, h->n_sms, h->side, 0,
                                          want_var == 2 ? 1 : 0)) {
                             set_error("i8 check launch failed: %s", cudaGetErrorString(cudaGetLastError()));

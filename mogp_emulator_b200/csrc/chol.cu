@@ -21,7 +21,7 @@
 // memory (red.release / ld.acquire + proxy fences for the TMA readers) order the tiles, nothing deadlocks, and
 // there is no per-step launch, tail or wave quantisation; outputs interleave in the ticket order, so many small
 // factorisations fill the machine as well as one large one.
-#include "common.cuh"
+#include "i8_common.cuh"
 #include "kernels.h"
 
 namespace mogp {
@@ -363,6 +363,63 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
     return 0;
 }
 
+// The D tile: R_jj (written by the two DIAG tiles, possibly on other SMs) -> shared memory, factor + invert (potf2_inv_block),
+// L_jj back to the matrix, inv(L_jj) to the Dinv slab, log-determinant, LAPACK info.  NTHR consumer threads (ctid), `base`:
+// the borrowed shared memory (>= sizeof(Potf2Smem)); named barriers 1 (all NTHR threads), 2 and 3.
+template <int NTHR>
+__device__ __forceinline__ void chol_d_tile(unsigned char* base, int ctid, double* A, double* Dinv, int64_t n_pad, int64_t rb,
+                                            int j, int o, int* info, double* scal, int trs) {
+    (void)trs;
+    Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(base);
+    double* Ablk = A + (rb + (int64_t)j * NB) * n_pad + (int64_t)j * NB;
+    // 16-byte loads, eight in flight per thread (a single 8-byte load per iteration left the 128 KB block waiting on 64
+    // sequential L2 round trips: 16 us)
+    {
+        static_assert(NTHR == 256, "load mapping");
+        const int cp = ctid & 63, r0 = ctid >> 6;          // column pair, first row; rows r0, r0 + 4, ...
+#pragma unroll
+        for (int it = 0; it < 32; it += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int r = r0 + 4 * (it + u);
+                v[u] = (2 * cp <= r) ? __ldcg(reinterpret_cast<const double2*>(Ablk + (int64_t)r * n_pad) + cp)
+                                     : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int r = r0 + 4 * (it + u);
+                sm.S[r * PS + 2 * cp] = (2 * cp <= r) ? v[u].x : 0.0;
+                sm.S[r * PS + 2 * cp + 1] = (2 * cp + 1 <= r) ? v[u].y : 0.0;
+            }
+        }
+    }
+    double ld_add = 0.0;
+#ifdef CHOL_TRACE
+    named_bar_sync(1, NTHR);
+    if (ctid == 0) CH_STAMP(trs, 1);
+#endif
+    const int fail = potf2_inv_block<NTHR, 2>(sm, ctid, Ablk, n_pad, &ld_add);
+#ifdef CHOL_TRACE
+    if (ctid == 0) CH_STAMP(trs, 5);
+#endif
+    if (fail) {
+        if (ctid == 0) info[o] = j * NB + fail;
+    } else {
+        double* Dblk = Dinv + (rb + (int64_t)j * NB) * NB;
+        for (int idx = ctid; idx < NB * NB; idx += NTHR) {
+            const int r = idx >> 7, c = idx & 127;
+            const int b = r >> 4, J = c >> 4;
+            double v = 0.0;
+            if (b == J) v = sm.InvD[(b * SB + (r & 15)) * (SB + 1) + (c & 15)];      // (zero above the diagonal)
+            else if (b > J) v = sm.S[(J * SB + (r & 15)) * PS + b * SB + (c & 15)];   // parked in the upper block (J, b)
+            Dblk[idx] = v;
+        }
+        // the D tiles of one output run strictly in order: plain read-modify-write is race-free
+        if (ctid == 0) scal[2 * o] = (j > 0 ? __ldcg(scal + 2 * o) : 0.0) + ld_add;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the dataflow kernel
 // ------------------------------------------------------------------------------------------
@@ -610,7 +667,9 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
             // the factorisation borrows the ring and the staging buffer: every consumer warp must be done reading them
             // for the previous tile (its last MMA stage, a DIAG tile's write-back) before the first store lands there
             named_bar_sync(1, Cfg::NCW * 32);
-#ifdef CHOL_TRACE
+#ifndef CHOL_TRACE
+            const int trs = -1;
+#else
             __shared__ int tr_slot;
             if (ctid == 0) tr_slot = atomicAdd(&chol_trace_count, 1);
             named_bar_sync(1, Cfg::NCW * 32);
@@ -619,55 +678,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                              unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); chol_trace_cur[sm_ & 255] = trs; }
             named_bar_sync(1, Cfg::NCW * 32);
 #endif
-            if (!skip) {
-                Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(base);
-                double* Ablk = p.A + (rb + (int64_t)j * NB) * p.n_pad + (int64_t)j * NB;
-                // R_jj (written by the two DIAG tiles on other SMs) -> shared memory: 16-byte loads, eight in flight per thread
-                // (a single 8-byte load per iteration left the 128 KB block waiting on 64 sequential L2 round trips: 16 us)
-                {
-                    const int cp = ctid & 63, r0 = ctid >> 6;          // column pair, first row; rows r0, r0 + 4, ...
-#pragma unroll
-                    for (int it = 0; it < 32; it += 8) {
-                        double2 v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const int r = r0 + 4 * (it + u);
-                            v[u] = (2 * cp <= r) ? __ldcg(reinterpret_cast<const double2*>(Ablk + (int64_t)r * p.n_pad) + cp)
-                                                 : make_double2(0.0, 0.0);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const int r = r0 + 4 * (it + u);
-                            sm.S[r * PS + 2 * cp] = (2 * cp <= r) ? v[u].x : 0.0;
-                            sm.S[r * PS + 2 * cp + 1] = (2 * cp + 1 <= r) ? v[u].y : 0.0;
-                        }
-                    }
-                }
-                double ld_add = 0.0;
-#ifdef CHOL_TRACE
-                named_bar_sync(1, Cfg::NCW * 32);
-                if (ctid == 0) CH_STAMP(trs, 1);
-#endif
-                const int fail = potf2_inv_block<Cfg::NCW * 32, 2>(sm, ctid, Ablk, p.n_pad, &ld_add);
-#ifdef CHOL_TRACE
-                if (ctid == 0) CH_STAMP(trs, 5);
-#endif
-                if (fail) {
-                    if (ctid == 0) p.info[o] = j * NB + fail;
-                } else {
-                    double* Dblk = p.Dinv + (rb + (int64_t)j * NB) * NB;
-                    for (int idx = ctid; idx < NB * NB; idx += Cfg::NCW * 32) {
-                        const int r = idx >> 7, c = idx & 127;
-                        const int b = r >> 4, J = c >> 4;
-                        double v = 0.0;
-                        if (b == J) v = sm.InvD[(b * SB + (r & 15)) * (SB + 1) + (c & 15)];      // (zero above the diagonal)
-                        else if (b > J) v = sm.S[(J * SB + (r & 15)) * PS + b * SB + (c & 15)];   // parked in the upper block (J, b)
-                        Dblk[idx] = v;
-                    }
-                    // the D tiles of one output run strictly in order: plain read-modify-write is race-free
-                    if (ctid == 0) p.scal[2 * o] = (j > 0 ? __ldcg(p.scal + 2 * o) : 0.0) + ld_add;
-                }
-            }
+            if (!skip) chol_d_tile<Cfg::NCW * 32>(base, ctid, p.A, p.Dinv, p.n_pad, rb, j, o, p.info, p.scal, trs);
             __threadfence();
             fence_proxy_async();
             named_bar_sync(1, Cfg::NCW * 32);   // everyone is done with the borrowed shared memory
@@ -767,6 +778,456 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// the same factorisation with the trailing updates on the int8 tensor cores (tcgen05)
+// ------------------------------------------------------------------------------------------
+// Same tiles, same ticket order, same progress counters and the same D tile as chol_dataflow_kernel; what changes is where the
+// O(n^3) part -- the history products sum_{k<j} L_jk L_(i,p),k^T of the ROW and DIAG tiles -- is evaluated: as exact integer
+// GEMM on S = 8 signed 7-bit planes per operand (tcgen05.mma kind::i8, s32 accumulators in TMEM; 36 plane pairs t + u <= 9,
+// products resolved to 2^-63 of the squared scale), the error-free splitting of the predict TRSM (trsm_i8.cu) with one more
+// digit (profiles/r01_ozaki_chol_study.txt: 8 digits are indistinguishable from the FP64 blocked factorisation on the
+// ill-conditioned cases, 7 are not).  A ROW tile is exactly a tile of that TRSM whose right-hand side is the panel of L itself:
+//
+//     T = A_(i,p),j^T - 2^(2e) sum_w 2^-7w acc_w          (TMEM -> registers -> the K-blocked buffer A_(i,p),j was TMA-loaded into)
+//     L_(i,p),j^T = inv(L_jj) T                           (FP64 DMMA; inv(L_jj) streamed in 8-column slabs, upper triangle skipped)
+//
+// and its result leaves the SM twice: as FP64 into the matrix (every other kernel of the library reads L in FP64) and as 8
+// digit planes into Lq -- the operands of the later columns of this factorisation AND the planes of L the predict TRSM needs
+// (no slicing pass after the fit).  |L_rc| <= sqrt(K_rr) = sqrt(sigma2 + nugget) gives the one power-of-two scale per output.
+// A DIAG tile stops after T (= its 64 rows of R_jj, written back in FP64); the D tile factors R_jj in FP64 as before.
+// Per CTA (384 threads): warps 0-7 consumers (TMEM drain, FP64 epilogue, D tiles), warp 8 MMA issuer, warp 9 tickets + plane
+// loader (progress-counter waits, cp.async.bulk into a 3-stage ring), warp 10 loader of the A tile and of inv(L_jj).
+constexpr int CHOL_I8_PLANES = 8;
+
+template <int S>
+struct CholI8Cfg {
+    static constexpr int NS = 3;
+    static constexpr int ASTAGE = S * I8_APLANE;            // planes of L_jk, one K = 32 step (128 rows)
+    static constexpr int BSTAGE = S * I8_BPLANE;            // planes of the tile's own 64 rows
+    static constexpr int STAGE = ASTAGE + BSTAGE;
+    static constexpr int OFF_T = NS * STAGE;                // T (FP64, K-blocked [16][64][8]); later the plane image [4][S][2048]
+    static constexpr int DSLAB = NB * 8 * 8;                // one 8-column K slab of inv(L_jj): 8 KB
+    static constexpr int OFF_D = OFF_T + NB * I8_BN * 8;
+    static constexpr int OFF_BAR = OFF_D + 2 * DSLAB;
+    static constexpr int SMEM = OFF_BAR + 256 + 128;
+    static constexpr int THREADS = (I8_NCW + 4) * 32;       // three role warps + one idle warp: setmaxnreg works on warpgroups
+    static_assert(S <= I8_LP && S * I8_BN <= 512, "planes / TMEM columns");
+    static_assert(4 * BSTAGE <= NB * I8_BN * 8, "the plane image reuses the T buffer");
+    static_assert((int)sizeof(Potf2Smem) <= OFF_D, "the D tile borrows the ring and the T buffer");
+    static_assert(SMEM <= 232448, "shared memory per CTA");
+};
+
+struct CholI8Params {
+    CholParams c;
+    int8_t* Lq;             // [E][lq_stride] planes of the strictly lower blocks of L
+    int64_t lq_stride;
+    int eS[MAXG];           // scale exponent per listed output: |L| 2^-eS <= 0.99
+};
+
+template <int S>
+__global__ void __launch_bounds__(CholI8Cfg<S>::THREADS, 1)
+chol_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD8, const CholI8Params pp) {
+    using Cfg = CholI8Cfg<S>;
+    constexpr int NS = Cfg::NS, STAGE = Cfg::STAGE, ASTAGE = Cfg::ASTAGE, BSTAGE = Cfg::BSTAGE, DSLAB = Cfg::DSLAB;
+    constexpr int SKIP = 1 << 30;
+    const CholParams& p = pp.c;
+    extern __shared__ __align__(128) unsigned char chol_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(chol_smem_raw) + 127) & ~uintptr_t(127));
+    double* Ts = reinterpret_cast<double*>(base + Cfg::OFF_T);                       // [16 slabs][64 rows of the panel][8]
+    unsigned char* img = base + Cfg::OFF_T;                                          // [4 K steps][S planes][2048]
+    unsigned char* dring = base + Cfg::OFF_D;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + Cfg::OFF_BAR);               // [NS]
+    uint64_t* empty = full + NS;                                                     // [NS]
+    uint64_t* acc_full = empty + NS;
+    uint64_t* acc_empty = acc_full + 1;
+    uint64_t* d_full = acc_empty + 1;                                                // [2]
+    uint64_t* d_empty = d_full + 2;                                                  // [2]
+    uint64_t* ts_full = d_empty + 2;                                                 // the A tile has landed in the T buffer
+    uint64_t* ts_free = ts_full + 1;                                                 // the T buffer (R written back / plane image read) is free
+    uint64_t* tq_full = ts_free + 1;                                                 // [QN]
+    uint64_t* tq_empty = tq_full + I8_QN;                                            // [QN]
+    uint64_t* d_done = tq_empty + I8_QN;                                             // [2]: a D tile is done with the borrowed memory (one per loader warp)
+    int* tq = reinterpret_cast<int*>(d_done + 2);                                    // [QN]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tq + I8_QN);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int T = p.T;
+    const int total = p.count * T * (T + 2);
+    const int blk = 2 * T + 8;   // ints per output in the progress area: prog[T][2] (blocks finished per row half), dprog
+
+    if (warp == I8_NCW) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, I8_NCW);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], I8_NCW);
+            mbar_init(&d_done[s], I8_NCW);
+        }
+        mbar_init(ts_full, 1);
+        mbar_init(ts_free, 1);
+        for (int s = 0; s < I8_QN; s++) {
+            mbar_init(&tq_full[s], 1);
+            mbar_init(&tq_empty[s], I8_NCW + 2);     // consumer warps + MMA issuer + A-tile / inv(L_jj) loader
+        }
+        fence_mbar_init();
+    }
+    i8_fence_before();
+    __syncthreads();
+    i8_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= I8_NCW) {
+        reg_dealloc<72>();
+        if (warp == I8_NCW + 1) {
+            // ================================ tickets + plane loader ================================
+            if (i8_elect_one()) {
+                int it = 0, dseq = 0;
+                for (int nq = 0;; nq++) {
+                    const int slot = nq % I8_QN;
+                    i8_wait(&tq_empty[slot], (uint32_t)(((nq / I8_QN) & 1) ^ 1));
+                    const int t = atomicAdd(p.sync, 1);
+                    if (t >= total) {
+                        tq[slot] = -1;
+                        mbar_arrive(&tq_full[slot]);
+                        break;
+                    }
+                    const TileId id = decode_ticket(t, T, p.count);
+                    const int o = p.outs[id.lo];
+                    int* prog = p.sync + CH_HDR + id.lo * blk;
+                    const int j = id.j;
+                    if (id.kind == TK_D) {
+                        // both halves of R_jj are in place (ROW tiles of the block row + its DIAG tile: j + 1 per half)
+                        wait_counter(prog + 2 * j, j + 1);
+                        wait_counter(prog + 2 * j + 1, j + 1);
+                        const bool skip = ld_acquire_gpu(p.info + o) != 0;
+                        tq[slot] = t | (skip ? SKIP : 0);
+                        mbar_arrive(&tq_full[slot]);
+                        // the D tile borrows the ring and the T buffer: nothing may be in flight into them
+                        i8_wait(&d_done[0], (uint32_t)(dseq & 1));
+                        dseq++;
+                        continue;
+                    }
+                    const bool skip = ld_acquire_gpu(p.info + o) != 0;   // a failed output only bumps its counters
+                    tq[slot] = t | (skip ? SKIP : 0);
+                    mbar_arrive(&tq_full[slot]);
+                    if (skip || j == 0) continue;
+                    const int8_t* lq = pp.Lq + (size_t)o * pp.lq_stride;
+                    const int8_t* a_src = lq + (size_t)(j * (j - 1) / 2) * I8_LBLOCK;                           // blocks (j, k)
+                    const int8_t* b_src = lq + (size_t)(id.i * (id.i - 1) / 2) * I8_LBLOCK + id.p * I8_BPLANE;  // blocks (i, k), rows of half p
+                    int* prog_own = prog + 2 * id.i + id.p;
+                    const bool all_ready = ld_acquire_gpu(prog_own) >= j && ld_acquire_gpu(prog + 2 * j) >= j &&
+                                           ld_acquire_gpu(prog + 2 * j + 1) >= j;
+                    if (all_ready) fence_proxy_async();
+                    for (int k = 0; k < j; k++) {
+                        if (!all_ready) {
+                            wait_counter(prog_own, k + 1);
+                            wait_counter(prog + 2 * j, k + 1);
+                            wait_counter(prog + 2 * j + 1, k + 1);
+                            fence_proxy_async();
+                        }
+                        for (int s = 0; s < 4; s++, it++) {
+                            const int rs = it % NS;
+                            if (it >= NS) i8_wait(&empty[rs], (uint32_t)(((it / NS) - 1) & 1));
+                            unsigned char* dst = base + rs * STAGE;
+                            const size_t off = (size_t)(4 * k + s) * I8_LSTAGE;
+                            mbar_arrive_expect_tx(&full[rs], STAGE);
+                            i8_bulk_load(dst, a_src + off, ASTAGE, &full[rs]);
+#pragma unroll
+                            for (int tt = 0; tt < S; tt++)
+                                i8_bulk_load(dst + ASTAGE + tt * I8_BPLANE, b_src + off + (size_t)tt * I8_APLANE, I8_BPLANE, &full[rs]);
+                        }
+                    }
+                }
+            }
+        } else if (warp == I8_NCW + 2) {
+            // ================================ A tile and inv(L_jj) loader ================================
+            if (i8_elect_one()) {
+                prefetch_tmap(&tmD8);
+                prefetch_tmap(&tmW);
+                int tseq = 0, dc = 0, dseq = 0;
+                for (int nq = 0;; nq++) {
+                    const int slot = nq % I8_QN;
+                    i8_wait(&tq_full[slot], (uint32_t)((nq / I8_QN) & 1));
+                    const int tw = tq[slot];
+                    mbar_arrive(&tq_empty[slot]);
+                    if (tw < 0) break;
+                    const TileId id = decode_ticket(tw & (SKIP - 1), T, p.count);
+                    if (id.kind == TK_D) {
+                        i8_wait(&d_done[1], (uint32_t)(dseq & 1));
+                        dseq++;
+                        continue;
+                    }
+                    const int j = id.j;
+                    if ((tw & SKIP) || (id.kind == TK_DIAG && j == 0)) continue;
+                    const int o = p.outs[id.lo];
+                    const int rb = (int)(o * p.n_pad);
+                    const int wrow = rb + id.i * NB + id.p * I8_BN;
+                    if (tseq > 0) i8_wait(ts_free, (uint32_t)((tseq - 1) & 1));
+                    tseq++;
+                    mbar_arrive_expect_tx(ts_full, NB * I8_BN * 8);
+                    for (int c2 = 0; c2 < NB / KC; c2++)
+                        tma_load_3d(Ts + c2 * (KC / 8) * I8_BN * 8, &tmW, 0, wrow, j * (NB / 8) + c2 * (KC / 8), ts_full);
+                    if (id.kind == TK_ROW) {
+                        const int* dprog = p.sync + CH_HDR + id.lo * blk + 2 * T;
+                        wait_counter(dprog, j + 1);          // inv(L_jj): published by the D tile of column j
+                        fence_proxy_async();
+                        for (int ch = 0; ch < NB / 8; ch++, dc++) {
+                            const int ds = dc & 1;
+                            if (dc >= 2) i8_wait(&d_empty[ds], (uint32_t)(((dc >> 1) - 1) & 1));
+                            mbar_arrive_expect_tx(&d_full[ds], DSLAB);
+                            tma_load_3d(dring + ds * DSLAB, &tmD8, 0, rb + j * NB, ch, &d_full[ds]);
+                        }
+                    }
+                }
+            }
+        } else if (warp == I8_NCW) {
+            // ================================ MMA issuer (one elected thread) ================================
+            if (i8_elect_one()) {
+                int it = 0, k = 0;
+                for (int nq = 0;; nq++) {
+                    const int slot = nq % I8_QN;
+                    i8_wait(&tq_full[slot], (uint32_t)((nq / I8_QN) & 1));
+                    const int tw = tq[slot];
+                    mbar_arrive(&tq_empty[slot]);
+                    if (tw < 0) break;
+                    if (tw & SKIP) continue;
+                    const TileId id = decode_ticket(tw, T, p.count);
+                    if (id.kind == TK_D || id.j == 0) continue;
+                    if (k > 0) {          // the consumers must have drained the accumulators of the previous tile
+                        i8_wait(acc_empty, (uint32_t)((k - 1) & 1));
+                        i8_fence_after();
+                    }
+                    k++;
+                    for (int st = 0; st < 4 * id.j; st++, it++) {
+                        const int rs = it % NS;
+                        i8_wait(&full[rs], (uint32_t)((it / NS) & 1));
+                        i8_fence_after();
+                        const uint32_t a0 = smem_u32(base + rs * STAGE), b0 = a0 + ASTAGE;
+                        const uint64_t bd0 = i8_desc(b0), bd1 = i8_desc(b0 + 4 * I8_BPLANE);
+#pragma unroll
+                        for (int tt = 1; tt <= S; tt++) {
+                            const int ncols = I8_BN * (S + 1 - tt);
+                            const uint32_t accum = (st == 0 && tt == 1) ? 0u : 1u;
+                            const uint32_t d0 = tmem + (uint32_t)(tt - 1) * I8_BN;
+                            const uint64_t ad = i8_desc(a0 + (tt - 1) * I8_APLANE);
+                            const int n1 = ncols > 256 ? 256 : ncols;
+                            i8_mma(d0, ad, bd0, accum, i8_idesc(n1));
+                            if (ncols > 256) i8_mma(d0 + 256, ad, bd1, accum, i8_idesc(ncols - 256));
+                        }
+                        i8_commit(&empty[rs]);
+                    }
+                    i8_commit(acc_full);
+                }
+            }
+        }
+    } else {
+        // ================================ consumers ================================
+        reg_alloc<216>();
+        const int q4 = warp & 3, h = warp >> 2;
+        const int r = q4 * 32 + lane;             // column inside block j = TMEM lane
+        const int g = lane >> 2, t4 = lane & 3;   // DMMA fragment coordinates
+        int k = 0, dc = 0, tseq = 0;
+        for (int nq = 0;; nq++) {
+            const int slot = nq % I8_QN;
+            i8_wait(&tq_full[slot], (uint32_t)((nq / I8_QN) & 1));
+            const int tw = tq[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tq_empty[slot]);
+            if (tw < 0) break;
+            const bool skip = (tw & SKIP) != 0;
+            const TileId id = decode_ticket(tw & (SKIP - 1), T, p.count);
+            const int o = p.outs[id.lo];
+            int* prog = p.sync + CH_HDR + id.lo * blk;
+            int* dprog = prog + 2 * T;
+            const int j = id.j;
+            const int64_t rb = (int64_t)o * p.n_pad;
+
+            if (id.kind == TK_D) {
+                // every consumer warp is done with the previous tile (the barrier that ends every tile), its MMAs have completed
+                // (acc_full) and both loader warps are parked on d_done: the ring and the T buffer are free to borrow
+                named_bar_sync(1, I8_NCW * 32);
+                if (!skip) chol_d_tile<I8_NCW * 32>(base, tid, p.A, p.Dinv, p.n_pad, rb, j, o, p.info, p.scal, -1);
+                __threadfence();
+                fence_proxy_async();
+                named_bar_sync(1, I8_NCW * 32);
+                if (tid == 0) red_release_gpu_add(dprog, 1);
+                if (lane == 0) {
+                    mbar_arrive(&d_done[0]);
+                    mbar_arrive(&d_done[1]);
+                }
+                continue;
+            }
+            int* prog_own = prog + 2 * id.i + id.p;
+            if (skip || (id.kind == TK_DIAG && j == 0)) {      // (R_00 = A_00 is in place)
+                if (tid == 0) red_release_gpu_add(prog_own, 1);
+                continue;
+            }
+            const int es = pp.eS[id.lo];
+            const int64_t wrow = rb + (int64_t)id.i * NB + id.p * I8_BN;
+
+            // ---- T = A_(i,p),j^T - 2^(2 es) sum_w 2^-7w acc_w, in place in the K-blocked buffer the A tile was loaded into ----
+            if (j > 0) {
+                long long hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) hi[c] = lo[c] = 0;
+                i8_wait(acc_full, (uint32_t)(k & 1));
+                k++;
+                i8_fence_after();
+#pragma unroll
+                for (int w = 0; w < S; w++) {
+                    uint32_t v[32];
+                    i8_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(w * I8_BN + h * 32), v);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        if (w < 4) hi[c] += (long long)(int32_t)v[c] << (I8_BITS * (3 - w));
+                        else lo[c] += (long long)(int32_t)v[c] << (I8_BITS * (S - 1 - w));
+                    }
+                }
+                i8_fence_before();
+                double acc[32];
+                {
+                    const double whi = __longlong_as_double((long long)(1023 - I8_BITS * 5) << 52);         // accumulator 3: 2^-35
+                    const double wlo = __longlong_as_double((long long)(1023 - I8_BITS * (S + 1)) << 52);   // accumulator S-1
+#pragma unroll
+                    for (int c = 0; c < 32; c++) acc[c] = fma((double)lo[c], wlo, (double)hi[c] * whi);
+                }
+                i8_wait(ts_full, (uint32_t)(tseq & 1));
+                const double nscale = -ldexp(1.0, 2 * es);
+                const int odd = (lane >> 3) & 1;
+                double* trow = Ts + (size_t)(r >> 3) * I8_BN * 8 + (size_t)h * 32 * 8 + (r & 7);
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const double va = odd ? acc[c + 1] : acc[c], vb = odd ? acc[c] : acc[c + 1];
+                    double* pa = trow + (c + odd) * 8;
+                    double* pb = trow + (c + 1 - odd) * 8;
+                    *pa = fma(va, nscale, *pa);
+                    *pb = fma(vb, nscale, *pb);
+                }
+            } else {
+                i8_wait(ts_full, (uint32_t)(tseq & 1));
+            }
+            tseq++;
+            named_bar_sync(1, I8_NCW * 32);
+
+            if (id.kind == TK_DIAG) {
+                if (lane == 0) mbar_arrive(acc_empty);          // (j > 0 here)
+                // R (64 rows of the diagonal block) back in place: 64-byte segments (8 columns of one row) per thread
+                for (int idx = tid; idx < (NB / 8) * I8_BN; idx += I8_NCW * 32) {
+                    const int k8 = idx / I8_BN, rr = idx - k8 * I8_BN;
+                    const double2* src = reinterpret_cast<const double2*>(Ts + (size_t)idx * 8);
+                    double2* dst = reinterpret_cast<double2*>(p.A + (wrow + rr) * p.n_pad + (int64_t)j * NB + k8 * 8);
+                    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                }
+                __threadfence();
+                named_bar_sync(1, I8_NCW * 32);
+                if (tid == 0) {
+                    mbar_arrive(ts_free);
+                    red_release_gpu_add(prog_own, 1);
+                }
+                continue;
+            }
+
+            // ---- L_(i,p),j^T = inv(L_jj) T : warp w owns the panel rows 8 w .. 8 w + 7 and all 128 columns of block j ----
+            double vf[8][4];
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) vf[mt][e] = 0.0;
+#pragma unroll
+            for (int ch = 0; ch < NB / 8; ch++, dc++) {
+                const int ds = dc & 1;
+                i8_wait(&d_full[ds], (uint32_t)((dc >> 1) & 1));
+                const double* As = reinterpret_cast<const double*>(dring + ds * DSLAB);
+                const double2 bf = *reinterpret_cast<const double2*>(Ts + ((size_t)ch * I8_BN + warp * 8 + g) * 8 + 2 * t4);
+#pragma unroll
+                for (int mt = ch >> 1; mt < 8; mt++) {         // inv(L_jj) is lower triangular: rows 16 mt .. need columns <= 16 mt + 15
+                    const double* ap = As + ((size_t)(mt * 16 + g) * 8 + 2 * t4);
+                    const double2 a0 = *reinterpret_cast<const double2*>(ap);
+                    const double2 a1 = *reinterpret_cast<const double2*>(ap + 64);
+                    dmma_16x8x8(vf[mt], a0.x, a1.x, a0.y, a1.y, bf.x, bf.y);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[ds]);
+            }
+            named_bar_sync(1, I8_NCW * 32);       // every warp is done reading T: the buffer becomes the plane image
+            // FP64 and int8 MMAs share one datapath (tools/probe_concurrency.cu): the accumulators go back to the MMA warp only
+            // after the FP64 part, as in the predict TRSM
+            if (j > 0 && lane == 0) mbar_arrive(acc_empty);
+
+            // ---- FP64 copy of the tile: element (column c of block j, panel row rr) -> A[wrow + rr][j NB + c] ----
+            // vf[mt][e]: c = 16 mt + g (+ 8 for e >= 2), rr = 8 warp + 2 t4 (+ 1 for odd e)
+#pragma unroll
+            for (int e1 = 0; e1 < 2; e1++) {
+                double* wr = p.A + (wrow + warp * 8 + 2 * t4 + e1) * p.n_pad + (int64_t)j * NB + g;
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++) {
+                    wr[mt * 16] = vf[mt][e1];
+                    wr[mt * 16 + 8] = vf[mt][2 + e1];
+                }
+            }
+            // ---- its S digit planes: byte (column c, panel row rr, plane tt) of the image at K step c / 32, then plane, then
+            //      (rr / 8) 256 + (c / 16 % 2) 128 + (rr % 8) 16 + c % 16 (4 x 4 byte transposes by shuffle, see trsm_i8.cu) ----
+            {
+                const int jj = g & 3;
+                unsigned char* ib = img + warp * 256 + (2 * t4 + (jj & 1)) * 16 + (g >> 2) * 4 + (jj >> 1) * 8;
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++) {
+                    int8_t dig[4][S];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) i8_digits_int<S>(vf[mt][e], es, dig[e]);
+                    unsigned char* dst = ib + (size_t)(mt >> 1) * BSTAGE + (mt & 1) * 128;
+#pragma unroll
+                    for (int tt = 0; tt < S; tt++) {
+                        uint32_t x = (uint32_t)(uint8_t)dig[0][tt] | ((uint32_t)(uint8_t)dig[1][tt] << 8) |
+                                     ((uint32_t)(uint8_t)dig[2][tt] << 16) | ((uint32_t)(uint8_t)dig[3][tt] << 24);
+                        uint32_t y = __shfl_xor_sync(0xffffffffu, x, 4);
+                        x = __byte_perm(x, y, (jj & 1) ? 0x3715 : 0x6240);
+                        y = __shfl_xor_sync(0xffffffffu, x, 8);
+                        x = __byte_perm(x, y, (jj & 2) ? 0x3276 : 0x5410);
+                        *reinterpret_cast<uint32_t*>(dst + tt * I8_BPLANE) = x;
+                    }
+                }
+                fence_proxy_async();              // generic-proxy writes of the image -> the bulk stores' async-proxy reads
+            }
+            __threadfence();                      // the FP64 copy
+            named_bar_sync(1, I8_NCW * 32);
+            if (tid == 0) {
+                // the 64 rows of half p of every (K step, plane) of block (i, j): 2 KB pieces of the 4 KB planes
+                int8_t* dstb = pp.Lq + (size_t)o * pp.lq_stride + (size_t)(id.i * (id.i - 1) / 2 + j) * I8_LBLOCK + id.p * I8_BPLANE;
+#pragma unroll 1
+                for (int s4 = 0; s4 < 4; s4++)
+#pragma unroll 1
+                    for (int tt = 0; tt < S; tt++)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(dstb + (size_t)s4 * I8_LSTAGE + (size_t)tt * I8_APLANE),
+                                       "r"(smem_u32(img + (s4 * S + tt) * I8_BPLANE)), "r"(I8_BPLANE) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the image has been read: the next A tile may land
+                mbar_arrive(ts_free);
+                i8_bulk_store_wait();                                             // the planes are in global memory
+                fence_proxy_async();
+                __threadfence();
+                red_release_gpu_add(prog_own, 1);
+            }
+        }
+    }
+    i8_fence_before();
+    __syncthreads();
+    if (warp == I8_NCW) {
+        i8_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    }
+}
+
 // the schedule, for the host (tests check that it is a permutation of the tiles in a topological order of their dependencies:
 // that order is what makes the spin-waits of the persistent kernel deadlock-free)
 void chol_ticket(int t, int T, int count, int out[5]) {
@@ -777,7 +1238,9 @@ void chol_ticket(int t, int T, int count, int out[5]) {
 // kernel attributes are per device: called once per device by mogp_create (api.cu keeps the per-device flag)
 int chol_init() {
     if (cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CholCfg::SMEM_BYTES) !=
-        cudaSuccess)
+            cudaSuccess ||
+        cudaFuncSetAttribute(chol_i8_kernel<CHOL_I8_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             CholI8Cfg<CHOL_I8_PLANES>::SMEM) != cudaSuccess)
         return 1;
     return 0;
 }
@@ -786,6 +1249,7 @@ int chol_make_maps(CholMaps* maps, double* A_slab, double* Dinv_slab, int64_t to
     if (make_kblocked_tmap(&maps->a128, A_slab, total_rows, n_pad, 128)) return 1;
     if (make_kblocked_tmap(&maps->a64, A_slab, total_rows, n_pad, 64)) return 1;
     if (make_kblocked_tmap(&maps->d128, Dinv_slab, total_rows, NB, 128)) return 1;
+    if (make_kblocked_tmap(&maps->d8, Dinv_slab, total_rows, NB, 128, 1)) return 1;
     return 0;
 }
 
@@ -807,6 +1271,30 @@ int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, c
     if (cudaGetLastError() != cudaSuccess) return -1;
     return 1;
 }
+
+// The same factorisation with the history products on the int8 tensor cores; also leaves the planes of the strictly lower
+// blocks of L in Lq (exps[k]: i8_scale_exponent of outs[k] with the nugget of this attempt).
+int chol_i8_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, const int* outs, const int* exps, int count,
+                         int64_t n_pad, int8_t* Lq, int64_t lq_stride, int* info, double* scal, int* sync, int n_sms,
+                         cudaStream_t st) {
+    if (count < 1 || count > MAXG) return -1;
+    CholI8Params pp{};
+    CholParams& p = pp.c;
+    p.A = A_slab; p.Dinv = Dinv_slab; p.n_pad = n_pad; p.T = (int)(n_pad / NB); p.count = count;
+    for (int i = 0; i < count; i++) {
+        p.outs[i] = outs[i];
+        pp.eS[i] = exps[i];
+    }
+    p.info = info; p.scal = scal; p.sync = sync;
+    pp.Lq = Lq; pp.lq_stride = lq_stride;
+    if (cudaMemsetAsync(sync, 0, chol_sync_bytes(count, p.T), st) != cudaSuccess) return -1;
+    const int64_t tiles = (int64_t)count * p.T * (p.T + 2);
+    const unsigned grid = (unsigned)(tiles < n_sms ? tiles : n_sms);
+    chol_i8_kernel<CHOL_I8_PLANES><<<grid, CholI8Cfg<CHOL_I8_PLANES>::THREADS, CholI8Cfg<CHOL_I8_PLANES>::SMEM, st>>>(maps.a64, maps.d8, pp);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return 1;
+}
+int chol_i8_planes() { return CHOL_I8_PLANES; }
 
 }  // namespace mogp
 

@@ -203,8 +203,8 @@ struct PipeState {
 void set_error(const char* fmt, ...);
 
 // K-blocked 3-D tensor map over a row-major FP64 matrix M[rows][ld]: dims (8, rows, ld/8),
-// box (8, box_rows, KC/8).  Returns 0 on success.
-int make_kblocked_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t ld, int box_rows);
+// box (8, box_rows, box_kslabs).  Returns 0 on success.
+int make_kblocked_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t ld, int box_rows, int box_kslabs = KC / 8);
 // 2-D tensor map over a row-major FP64 matrix M[rows][cols] (cols contiguous): box (box_cols, box_rows)
 int make_2d_tmap(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                  int box_cols);

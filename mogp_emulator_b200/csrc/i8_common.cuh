@@ -78,7 +78,7 @@ __device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// S signed 7-bit digits of v 2^-es in [-0.5, 0.5] in INTEGER arithmetic (FP64 instructions share the tensor datapath with the
+// S signed 7-bit digits of v 2^-es in [-0.99, 0.99] in INTEGER arithmetic (FP64 instructions share the tensor datapath with the
 // int8 MMAs on this chip -- tools/probe_concurrency.cu -- so the epilogue keeps them to a minimum): q = round(v 2^(7S - es))
 // from the bits of v, then d_t = round(q / 2^(7(S-t))) top down, q -= d_t 2^(7(S-t)).  sum_t d_t 2^-7t = q 2^-7S exactly;
 // |d_t| <= 64 (|d_1| <= 127 for out-of-range input, which degrades instead of wrapping int8).  Differs from the FP64 form
@@ -88,12 +88,13 @@ __device__ __forceinline__ void i8_digits_int(double v, int es, int8_t (&dig)[S]
     const long long bits = __double_as_longlong(v);
     const int e = (int)((bits >> 52) & 0x7FF);
     const unsigned long long mant = ((unsigned long long)bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
-    int sh = 1075 + es - 7 * S - e;                        // v 2^(7S - es) = mant 2^-sh
+    const int sh = 1075 + es - 7 * S - e;                  // v 2^(7S - es) = mant 2^-sh; |v 2^-es| < 1: sh >= 53 - 7 S
     long long q = 0;
     if (e != 0 && sh < 64) {
-        sh = sh < 1 ? 1 : sh;                              // (never for |v 2^-es| <= 0.5: sh >= 4)
-        q = (long long)((mant + (1ull << (sh - 1))) >> sh);
         const long long qmax = 127ll << (7 * (S - 1));
+        if (sh >= 1) q = (long long)((mant + (1ull << (sh - 1))) >> sh);
+        else if (sh >= -9) q = (long long)(mant << (-sh));  // S = 8: the grid 2^-56 is finer than the ulp of the large entries (exact)
+        else q = qmax;                                     // far out of range (or NaN / inf)
         q = q > qmax ? qmax : q;
         q = bits < 0 ? -q : q;
     }
@@ -110,7 +111,7 @@ __device__ __forceinline__ void i8_digits_int(double v, int es, int8_t (&dig)[S]
 // The same digits in FP64 (the slicing pass of L, a separate kernel):  x = sum_t d_t 2^-7t + O(2^-(7S+1)), every step exact.
 template <int S>
 __device__ __forceinline__ void i8_digits(double x, int8_t (&dig)[S]) {
-    x = fmin(fmax(x, -0.99), 0.99);        // in-range data has |x| <= 0.5; out-of-range input degrades instead of wrapping int8
+    x = fmin(fmax(x, -0.99), 0.99);        // in-range data has |x| <= 0.99; out-of-range input degrades instead of wrapping int8
     double y = x;
 #pragma unroll
     for (int t = 0; t < S; t++) {

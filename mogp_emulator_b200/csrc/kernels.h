@@ -12,6 +12,7 @@ struct CholMaps {
     CUtensorMap a128;  // K-blocked map over the matrix slab [E*n_pad][n_pad], box 128 rows
     CUtensorMap a64;   // same slab, box 64 rows
     CUtensorMap d128;  // K-blocked map over the Dinv slab [E*n_pad][128], box 128 rows
+    CUtensorMap d8;    // same slab, box 128 rows x one 8-column K slab
 };
 
 // per-output hyperparameters in device memory: [w_0 .. w_{d-1}, sigma2, nugget]
@@ -25,6 +26,13 @@ size_t chol_sync_bytes(int count, int T);
 // must be zero.  Returns #launches or -1.
 int chol_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, const int* outs, int count,
                       int64_t n_pad, int* info, double* scal, int* sync, int n_sms, cudaStream_t st);
+
+// the same with the history products on the int8 tensor cores (tcgen05, 8 planes per operand); also writes the planes of the
+// strictly lower blocks of L to Lq (layout of i8_slice_L; exps[k] = i8_scale_exponent of outs[k])
+int chol_i8_factor_batch(const CholMaps& maps, double* A_slab, double* Dinv_slab, const int* outs, const int* exps, int count,
+                         int64_t n_pad, int8_t* Lq, int64_t lq_stride, int* info, double* scal, int* sync, int n_sms,
+                         cudaStream_t st);
+int chol_i8_planes();
 
 // ticket t of a launch over `count` outputs with T block rows -> {kind (0 DIAG, 1 D, 2 ROW), output, block row i, half p, column j}
 void chol_ticket(int t, int T, int count, int out[5]);
@@ -73,7 +81,7 @@ size_t i8_lq_bytes(int T, int S);                           // planes of L per o
 size_t i8_vq_bytes(int count, int panels, int T, int S);    // planes of V for one batched call
 size_t i8_sync_bytes(int count, int panels);                // ticket counter + per-panel progress words
 int i8_panel_width();
-// exponent e of the common power-of-two scale of L and V of one output: sqrt(sigma2 + nugget) <= 2^(e-1)
+// exponent e of the common power-of-two scale of L and V of one output: sqrt(sigma2 + nugget) <= 0.99 2^e
 int i8_scale_exponent(double sigma2, double nugget);
 // planes of the strictly lower 128 x 128 blocks of L of the listed outputs (exps[k] = i8_scale_exponent of outs[k])
 int i8_slice_L(int S, const double* A_slab, int64_t n_pad, const int* outs, const int* exps, int count, int8_t* Lq,

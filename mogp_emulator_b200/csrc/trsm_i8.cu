@@ -67,7 +67,7 @@ struct I8SliceParams {
     const double* A;       // L slab [E][n_pad][n_pad]
     int64_t n_pad;
     int outs[MAXG];
-    int eL[MAXG];          // scale exponent per listed output: L 2^-eL in [-0.5, 0.5]
+    int eL[MAXG];          // scale exponent per listed output: L 2^-eL in [-0.99, 0.99]
     int8_t* Lq;            // [E][lq_stride]
     int64_t lq_stride;
 };
@@ -590,12 +590,16 @@ int i8_panel_width() { return I8_BN; }
 size_t i8_sync_bytes(int count, int panels) { return sizeof(int) * ((size_t)I8_SYNC_HDR + (size_t)count * panels); }
 
 // |L_rc| <= sqrt(K_rr) = sqrt(sigma2 + nugget) and |V| <= sqrt(k(x*, x*)) = sqrt(sigma2): one scale 2^e with
-// sqrt(sigma2 + nugget) <= 2^(e-1) serves both operands (scaled entries in [-0.5, 0.5])
+// sqrt(sigma2 + nugget) <= 0.99 2^e serves both operands.  Scaled entries lie in [-0.99, 0.99]: the leading digit may reach
+// +-127 (it is an int8), all others stay within +-64, and the s32 accumulators keep their headroom (the weight with the most
+// pairs, S of them, holds two pairs with a leading digit: n (2 * 127 * 64 + (S - 2) * 64^2) < 2^31 up to n = 32768).  Scaling
+// to [-0.5, 0.5] instead (round 1 / early round 2) wasted a bit whenever sqrt(sigma2 + nugget) sat just above a power of two --
+// sigma2 = 1 with any nugget, the benchmark's case: 4 x the truncation error.
 int i8_scale_exponent(double sigma2, double nugget) {
     const double bound = sqrt(sigma2 + nugget);
     int e = 0;
-    frexp(bound > 0.0 ? bound : 1.0, &e);      // bound = f 2^e, f in [0.5, 1)
-    return e + 1;
+    const double f = frexp(bound > 0.0 ? bound : 1.0, &e);      // bound = f 2^e, f in [0.5, 1)
+    return f <= 0.99 ? e : e + 1;
 }
 
 int i8_slice_L(int S, const double* A_slab, int64_t n_pad, const int* outs, const int* exps, int count, int8_t* Lq,

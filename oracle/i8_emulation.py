@@ -5,7 +5,7 @@ result is what tcgen05.mma.kind::i8 with s32 accumulation produces.  Conventions
 digits by round-to-nearest, digit pairs (t, u) with t + u <= S + 1, V re-sliced after every block row.
 
 ``trsm_variance`` is the kernel of round 2 (rows-of-L form): the strictly lower blocks of L and every solved block row V_i are
-sliced with ONE scale 2^e per output, sqrt(sigma2 + nugget) <= 2^(e-1); T_i = K*_i - sum_j L_ij V_j from the integer
+sliced with ONE scale 2^e per output, sqrt(sigma2 + nugget) <= 0.99 2^e; T_i = K*_i - sum_j L_ij V_j from the integer
 products; V_i = inv(L_ii) T_i in FP64.  ``trsm_variance_ltilde`` is the kernel of round 1 (L~ = blockdiag(L_ii)^-1 L sliced
 with one scale per row, K* pre-multiplied), kept because profiles/r01_i8_check.txt was measured with it.
 Used to check that the error the GPU path shows against the FP64 path is the error of the designed arithmetic, not of its
@@ -44,8 +44,9 @@ def sliced_product(A, eA, Vd, S):
 
 
 def scale_exponent(sigma2, nugget):
-    """csrc/trsm_i8.cu i8_scale_exponent: e with sqrt(sigma2 + nugget) <= 2^(e-1)."""
-    return int(np.frexp(np.sqrt(sigma2 + nugget))[1]) + 1
+    """csrc/trsm_i8.cu i8_scale_exponent: e with sqrt(sigma2 + nugget) <= 0.99 2^e (the leading digit may reach +-127)."""
+    f, e = np.frexp(np.sqrt(sigma2 + nugget))
+    return int(e) if f <= 0.99 else int(e) + 1
 
 
 def trsm_variance(L, Ks, sigma2, nugget, S, include_nugget=True):
@@ -98,3 +99,35 @@ def trsm_variance_ltilde(L, Ks, sigma2, nugget, S, include_nugget=True):
         for t, d in enumerate(digits(V * 2.0 ** -eV, S)):
             Vd[t][blk] = d
     return sigma2 + (nugget if include_nugget else 0.0) - norms
+
+
+def cholesky_i8(K, sigma2, nugget, S=8):
+    """The arithmetic of csrc/chol.cu chol_i8_kernel: left-looking blocked factorisation (block 128) of K = sigma2 k(X, X) +
+    nugget I whose history products sum_{k<j} L_ik L_jk^T come from S signed 7-bit digit planes of the blocks of L already
+    computed (ONE scale 2^e per output, sqrt(sigma2 + nugget) <= 0.99 2^e; digit pairs t + u <= S + 1; exact integer sums),
+    the diagonal blocks factored and the triangular solves done in FP64.  Returns L (n, n)."""
+    n = K.shape[0]
+    e = scale_exponent(sigma2, nugget)
+    L = np.zeros_like(K)
+    Ld = [np.zeros_like(K) for _ in range(S)]            # digit planes of the strictly lower blocks
+    for j0 in range(0, n, NB):
+        j1 = min(n, j0 + NB)
+        panel = K[j0:, j0:j1].copy()
+        if j0 > 0:
+            acc = np.zeros_like(panel)
+            for w in range(2, S + 2):
+                part = np.zeros_like(panel)
+                for t in range(1, w):
+                    u = w - t
+                    if t <= S and u <= S:
+                        part += Ld[u - 1][j0:, :j0] @ Ld[t - 1][j0:j1, :j0].T
+                acc += part * 2.0 ** (-BITS * w)
+            panel -= acc * 2.0 ** (2 * e)
+        Ljj = np.linalg.cholesky(panel[:j1 - j0])
+        L[j0:j1, j0:j1] = Ljj
+        if j1 < n:
+            below = np.linalg.solve(Ljj, panel[j1 - j0:].T).T      # the kernel multiplies by the stored inverse of L_jj (DMMA)
+            L[j1:, j0:j1] = below
+            for t, dg in enumerate(digits(below * 2.0 ** -e, S)):
+                Ld[t][j1:, j0:j1] = dg
+    return L

@@ -40,9 +40,10 @@ def test_emulated_scheme_error_against_tolerance(n, d, m, kernel, nugget, theta_
 
 
 def test_check_threshold_separates_good_from_bad_conditioning():
-    """The a-posteriori check of the int8 path accepts 1 % of the parity bar.  On the worst family found (smooth SqExp, d = 2)
-    the emulated error is far inside that at nugget 1e-6 sigma^2 and far outside at 1e-10: the check, not a nugget
-    heuristic, is what routes such emulators."""
+    """The a-posteriori check of the int8 path accepts 1 % of the parity bar (plus the FP64 rounding floor).  On the worst
+    family found (smooth SqExp, d = 2) the emulated error of seven planes is far inside that at nugget 1e-6 sigma^2 and still
+    inside it at 1e-10 (scale 0.99 2^e; with the [-0.5, 0.5] scaling of round 1 it was 4 x larger and outside); six planes
+    are far outside at 1e-10: the check, not a nugget heuristic, is what routes such emulators."""
     X, Y, Xs = orc.make_workload(600, 2, 1, 200, seed=21)
     theta = np.array([0.5, 0.5, 0.0])
     ratios = {}
@@ -53,8 +54,9 @@ def test_check_threshold_separates_good_from_bad_conditioning():
         V = scipy.linalg.solve_triangular(L, Ks, lower=True)
         ref = 1.0 + nugget - np.sum(V * V, axis=0)
         allowed = 0.01 * (1e-4 * np.abs(ref) + 1e-4 * nugget) + 256 * np.finfo(float).eps * (1.0 + nugget)
-        ratios[nugget] = float(np.max(np.abs(emu.trsm_variance(L, Ks, 1.0, nugget, 7) - ref) / allowed))
-    assert ratios[1e-6] < 1.0 < ratios[1e-10], ratios
+        for S in (6, 7):
+            ratios[nugget, S] = float(np.max(np.abs(emu.trsm_variance(L, Ks, 1.0, nugget, S) - ref) / allowed))
+    assert ratios[1e-6, 7] < 0.1 and ratios[1e-10, 7] < 1.0 < 10.0 < ratios[1e-10, 6], ratios
 
 
 def test_digits_are_exact_and_bounded():
@@ -67,3 +69,34 @@ def test_digits_are_exact_and_bounded():
         assert np.max(np.abs(back - x)) <= 2.0 ** (-7 * S - 1) * (1 + 1e-12)
     edge = emu.digits(np.array([0.4999999, -0.4999999, 0.75]), 6)          # |x| < 0.5 in range; 0.75 degrades, never wraps int8
     assert np.all(np.abs(edge[0]) <= 127)
+
+
+@pytest.mark.parametrize("n,d,theta_corr,nugget,kernel", [
+    (700, 10, 1.0, 1e-6, orc.SQEXP),        # the benchmark's conditioning
+    (900, 3, -1.0, 1e-8, orc.SQEXP),        # smooth, low-dimensional: ill-conditioned
+    (640, 5, 0.0, 1e-8, orc.MAT52),
+])
+def test_cholesky_on_int8_planes_is_fp64_equivalent(n, d, theta_corr, nugget, kernel):
+    """The Cholesky whose history products come from 8 signed 7-bit planes (chol_i8_kernel) against LAPACK: the factor's
+    backward error stays at the level of the FP64 blocked factorisation's own, and the quantities the parity tests check
+    (log det, y^T K^-1 y, posterior mean) keep their bars with orders of magnitude to spare."""
+    X, Y, Xs = orc.make_workload(n, d, 1, 64, seed=5)
+    theta = np.append(np.full(d, theta_corr), 0.0)
+    K = orc.kernel_f(X, X, theta[:d], kernel) + nugget * np.eye(n)
+    Ks = orc.kernel_f(X, Xs, theta[:d], kernel)
+    L_ref = np.linalg.cholesky(K)
+    L = emu.cholesky_i8(K, 1.0, nugget, S=8)
+    back = np.abs(L @ L.T - K).max()
+    back_ref = np.abs(L_ref @ L_ref.T - K).max()
+    assert back <= max(8.0 * back_ref, 2e-15), (back, back_ref)
+    y = Y[0]
+    a, a_ref = scipy.linalg.cho_solve((L, True), y), scipy.linalg.cho_solve((L_ref, True), y)
+    ld, ld_ref = 2 * np.log(np.diag(L)).sum(), 2 * np.log(np.diag(L_ref)).sum()
+    cond = np.linalg.cond(K)
+    assert abs(ld - ld_ref) <= 1e-9 * max(1.0, cond * 1e-8) * abs(ld_ref)
+    assert abs(y @ a - y @ a_ref) <= 1e-9 * max(1.0, cond * 1e-8) * abs(y @ a_ref)
+    np.testing.assert_allclose(Ks.T @ a, Ks.T @ a_ref, rtol=1e-6, atol=1e-6 * np.abs(Ks.T @ a_ref).max())
+    # seven planes are visibly worse on the ill-conditioned case (why the Cholesky uses one digit more than the predict TRSM)
+    if theta_corr < 0:
+        L7 = emu.cholesky_i8(K, 1.0, nugget, S=7)
+        assert np.abs(L7 @ L7.T - K).max() > 4.0 * back
