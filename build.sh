@@ -4,8 +4,8 @@
 set -e
 cd "$(dirname "$0")"
 SRC=mogp_emulator_b200/csrc
-OUT=mogp_emulator_b200/libmogp_b200.so
-OBJ=build/obj
+OUT=${OUT:-mogp_emulator_b200/libmogp_b200.so}      # OBJ=build/obj_trace OUT=build/libmogp_trace.so ./build.sh -DCHOL_TRACE: a debug build beside the product
+OBJ=${OBJ:-build/obj}
 mkdir -p $OBJ
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 pids=()

@@ -53,6 +53,9 @@ struct Potf2Smem {
     double red[32];
     double ri;
     int fail;
+#ifdef CHOL_TRACE
+    unsigned long long stamps[32];
+#endif
 };
 
 // pv = sqrt(d) and ri = 1 / sqrt(d) for a pivot d > 0.  A dependent FP64 instruction costs ~55 cycles on this chip and the
@@ -76,41 +79,55 @@ __device__ __forceinline__ void sqrt_and_reciprocal(double d, double& pv, double
 // (a1) of potf2_inv_block: Cholesky of the 16x16 diagonal sub-block at (j0, j0) by ONE warp.  Lane r (mod 16) owns
 // row j0+r in registers; pivots and multipliers travel by shuffle, so the 16-step dependency chain has no barrier.
 // Writes L11 back to sm.S and sm.Lr, the reciprocal pivots to sm.rd, or sets sm.fail (1-based failing column).
+//
+// This is ONE warp's instruction stream on the critical path of the whole factorisation: what counts is its length.
+//   * Every lane updates every column c > j with one FMA; entries above the diagonal (c > r) turn into garbage that nothing
+//     reads (shuffles read a[j] of the lanes c > j only, lanes 16..31 hold zeros).  Selects that kept them clean, and the
+//     two-rounding form computed beside the FMA for every entry, were 2/3 of ~230 instructions per pivot.
+//   * The entry that becomes the lane's own pivot lives in a separate register and is updated as d - round(l*l) (two
+//     roundings, the dot-then-subtract form of LAPACK's unblocked kernel) so that exactly duplicated rows fail the un-jittered
+//     factorisation the same way the CPU reference does.  Its multiplier is the lane's own a[j]: no shuffle on that chain.
+//   * The warp must arrive converged: the shuffles take a software path (BRA.DIV) otherwise, ~10 x slower -- a lane-0 trace
+//     stamp in front of the call did exactly that to the timeline tool (a "34 us first pivot block" that the product never had).
+//   (Rolling the pivot loop around a shifting register window -- 90 instructions instead of 16 x 85 -- was measured: 5.5 us per
+//   block against 3.5 us, every pivot then updates all 15 columns; instruction fetch is not what bounds this function.)
 __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
+    __syncwarp();
     const int r = lane & 15;
+    const bool act = lane < SB;                        // lanes 16..31 idle along
     double a[SB];
 #pragma unroll
-    for (int jj = 0; jj < SB; jj++) a[jj] = (jj <= r && lane < SB) ? sm.S[(j0 + r) * PS + j0 + jj] : 0.0;   // lanes 16..31 only relay
+    for (int jj = 0; jj < SB; jj++) a[jj] = (jj <= r && act) ? sm.S[(j0 + r) * PS + j0 + jj] : 0.0;
+    double diag = act ? sm.S[(j0 + r) * PS + j0 + r] : 1.0;
+    volatile double* Lr = sm.Lr;                       // column j of L11 is exchanged through sm.Lr (where it has to end up anyway)
+    volatile double* dd = &sm.ri;                      // the next pivot
+    if (lane == 0) *dd = diag;
+    __syncwarp();
     int fail = 0;
 #pragma unroll
     for (int j = 0; j < SB; j++) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        const double d = *dd;
         // also catches NaN (LAPACK: ajj <= 0 or isnan); warp-uniform.  No early exit: the loop stays fully
-        // unrolled (register-resident a[]); what follows a failed pivot is never stored.
+        // unrolled (register-resident a[]); what follows a failed pivot is never used.
         if (fail == 0 && !(d > 0.0)) fail = j0 + j + 1;
         double pv, ri;
         sqrt_and_reciprocal(d, pv, ri);
-        a[j] = (r == j) ? pv : a[j] * ri;   // LAPACK scales the column by the reciprocal pivot (entries above the diagonal are 0)
+        a[j] = (r == j) ? pv : a[j] * ri;   // LAPACK scales the column by the reciprocal pivot
         if (lane == 0) sm.rd[j0 + j] = ri;
+        diag = __dsub_rn(diag, __dmul_rn(a[j], a[j]));
+        __syncwarp();                        // every lane has read the pivot
+        if (act) Lr[r * (SB + 1) + j] = (r >= j) ? a[j] : 0.0;
+        if (lane == j + 1) *dd = diag;
+        __syncwarp();
 #pragma unroll
-        for (int c = j + 1; c < SB; c++) {
-            const double l = __shfl_sync(0xffffffffu, a[j], c);
-            // the entry that becomes a pivot is updated as a - round(l*l) (two roundings, the dot-then-subtract
-            // form of LAPACK's unblocked kernel) so that exactly duplicated rows fail the un-jittered
-            // factorisation the same way the CPU reference does.
-            const double two = __dsub_rn(a[c], __dmul_rn(a[j], l));
-            const double one = fma(-a[j], l, a[c]);
-            a[c] = (r == c) ? two : ((r > c) ? one : a[c]);
-        }
+        for (int c = j + 1; c < SB; c++) a[c] = fma(-a[j], Lr[c * (SB + 1) + j], a[c]);
     }
     if (fail) {
         if (lane == 0) sm.fail = fail;
-    } else if (lane < SB) {
+    } else if (act) {
 #pragma unroll
-        for (int jj = 0; jj < SB; jj++) {
+        for (int jj = 0; jj < SB; jj++)
             if (jj <= r) sm.S[(j0 + r) * PS + j0 + jj] = a[jj];
-            sm.Lr[r * (SB + 1) + jj] = a[jj];
-        }
     }
 }
 
@@ -122,10 +139,13 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
 __device__ int chol_trace_cur[256];     // per SM: slot of the D tile in flight (trace build only)
 #define CH_STAMP_IN(ev) do { if (tid == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); CH_STAMP(chol_trace_cur[sm_ & 255], ev); } } while (0)
 __device__ unsigned long long chol_trace_buf2[CH_TRACE_N * 32];
-#define CH_STAMP2(cond, ev) do { if (cond) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); const int sl_ = chol_trace_cur[sm_ & 255]; if (sl_ >= 0 && sl_ < CH_TRACE_N) chol_trace_buf2[sl_ * 32 + (ev)] = globaltimer_ns(); } } while (0)
+// (stamps go to shared memory and are flushed after the tile: a global store per stamp perturbed what it measured)
+#define CH_STAMP2(cond, ev) do { if (cond) sm.stamps[ev] = globaltimer_ns(); } while (0)
+#define CH_STAMP2_FLUSH() do { if (tid < 32) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); const int sl_ = chol_trace_cur[sm_ & 255]; if (sl_ >= 0 && sl_ < CH_TRACE_N) chol_trace_buf2[sl_ * 32 + tid] = sm.stamps[tid]; } } while (0)
 #else
 #define CH_STAMP_IN(ev) do { } while (0)
 #define CH_STAMP2(cond, ev) do { } while (0)
+#define CH_STAMP2_FLUSH() do { } while (0)
 #endif
 
 template <int NTHR, int BAR_ALL>
@@ -338,6 +358,7 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
     }
     if (sm.fail) return sm.fail;
     CH_STAMP_IN(2);
+    CH_STAMP2_FLUSH();
 
     // ---- write L_kk back (upper part of the block zeroed) and accumulate log det -------------
     for (int idx = tid; idx < NB * NB; idx += NTHR) {

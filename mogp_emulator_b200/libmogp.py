@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmogp_b200.so")
+# MOGP_LIB: a debug build of the same library (tools/*_timeline.py: -DCHOL_TRACE / -DI8_TRACE), never another implementation
+LIB_PATH = os.environ.get("MOGP_LIB") or os.path.join(_HERE, "libmogp_b200.so")
 
 OK, ERR_CUDA, ERR_ARG, ERR_NOT_PD, ERR_NOT_FIT, ERR_NCCL, ERR_NOMEM, ERR_FPE = range(8)
 GET_K, GET_L, GET_ALPHA, GET_KINV = range(4)

@@ -35,7 +35,7 @@ print("# medians (us):", " ".join("%s %.1f" % (nm, np.median(d_[:, k])) for k, n
 lib.mogp_debug_chol_trace2.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 buf2 = (ctypes.c_ulonglong * (32 * cnt))()
 lib.mogp_debug_chol_trace2(buf2, 32 * cnt)
-b = np.array(buf2[:], dtype=np.int64).reshape(cnt, 32)
+b = np.array(buf2[:], dtype=np.uint64).astype(np.int64).reshape(cnt, 32)
 ev = ["start", "a1(0) done", "a2(0)+barriers", "after b1(0)", "a1(1) done", "b2(0) done (warp 1)", "after barrier", "a2(1) done",
       None, None, "after b1(3)", "a1(4) done", "b2(3) done (warp 1)", "after barrier", "a2(4) done"]
 for k in range(1, 15):
