@@ -21,6 +21,8 @@
 // memory (red.release / ld.acquire + proxy fences for the TMA readers) order the tiles, nothing deadlocks, and
 // there is no per-step launch, tail or wave quantisation; outputs interleave in the ticket order, so many small
 // factorisations fill the machine as well as one large one.
+#include <type_traits>
+
 #include "i8_common.cuh"
 #include "kernels.h"
 
@@ -48,7 +50,7 @@ struct Potf2Smem {
     double S[NB * PS];                         // lower: L; upper blocks (J, b): the off-diagonal blocks X_bJ of inv(L)
     double InvD[NSB * SB * (SB + 1)];          // inverses of the eight 16x16 diagonal sub-blocks of L (zero above the diagonal)
     double Tmp[(NSB - 1) * SB * (SB + 1)];     // per (b, J) pair: sum_b' L_bb' X_b'J
-    double Lr[SB * (SB + 1)];
+    double Lr[2][SB * (SB + 1)];               // L11 of the current panel (parity of the panel: the chain warp is one panel ahead)
     double rd[NB];
     double red[32];
     double ri;
@@ -99,7 +101,7 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
 #pragma unroll
     for (int jj = 0; jj < SB; jj++) a[jj] = (jj <= r && act) ? sm.S[(j0 + r) * PS + j0 + jj] : 0.0;
     double diag = act ? sm.S[(j0 + r) * PS + j0 + r] : 1.0;
-    volatile double* Lr = sm.Lr;                       // column j of L11 is exchanged through sm.Lr (where it has to end up anyway)
+    volatile double* Lr = sm.Lr[(j0 / SB) & 1];        // column j of L11 is exchanged through sm.Lr (where it has to end up anyway)
     volatile double* dd = &sm.ri;                      // the next pivot
     if (lane == 0) *dd = diag;
     __syncwarp();
@@ -132,8 +134,8 @@ __device__ __noinline__ void potf2_diag16(Potf2Smem& sm, int j0, int lane) {
 }
 
 // On entry sm.S holds the lower triangle of the block (upper part zero).  On success (returns 0) the diagonal 16x16
-// blocks of sm.S hold inv(L)'s diagonal blocks and its upper blocks (J, b) the off-diagonal blocks X_bJ, Lout (global, row stride ld) has received L with a zero upper part, and *logdet_add is
-// 2*sum(log L_ii) on thread 0.  On failure returns the 1-based index of the failing pivot (LAPACK info).
+// blocks of sm.InvD hold inv(L)'s diagonal blocks and the upper blocks (J, b) of sm.S its off-diagonal blocks X_bJ, the lower
+// triangle of sm.S holds L (the caller writes both out), and *logdet_add is 2*sum(log L_ii) on thread 0.  On failure returns the 1-based index of the failing pivot (LAPACK info).
 // BAR_ALL: named barrier id for the NTHR participating threads.
 #ifdef CHOL_TRACE
 __device__ int chol_trace_cur[256];     // per SM: slot of the D tile in flight (trace build only)
@@ -149,8 +151,7 @@ __device__ unsigned long long chol_trace_buf2[CH_TRACE_N * 32];
 #endif
 
 template <int NTHR, int BAR_ALL>
-__device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* __restrict__ Lout, int64_t ld,
-                                               double* logdet_add) {
+__device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* logdet_add) {
     constexpr int NG = NTHR / NB;   // thread groups of 128
     static_assert(NTHR % NB == 0 && NG >= 1 && SB % NG == 0, "thread count");
     if (tid == 0) sm.fail = 0;
@@ -161,67 +162,20 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
     // (a2) the rows below it, one thread per row, (b) the trailing update of the block.  The 16-step dependency
     // chain of (a1) is the long pole, so (b) is split: (b1) first the 16 columns the NEXT panel needs (all threads),
     // then warp 0 runs (a1) of panel s+1 while warps 1.. run (b2), the rest of the trailing update.
-    auto rows_below = [&](int j0) {   // (a2): needs only L11 (sm.Lr) and the reciprocal pivots (sm.rd)
-        if (tid < NB - j0 - SB) {
-            const int r = j0 + SB + tid;
-            double a[SB];
-#pragma unroll
-            for (int jj = 0; jj < SB; jj++) a[jj] = sm.S[r * PS + j0 + jj];
-#pragma unroll
-            for (int j = 0; j < SB; j++) {
-                a[j] *= sm.rd[j0 + j];
-#pragma unroll
-                for (int c = j + 1; c < SB; c++) a[c] = fma(-a[j], sm.Lr[c * (SB + 1) + j], a[c]);
-            }
-#pragma unroll
-            for (int jj = 0; jj < SB; jj++) sm.S[r * PS + j0 + jj] = a[jj];
-        }
-    };
-    // S[r][c] -= sum_kk S[r][j0+kk] * S[c][j0+kk] for c = c_lo + q, + nq, ... while c <= min(r, c_hi); 4 dots at a time
-    auto update_row = [&](int j0, int r, int c_lo, int c_hi, int q, int nq) {
+    auto rows_below = [&](int j0, int r) {   // (a2) of row r: needs only L11 (sm.Lr) and the reciprocal pivots (sm.rd) of the panel
+        const double* Lr = sm.Lr[(j0 / SB) & 1];
         double a[SB];
 #pragma unroll
-        for (int kk = 0; kk < SB; kk++) a[kk] = sm.S[r * PS + j0 + kk];
-        const int cmax = (r < c_hi) ? r : c_hi;
-        int c = c_lo + q;
-        // eight dot products at a time: a dependent DFMA costs ~50 cycles on this chip, the chains of one dot are 16 long
-        for (; c + 7 * nq <= cmax; c += 8 * nq) {
-            double dd[8];
+        for (int jj = 0; jj < SB; jj++) a[jj] = sm.S[r * PS + j0 + jj];
 #pragma unroll
-            for (int u = 0; u < 8; u++) dd[u] = 0.0;
-            const double* s0 = sm.S + c * PS + j0;
+        for (int j = 0; j < SB; j++) {
+            a[j] *= sm.rd[j0 + j];
 #pragma unroll
-            for (int kk = 0; kk < SB; kk++)
-#pragma unroll
-                for (int u = 0; u < 8; u++) dd[u] = fma(a[kk], s0[u * nq * PS + kk], dd[u]);
-            double* dst = sm.S + r * PS + c;
-#pragma unroll
-            for (int u = 0; u < 8; u++) dst[u * nq] -= dd[u];
+            for (int c = j + 1; c < SB; c++) a[c] = fma(-a[j], Lr[c * (SB + 1) + j], a[c]);
         }
-        for (; c + 3 * nq <= cmax; c += 4 * nq) {
-            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-            const double* s0 = sm.S + c * PS + j0;
-            const double* s1 = s0 + nq * PS;
-            const double* s2 = s1 + nq * PS;
-            const double* s3 = s2 + nq * PS;
 #pragma unroll
-            for (int kk = 0; kk < SB; kk++) {
-                d0 = fma(a[kk], s0[kk], d0);
-                d1 = fma(a[kk], s1[kk], d1);
-                d2 = fma(a[kk], s2[kk], d2);
-                d3 = fma(a[kk], s3[kk], d3);
-            }
-            double* dst = sm.S + r * PS + c;
-            dst[0] -= d0; dst[nq] -= d1; dst[2 * nq] -= d2; dst[3 * nq] -= d3;
-        }
-        for (; c <= cmax; c += nq) {
-            double dot = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < SB; kk++) dot = fma(a[kk], sm.S[c * PS + j0 + kk], dot);
-            sm.S[r * PS + c] -= dot;
-        }
+        for (int jj = 0; jj < SB; jj++) sm.S[r * PS + j0 + jj] = a[jj];
     };
-
     // ---- inverse of the block, one 16-row block row at a time -------------------------------------------------------
     // inv_diag16(b): Inv_bb by one warp, lane c (< 16) solves L_bb x = e_c with the stored reciprocal pivots.
     // inv_offdiag(b, J): X_bJ = -Inv_bb * sum_{b'=J}^{b-1} L_bb' X_b'J (X_JJ = Inv_JJ) by one warp, every lane a 2x4 micro-tile
@@ -247,124 +201,152 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
             for (int i = 0; i < SB; i++) Ib[i * (SB + 1) + c] = x[i];
         }
     };
+    // FP64 tensor pipe: both products are 16 x 16 x 16 (two column tiles of 8, two K steps each); T passes through sm.Tmp to turn
+    // from accumulator layout into a B operand.  (Scalar 2 x 4 micro-tiles took 1.1 .. 5.3 us per block row -- longer than the
+    // chain warp's panel -- and 4.8 us for the last one, which is not in anybody's shadow.)
     auto inv_offdiag = [&](int b, int J, int lane) {
         if (J >= b) return;
-        const int ti = lane >> 2, tc = lane & 3;
-        const double* L0 = sm.S + (b * SB + ti) * PS;
-        const double* L1 = L0 + 8 * PS;
-        double t[4][2][4];
+        const int g = lane >> 2, t4 = lane & 3;
+        double acc[2][4];
 #pragma unroll
-        for (int z = 0; z < 4; z++)
+        for (int n = 0; n < 2; n++)
 #pragma unroll
-            for (int a = 0; a < 2; a++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) t[z][a][q] = 0.0;
+            for (int e = 0; e < 4; e++) acc[n][e] = 0.0;
         for (int bp = J; bp < b; bp++) {
             // X_b'J[k][c]: the inverted diagonal block (b' == J) or the parked block (J, b')
-            const double* xs = (bp == J) ? (sm.InvD + J * SB * (SB + 1) + 4 * tc) : (sm.S + (J * SB) * PS + bp * SB + 4 * tc);
+            const double* xs = (bp == J) ? (sm.InvD + J * SB * (SB + 1)) : (sm.S + (J * SB) * PS + bp * SB);
             const int xstride = (bp == J) ? (SB + 1) : PS;
-            const double* l0 = L0 + bp * SB;
-            const double* l1 = L1 + bp * SB;
+            const double* la = sm.S + (b * SB + g) * PS + bp * SB + t4;
 #pragma unroll
-            for (int k = 0; k < SB; k++) {
-                const double a0 = l0[k], a1 = l1[k];
-                const double* x = xs + k * xstride;
+            for (int kk = 0; kk < SB; kk += 8) {
+                const double a0 = la[kk], a1 = la[8 * PS + kk], a2 = la[kk + 4], a3 = la[8 * PS + kk + 4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    t[k & 3][0][q] = fma(a0, x[q], t[k & 3][0][q]);
-                    t[k & 3][1][q] = fma(a1, x[q], t[k & 3][1][q]);
-                }
+                for (int n = 0; n < 2; n++)
+                    dmma_16x8x8(acc[n], a0, a1, a2, a3, xs[(kk + t4) * xstride + 8 * n + g], xs[(kk + t4 + 4) * xstride + 8 * n + g]);
             }
         }
         double* tp = sm.Tmp + J * SB * (SB + 1);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            tp[ti * (SB + 1) + 4 * tc + q] = (t[0][0][q] + t[1][0][q]) + (t[2][0][q] + t[3][0][q]);
-            tp[(ti + 8) * (SB + 1) + 4 * tc + q] = (t[0][1][q] + t[1][1][q]) + (t[2][1][q] + t[3][1][q]);
+        for (int n = 0; n < 2; n++) {
+            tp[g * (SB + 1) + 8 * n + 2 * t4] = acc[n][0];
+            tp[g * (SB + 1) + 8 * n + 2 * t4 + 1] = acc[n][1];
+            tp[(g + 8) * (SB + 1) + 8 * n + 2 * t4] = acc[n][2];
+            tp[(g + 8) * (SB + 1) + 8 * n + 2 * t4 + 1] = acc[n][3];
         }
         __syncwarp();
-        const double* i0 = sm.InvD + b * SB * (SB + 1) + ti * (SB + 1);      // rows ti, ti+8 of Inv_bb (zero above the diagonal)
-        const double* i1 = i0 + 8 * (SB + 1);
-        double y[4][2][4];
+        const double* ia = sm.InvD + b * SB * (SB + 1) + g * (SB + 1) + t4;      // Inv_bb (zero above the diagonal)
+        double y[2][4];
 #pragma unroll
-        for (int z = 0; z < 4; z++)
+        for (int n = 0; n < 2; n++)
 #pragma unroll
-            for (int a = 0; a < 2; a++)
+            for (int e = 0; e < 4; e++) y[n][e] = 0.0;
 #pragma unroll
-                for (int q = 0; q < 4; q++) y[z][a][q] = 0.0;
+        for (int kk = 0; kk < SB; kk += 8) {
+            const double a0 = ia[kk], a1 = ia[8 * (SB + 1) + kk], a2 = ia[kk + 4], a3 = ia[8 * (SB + 1) + kk + 4];
 #pragma unroll
-        for (int k = 0; k < SB; k++) {
-            const double a0 = i0[k], a1 = i1[k];
-            const double* x = tp + k * (SB + 1) + 4 * tc;
+            for (int n = 0; n < 2; n++)
+                dmma_16x8x8(y[n], a0, a1, a2, a3, tp[(kk + t4) * (SB + 1) + 8 * n + g], tp[(kk + t4 + 4) * (SB + 1) + 8 * n + g]);
+        }
+        double* xo = sm.S + (J * SB + g) * PS + b * SB + 2 * t4;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                y[k & 3][0][q] = fma(a0, x[q], y[k & 3][0][q]);
-                y[k & 3][1][q] = fma(a1, x[q], y[k & 3][1][q]);
+        for (int n = 0; n < 2; n++) {
+            xo[8 * n] = -y[n][0];
+            xo[8 * n + 1] = -y[n][1];
+            xo[8 * PS + 8 * n] = -y[n][2];
+            xo[8 * PS + 8 * n + 1] = -y[n][3];
+        }
+    };
+    // C[R0 + i][C0 + c] -= sum_k P[R0 + i][k] P[C0 + c][k] for a 16 x (8 NT) tile, P = S[:, j0 .. j0+15]: DMMA into a zero
+    // accumulator, then ONE subtraction per entry (the dot-then-subtract form of the scalar update_row)
+    auto update_tile = [&](int j0, int R0, int C0, int lane, auto nt_tag) {
+        constexpr int NT = decltype(nt_tag)::value;
+        const int g = lane >> 2, t4 = lane & 3;
+        const double* pa = sm.S + (R0 + g) * PS + j0 + t4;
+        double acc[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; n++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[n][e] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < SB; kk += 8) {
+            const double a0 = pa[kk], a1 = pa[8 * PS + kk], a2 = pa[kk + 4], a3 = pa[8 * PS + kk + 4];
+#pragma unroll
+            for (int n = 0; n < NT; n++) {
+                const double* pb = sm.S + (C0 + 8 * n + g) * PS + j0 + t4 + kk;
+                dmma_16x8x8(acc[n], a0, a1, a2, a3, pb[0], pb[4]);
             }
         }
-        double* xo = sm.S + (J * SB) * PS + b * SB + 4 * tc;
+        double* pc = sm.S + (R0 + g) * PS + C0 + 2 * t4;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            xo[ti * PS + q] = -((y[0][0][q] + y[1][0][q]) + (y[2][0][q] + y[3][0][q]));
-            xo[(ti + 8) * PS + q] = -((y[0][1][q] + y[1][1][q]) + (y[2][1][q] + y[3][1][q]));
+        for (int n = 0; n < NT; n++) {
+            pc[8 * n] -= acc[n][0];
+            pc[8 * n + 1] -= acc[n][1];
+            pc[8 * PS + 8 * n] -= acc[n][2];
+            pc[8 * PS + 8 * n + 1] -= acc[n][3];
         }
     };
 
+    // The chain of the tile is a1(0) -> [a2 of the next diagonal block's 16 rows -> their 16x16 update -> a1(s+1)] x 7, and ONE warp
+    // walks it without waiting for anybody: warp 0 solves the 16 rows below its pivot block itself (a2n), applies them to the next
+    // diagonal block (b1n) and goes straight on to that block's pivots.  The other seven warps follow one panel behind: the
+    // rows further down (a2r), then -- once warp 0's 16 rows are in shared memory (named barrier BAR_ALL + 2: warp 0 only arrives) --
+    // the trailing update of everything below the next diagonal block (b1r + b2) and block row s of the inverse.  One barrier per
+    // panel.  (Before: a1, a2 and b1 each ended in a barrier of all eight warps, 5 us of every 8.4 us panel.)
     CH_STAMP2(tid == 0, 0);
     if (tid < 32) potf2_diag16(sm, 0, tid);
     CH_STAMP2(tid == 0, 1);
     named_bar_sync(BAR_ALL, NTHR);
     if (sm.fail) return sm.fail;
-    rows_below(0);
-    named_bar_sync(BAR_ALL, NTHR);
-    CH_STAMP2(tid == 0, 2);
     for (int s = 0; s + 1 < NB / SB; s++) {
         const int j0 = s * SB;
-        const int nrow = NB - j0 - SB;   // rows below panel s
-        // (b1) columns of the next panel: thread (row, column parity)
-        {
-            constexpr int NQ1 = NTHR / NB;
-            const int t = tid & (NB - 1), q = tid >> 7;
-            if (t < nrow) update_row(j0, j0 + SB + t, j0 + SB, j0 + 2 * SB - 1, q, NQ1);
-        }
-        named_bar_sync(BAR_ALL, NTHR);
-        CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 3 : 10);      // after b1
+        const int nrow2 = NB - j0 - 2 * SB;   // rows below the next diagonal block
         if (tid < 32) {
-            potf2_diag16(sm, j0 + SB, tid);                         // (a1) of panel s+1
-            CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 4 : 11);  // a1 done
+            if (tid < SB) rows_below(j0, j0 + SB + tid);                                            // a2n
+            __syncwarp();
+            update_tile(j0, j0 + SB, j0 + SB, tid, std::integral_constant<int, 2>());                // b1n (entries above the diagonal: unused)
+            __threadfence_block();
+            asm volatile("bar.arrive %0, %1;" ::"r"(BAR_ALL + 2), "r"(NTHR) : "memory");
+            __syncwarp();
+            potf2_diag16(sm, j0 + SB, tid);                                                         // a1 of panel s+1
+            CH_STAMP2(tid == 0, 2 + 3 * s);       // chain warp done with panel s+1's pivots
         } else {
-            // (b2) the remaining columns (>= j0+32); rows folded in pairs (short + long) so that every thread gets
-            // the same number of columns
-            constexpr int NT2 = NTHR - 32, PAIRS = 56, NQ2 = NT2 / PAIRS;
-            static_assert(NT2 % PAIRS == 0 && PAIRS >= (NB - 2 * SB) / 2, "update-warp mapping");
-            const int tt = tid - 32, t = tt % PAIRS, q = tt / PAIRS;
-            const int nrow2 = nrow - SB;
-            if (t < nrow2 / 2) {
-                update_row(j0, j0 + 2 * SB + t, j0 + 2 * SB, NB - 1, q, NQ2);
-                update_row(j0, NB - 1 - t, j0 + 2 * SB, NB - 1, q, NQ2);
+            static_assert(NTHR - 32 >= NB - 2 * SB, "one thread per row below the next diagonal block");
+            const int tt = tid - 32;
+            if (tt < nrow2) rows_below(j0, j0 + 2 * SB + tt);                                        // a2r
+            named_bar_sync(BAR_ALL + 2, NTHR);
+            // (b1r + b2) the trailing update below the next diagonal block on the FP64 tensor pipe:
+            //     S[r][c] -= sum_k P[r][k] P[c][k],   P = S[:, j0 .. j0+15],   rows r >= j0+32, columns j0+16 <= c <= r
+            // in tiles of 16 rows x 16 columns (K = 16: DMMAs into zero accumulators, then ONE subtraction per entry -- the
+            // dot-then-subtract form of the scalar update it replaces), dealt round-robin to the seven warps.  Tiles that cross the
+            // diagonal also write entries above it: nothing reads those (potf2_diag16, rows_below and this update read the lower
+            // triangle, the parked inverse blocks of these rows are written later, the write-back masks).  Scalar FMAs from shared
+            // memory (one 8-byte load per FMA) took 8.3 us for panel 0 -- twice the chain warp's 4.6 us; this takes under 1 us.
+            {
+                const int wid = (tid >> 5) - 1, lane = tid & 31;
+                const int mt = nrow2 / SB;                       // 16-row tiles; tile row mi has 2 + mi PAIRS of column tiles
+                const int total = mt * (mt + 3) / 2;
+                for (int tile = wid; tile < total; tile += NTHR / 32 - 1) {
+                    int mi = 0;
+                    while ((mi + 1) * (mi + 4) / 2 <= tile) mi++;
+                    const int ni = tile - mi * (mi + 3) / 2;
+                    update_tile(j0, j0 + 2 * SB + SB * mi, j0 + SB + 16 * ni, lane, std::integral_constant<int, 2>());
+                }
             }
-            CH_STAMP2(tid == 32 && (s == 0 || s == 3), s == 0 ? 5 : 12); // b2 done (one of its warps)
+            CH_STAMP2(tid == 32, 3 + 3 * s);      // trailing update done
             // block row s of the inverse (panel s of L is final): Inv_ss by warp 1, then X_sJ for J < s by the warps 1..7
             if (tid < 64) inv_diag16(s, tid & 31);
             named_bar_sync(BAR_ALL + 1, NTHR - 32);
             inv_offdiag(s, (tid >> 5) - 1, tid & 31);
+            CH_STAMP2(tid == 32, 4 + 3 * s);      // block row s of the inverse done (warp 1)
         }
         named_bar_sync(BAR_ALL, NTHR);
-        CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 6 : 13);      // after the a1 / b2 barrier
         if (sm.fail) return sm.fail;
-        rows_below(j0 + SB);                                        // (a2) of panel s+1
-        CH_STAMP2(tid == 0 && (s == 0 || s == 3), s == 0 ? 7 : 14);      // a2 done (this thread)
-        named_bar_sync(BAR_ALL, NTHR);
     }
     if (sm.fail) return sm.fail;
     CH_STAMP_IN(2);
     CH_STAMP2_FLUSH();
 
-    // ---- write L_kk back (upper part of the block zeroed) and accumulate log det -------------
-    for (int idx = tid; idx < NB * NB; idx += NTHR) {
-        const int r = idx >> 7, c = idx & 127;
-        Lout[(int64_t)r * ld + c] = sm.S[r * PS + c];
-    }
+    // ---- log det (L_kk itself is written back by the caller, after inv(L_kk) has been published) -------------
     {
         double v = (tid < NB) ? log(sm.S[tid * PS + tid]) : 0.0;
 #pragma unroll
@@ -385,60 +367,89 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* _
 }
 
 // The D tile: R_jj (written by the two DIAG tiles, possibly on other SMs) -> shared memory, factor + invert (potf2_inv_block),
-// L_jj back to the matrix, inv(L_jj) to the Dinv slab, log-determinant, LAPACK info.  NTHR consumer threads (ctid), `base`:
-// the borrowed shared memory (>= sizeof(Potf2Smem)); named barriers 1 (all NTHR threads), 2 and 3.
+// inv(L_jj) to the Dinv slab, log-determinant, LAPACK info, PUBLISH (dprog: the ROW tiles of column j wait for inv(L_jj) only),
+// then L_jj back to the matrix (nothing inside the factorisation reads the diagonal block of L again).  NTHR consumer threads
+// (ctid), `base`: the borrowed shared memory (>= sizeof(Potf2Smem)); named barriers 1 (all NTHR threads), 2, 3 and 4.  Ends with
+// barrier 1: every thread is done with the shared memory.
 template <int NTHR>
 __device__ __forceinline__ void chol_d_tile(unsigned char* base, int ctid, double* A, double* Dinv, int64_t n_pad, int64_t rb,
-                                            int j, int o, int* info, double* scal, int trs) {
+                                            int j, int o, int* info, double* scal, int* dprog, bool skip, int trs) {
     (void)trs;
     Potf2Smem& sm = *reinterpret_cast<Potf2Smem*>(base);
     double* Ablk = A + (rb + (int64_t)j * NB) * n_pad + (int64_t)j * NB;
-    // 16-byte loads, eight in flight per thread (a single 8-byte load per iteration left the 128 KB block waiting on 64
-    // sequential L2 round trips: 16 us)
-    {
-        static_assert(NTHR == 256, "load mapping");
-        const int cp = ctid & 63, r0 = ctid >> 6;          // column pair, first row; rows r0, r0 + 4, ...
+    int fail = 1;
+    if (!skip) {
+        // 16-byte loads, eight in flight per thread (a single 8-byte load per iteration left the 128 KB block waiting on 64
+        // sequential L2 round trips: 16 us)
+        {
+            static_assert(NTHR == 256, "load mapping");
+            const int cp = ctid & 63, r0 = ctid >> 6;          // column pair, first row; rows r0, r0 + 4, ...
 #pragma unroll
-        for (int it = 0; it < 32; it += 8) {
-            double2 v[8];
+            for (int it = 0; it < 32; it += 8) {
+                double2 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int r = r0 + 4 * (it + u);
-                v[u] = (2 * cp <= r) ? __ldcg(reinterpret_cast<const double2*>(Ablk + (int64_t)r * n_pad) + cp)
-                                     : make_double2(0.0, 0.0);
-            }
+                for (int u = 0; u < 8; u++) {
+                    const int r = r0 + 4 * (it + u);
+                    v[u] = (2 * cp <= r) ? __ldcg(reinterpret_cast<const double2*>(Ablk + (int64_t)r * n_pad) + cp)
+                                         : make_double2(0.0, 0.0);
+                }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int r = r0 + 4 * (it + u);
-                sm.S[r * PS + 2 * cp] = (2 * cp <= r) ? v[u].x : 0.0;
-                sm.S[r * PS + 2 * cp + 1] = (2 * cp + 1 <= r) ? v[u].y : 0.0;
+                for (int u = 0; u < 8; u++) {
+                    const int r = r0 + 4 * (it + u);
+                    sm.S[r * PS + 2 * cp] = (2 * cp <= r) ? v[u].x : 0.0;
+                    sm.S[r * PS + 2 * cp + 1] = (2 * cp + 1 <= r) ? v[u].y : 0.0;
+                }
             }
         }
-    }
-    double ld_add = 0.0;
+        double ld_add = 0.0;
 #ifdef CHOL_TRACE
+        named_bar_sync(1, NTHR);
+        if (ctid == 0) CH_STAMP(trs, 1);
+#endif
+        fail = potf2_inv_block<NTHR, 2>(sm, ctid, &ld_add);
+#ifdef CHOL_TRACE
+        if (ctid == 0) CH_STAMP(trs, 5);
+#endif
+        if (fail) {
+            if (ctid == 0) info[o] = j * NB + fail;
+        } else {
+            // inv(L_jj): two columns per thread and store (a pair never straddles a 16-column block)
+            double* Dblk = Dinv + (rb + (int64_t)j * NB) * NB;
+            for (int idx = ctid; idx < NB * NB / 2; idx += NTHR) {
+                const int r = idx >> 6, c = (idx & 63) * 2;
+                const int b = r >> 4, J = c >> 4;
+                double2 v = make_double2(0.0, 0.0);
+                if (b == J) {                                                            // (zero above the diagonal)
+                    const double* q = sm.InvD + (b * SB + (r & 15)) * (SB + 1) + (c & 15);
+                    v = make_double2(q[0], q[1]);
+                } else if (b > J) {                                                      // parked in the upper block (J, b)
+                    const double* q = sm.S + (J * SB + (r & 15)) * PS + b * SB + (c & 15);
+                    v = make_double2(q[0], q[1]);
+                }
+                *reinterpret_cast<double2*>(Dblk + 2 * idx) = v;
+            }
+            // the D tiles of one output run strictly in order: plain read-modify-write is race-free (and it must precede the
+            // publication: the next D tile of this output can start as soon as the tiles that wait for this one have run)
+            if (ctid == 0) scal[2 * o] = (j > 0 ? __ldcg(scal + 2 * o) : 0.0) + ld_add;
+        }
+    }
+    __threadfence();
+    fence_proxy_async();
     named_bar_sync(1, NTHR);
-    if (ctid == 0) CH_STAMP(trs, 1);
-#endif
-    const int fail = potf2_inv_block<NTHR, 2>(sm, ctid, Ablk, n_pad, &ld_add);
 #ifdef CHOL_TRACE
-    if (ctid == 0) CH_STAMP(trs, 5);
+    if (ctid == 0) CH_STAMP(trs, 6);
 #endif
-    if (fail) {
-        if (ctid == 0) info[o] = j * NB + fail;
-    } else {
-        double* Dblk = Dinv + (rb + (int64_t)j * NB) * NB;
-        for (int idx = ctid; idx < NB * NB; idx += NTHR) {
-            const int r = idx >> 7, c = idx & 127;
-            const int b = r >> 4, J = c >> 4;
-            double v = 0.0;
-            if (b == J) v = sm.InvD[(b * SB + (r & 15)) * (SB + 1) + (c & 15)];      // (zero above the diagonal)
-            else if (b > J) v = sm.S[(J * SB + (r & 15)) * PS + b * SB + (c & 15)];   // parked in the upper block (J, b)
-            Dblk[idx] = v;
+    if (ctid == 0) red_release_gpu_add(dprog, 1);
+    if (!fail) {
+        for (int idx = ctid; idx < NB * NB / 2; idx += NTHR) {
+            const int r = idx >> 6, c = (idx & 63) * 2;
+            const double* q = sm.S + r * PS + c;
+            // (above the diagonal: parked inverse blocks and spill of the trailing updates)
+            *reinterpret_cast<double2*>(Ablk + (int64_t)r * n_pad + c) = make_double2(c <= r ? q[0] : 0.0, c + 1 <= r ? q[1] : 0.0);
         }
-        // the D tiles of one output run strictly in order: plain read-modify-write is race-free
-        if (ctid == 0) scal[2 * o] = (j > 0 ? __ldcg(scal + 2 * o) : 0.0) + ld_add;
+        __threadfence();
     }
+    named_bar_sync(1, NTHR);   // everyone is done with the borrowed shared memory
 }
 
 // ------------------------------------------------------------------------------------------
@@ -644,7 +655,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                 if (!vs_loaded) load_vs();
                 if (id.kind == TK_ROW) {
                     // inv(L_jj): published by the D tile of column j
-                    wait_counter(dprog, Cfg::NCW * (j + 1));
+                    wait_counter(dprog, j + 1);
                     fence_proxy_async();
                     for (int ch = 0; ch < NCH; ch++) {
                         mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
@@ -699,17 +710,8 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                              unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); chol_trace_cur[sm_ & 255] = trs; }
             named_bar_sync(1, Cfg::NCW * 32);
 #endif
-            if (!skip) chol_d_tile<Cfg::NCW * 32>(base, ctid, p.A, p.Dinv, p.n_pad, rb, j, o, p.info, p.scal, trs);
-            __threadfence();
-            fence_proxy_async();
-            named_bar_sync(1, Cfg::NCW * 32);   // everyone is done with the borrowed shared memory
-#ifdef CHOL_TRACE
-            if (ctid == 0) CH_STAMP(trs, 6);
-#endif
-            if (lane == 0) {
-                red_release_gpu_add(dprog, 1);
-                mbar_arrive(d_done);
-            }
+            chol_d_tile<Cfg::NCW * 32>(base, ctid, p.A, p.Dinv, p.n_pad, rb, j, o, p.info, p.scal, dprog, skip, trs);
+            if (lane == 0) mbar_arrive(d_done);
             continue;
         }
         if (skip) {
@@ -1076,11 +1078,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 // every consumer warp is done with the previous tile (the barrier that ends every tile), its MMAs have completed
                 // (acc_full) and both loader warps are parked on d_done: the ring and the T buffer are free to borrow
                 named_bar_sync(1, I8_NCW * 32);
-                if (!skip) chol_d_tile<I8_NCW * 32>(base, tid, p.A, p.Dinv, p.n_pad, rb, j, o, p.info, p.scal, -1);
-                __threadfence();
-                fence_proxy_async();
-                named_bar_sync(1, I8_NCW * 32);
-                if (tid == 0) red_release_gpu_add(dprog, 1);
+                chol_d_tile<I8_NCW * 32>(base, tid, p.A, p.Dinv, p.n_pad, rb, j, o, p.info, p.scal, dprog, skip, -1);
                 if (lane == 0) {
                     mbar_arrive(&d_done[0]);
                     mbar_arrive(&d_done[1]);

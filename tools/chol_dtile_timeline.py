@@ -36,12 +36,13 @@ lib.mogp_debug_chol_trace2.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctype
 buf2 = (ctypes.c_ulonglong * (32 * cnt))()
 lib.mogp_debug_chol_trace2(buf2, 32 * cnt)
 b = np.array(buf2[:], dtype=np.uint64).astype(np.int64).reshape(cnt, 32)
-ev = ["start", "a1(0) done", "a2(0)+barriers", "after b1(0)", "a1(1) done", "b2(0) done (warp 1)", "after barrier", "a2(1) done",
-      None, None, "after b1(3)", "a1(4) done", "b2(3) done (warp 1)", "after barrier", "a2(4) done"]
-for k in range(1, 15):
-    if ev[k] is None or k == 10:
-        continue
-    print("# factor phases, median over D tiles (us): %-24s +%.2f" % (ev[k], np.median((b[:, k] - b[:, k - 1]) / 1e3)))
-print("# (b2 done is measured from 'after b1')", "b2(0): %.2f" % np.median((b[:, 5] - b[:, 3]) / 1e3), "b2(3): %.2f" % np.median((b[:, 12] - b[:, 10]) / 1e3),
-      " a1(1): %.2f" % np.median((b[:, 4] - b[:, 3]) / 1e3), " a1(4): %.2f" % np.median((b[:, 11] - b[:, 10]) / 1e3))
+# stamps of potf2_inv_block (shared memory, flushed after the tile): 0 start, 1 a1(0) done, then per panel s = 0..6:
+# 2+3s chain warp done (a2n + b1n + a1(s+1)), 3+3s trailing update done (warp 1), 4+3s block row s of the inverse done (warp 1)
+med = lambda x: float(np.median(x)) / 1e3
+print("# a1(0): %.2f us" % med(b[:, 1] - b[:, 0]))
+start = b[:, 1]
+for s_ in range(7):
+    ch, up, iv = b[:, 2 + 3 * s_], b[:, 3 + 3 * s_], b[:, 4 + 3 * s_]
+    print("# panel %d (us from the barrier): chain warp %.2f | a2r + trailing update %.2f, + inverse row %.2f" % (s_, med(ch - start), med(up - start), med(iv - start)))
+    start = np.maximum(ch, iv)
 print(gp._handle.timings())
