@@ -378,6 +378,8 @@ def other_configs(device, peak_dmma):
                  "device_ms": {"kmat": tm["kmat_ms"] / 2, "cholesky": tm["chol_ms"] / 2, "fit_solves": tm["solve_ms"] / 2,
                                "kstar_and_mean": tm["kstar_ms"] / 2, "predict_trsm": tm["trsm_ms"] / 2},
                  "cholesky_tflops": chol_tf, "cholesky_frac_of_dmma_peak": chol_tf / peak_dmma,
+                 "cholesky_path": ("int8 tcgen05 history products (8 planes per operand), FP64 diagonal tiles and epilogue: "
+                                   "FP64-EQUIVALENT TFLOP/s") if tm.get("chol_i8_outputs", 0) > 0 else "FP64 DMMA",
                  "kmat_GBps": (8.0 * n * n + 8.0 * n * d) / (tm["kmat_ms"] / 2 * 1e-3) * 1e-9,
                  "all_finite": bool(np.all(np.isfinite(r.mean)) and np.all(np.isfinite(r.unc)))}
     gp.close()
@@ -392,6 +394,27 @@ def workload_config(name, wl, gpus):
             "parallelism": "outputs block-partitioned over %d rank(s), one all-gather of posteriors" % gpus,
             "l2_policy": "working set (%.1f GB of factors + workspace per step) exceeds the 126 MB L2; no flush needed"
                          % (E * n * n * 8 / 1e9)}
+
+
+def cholesky_report(libmogp, device, tm, n_outputs, n, steps, peak_dmma):
+    """The factorisation phase of the timed steps: which kernel ran, FP64(-equivalent) TFLOP/s against the DMMA issue peak, and
+    for the tcgen05 path its int8 tensor ops against the int8 issue peak (DESIGN.md section 3 states the count: per ROW / DIAG
+    tile of block column j, 4 j K-steps x 36 plane pairs x 2*128*64*32)."""
+    if not tm.get("chol_ms"):
+        return {"path": "none"}
+    ms = tm["chol_ms"] / steps
+    T = (n + 127) // 128
+    tf = n_outputs * (n ** 3) / 3.0 / (ms * 1e-3) * 1e-12
+    out = {"ms": ms, "outputs": n_outputs, "fp64_equivalent_tflops": tf, "vs_dmma_peak": tf / peak_dmma, "dmma_peak_tflops": peak_dmma}
+    if tm.get("chol_i8_outputs", 0) > 0:
+        ops = n_outputs * sum(2 * (T - j) * 4 * j for j in range(T)) * 36 * 2.0 * 128 * 64 * 32
+        peak256, _ = libmogp.peak_i8_tops(device)
+        out.update(path="int8 tcgen05 (chol_i8_kernel: 8 signed 7-bit planes per operand, pairs t + u <= 9; diagonal tiles, "
+                        "triangular solves against inv(L_jj) and recombination in FP64)",
+                   int8_tops=ops / (ms * 1e-3) * 1e-12, int8_peak_tops=peak256, int8_frac=ops / (ms * 1e-3) * 1e-12 / peak256)
+    else:
+        out["path"] = "FP64 DMMA (chol_dataflow_kernel)"
+    return out
 
 
 def run_b200(args, wl):
@@ -522,6 +545,13 @@ def run_b200(args, wl):
     else:
         config["trsm_path"] = "FP64 DMMA"
         dtype = "f64"
+    cholesky = cholesky_report(libmogp, device, tm, e_loc, n, args.steps, peak)
+    if cholesky["path"].startswith("int8"):
+        config["cholesky_path"] = cholesky["path"]
+        dtype = dtype.replace("f64 (", "f64 (Cholesky history products: 8 x int8 planes on tcgen05, exact s32 accumulation, FP64 diagonal tiles and epilogue; ") \
+            if "(" in dtype else "f64 (Cholesky history products: 8 x int8 planes on tcgen05, exact s32 accumulation, FP64 diagonal tiles and epilogue)"
+    else:
+        config["cholesky_path"] = cholesky["path"]
     line = {
         "metric": "gp_fit_predict_seconds", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
@@ -545,6 +575,7 @@ def run_b200(args, wl):
         "host_wall_ms_per_step": dict(wall_ms, predict_device_part=tm["predict_device_wall_ms"] / args.steps,
                                       predict_copy_out=tm["predict_d2h_wall_ms"] / args.steps),
         "cholesky_tflops": (e_loc * (n ** 3) / 3.0) / (tm["chol_ms"] / args.steps * 1e-3) * 1e-12 if tm["chol_ms"] else None,
+        "cholesky": cholesky,
         "fit_tflops": (e_loc * (n ** 3) / 3.0) / (tm["fit_ms"] / args.steps * 1e-3) * 1e-12 if tm["fit_ms"] else None,
     }
     if not args.no_cpu:
@@ -567,7 +598,9 @@ def run_b200(args, wl):
         # the same step on the all-FP64 path (MOGP_TRSM_I8=0 is read when an emulator is constructed), in the same run on the
         # same box: the number the int8 figures stand beside.  One warm-up step, two timed.
         saved = os.environ.get("MOGP_TRSM_I8")
+        saved_c = os.environ.get("MOGP_CHOL_I8")
         os.environ["MOGP_TRSM_I8"] = "0"
+        os.environ["MOGP_CHOL_I8"] = "0"
         try:
             gpf = MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget, device=device)
             step(gpf)
@@ -581,9 +614,14 @@ def run_b200(args, wl):
             line["all_fp64_path"] = {"value": dtf, "unit": "s", "predict_trsm_ms": tf["trsm_ms"] / 2, "cholesky_ms": tf["chol_ms"] / 2,
                                      "trsm_tflops": trsm_flops / (tf["trsm_ms"] / 2 * 1e-3) * 1e-12,
                                      "var_max_abs_int8_vs_fp64": float(np.max(np.abs(rf.unc - res.unc))),
-                                     "mean_identical": bool(np.array_equal(rf.mean, res.mean)),
-                                     "note": "MOGP_TRSM_I8=0: predict_trsm_kernel (DMMA) instead of i8_trsm_kernel; everything else identical"}
+                                     "mean_max_rel_int8_vs_fp64": float(np.max(np.abs(rf.mean - res.mean)) / np.max(np.abs(rf.mean))),
+                                     "note": "MOGP_TRSM_I8=0 MOGP_CHOL_I8=0: predict_trsm_kernel and chol_dataflow_kernel (DMMA) instead "
+                                             "of i8_trsm_kernel and chol_i8_kernel; everything else identical"}
         finally:
+            if saved_c is None:
+                os.environ.pop("MOGP_CHOL_I8", None)
+            else:
+                os.environ["MOGP_CHOL_I8"] = saved_c
             if saved is None:
                 os.environ.pop("MOGP_TRSM_I8", None)
             else:

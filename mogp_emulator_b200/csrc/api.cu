@@ -113,8 +113,8 @@ constexpr int I8_DEFAULT_PLANES = 7;   // default of MOGP_TRSM_I8 (see mogp_crea
 // MOGP_CHOL_I8 unset: the Cholesky takes the tcgen05 path when outputs x (block rows)^2 of the launch reaches this.  The
 // history products are ~2 x faster there (profiles/r02_chol_i8_check.txt: 32 x n=4096 24.7 -> 11.9 ms, one n=16384 43.5 -> 23.0 ms),
 // but a launch of a few small matrices is bound by the chain D(j) -> ROW(j+1, ., j) -> DIAG(j+1) -> D(j+1), whose tiles have the
-// longer epilogue on that path (4 x n=4096: 4.05 -> 4.71 ms, one: 3.65 -> 3.92 ms).  Work / chain ~ outputs x T^3 / T.
-constexpr int64_t CHOL_I8_MIN_WORK = 6144;
+// longer epilogue on that path (one n=4096 matrix: 2.64 ms FP64, 2.79 ms int8; four: 3.52 / 3.31 ms).  Work / chain ~ outputs x T^3 / T.
+constexpr int64_t CHOL_I8_MIN_WORK = 4096;
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H,
        T_I8_PREP, T_I8_CHECK, T_I8_ROWS, T_I8_NROWS, T_I8_NFALLBACK, T_CHOL_I8_N, T_COUNT };
 

@@ -312,7 +312,13 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* l
         } else {
             static_assert(NTHR - 32 >= NB - 2 * SB, "one thread per row below the next diagonal block");
             const int tt = tid - 32;
-            if (tt < nrow2) rows_below(j0, j0 + 2 * SB + tt);                                        // a2r
+            if (tt < nrow2) rows_below(j0, j0 + 2 * SB + tt);                                        // a2r (warps 1..3 at most)
+            // block row s of the inverse (panel s of L is final): Inv_ss by warp 7 (it has no row of a2r), then X_sJ for J < s by the
+            // warps 1..7 -- before the trailing update, which has to wait for the chain warp's 16 rows anyway
+            if (tid >= NTHR - 32) inv_diag16(s, tid & 31);
+            named_bar_sync(BAR_ALL + 1, NTHR - 32);
+            inv_offdiag(s, (tid >> 5) - 1, tid & 31);
+            CH_STAMP2(tid == 32, 3 + 3 * s);      // block row s of the inverse done (warp 1)
             named_bar_sync(BAR_ALL + 2, NTHR);
             // (b1r + b2) the trailing update below the next diagonal block on the FP64 tensor pipe:
             //     S[r][c] -= sum_k P[r][k] P[c][k],   P = S[:, j0 .. j0+15],   rows r >= j0+32, columns j0+16 <= c <= r
@@ -320,7 +326,8 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* l
             // dot-then-subtract form of the scalar update it replaces), dealt round-robin to the seven warps.  Tiles that cross the
             // diagonal also write entries above it: nothing reads those (potf2_diag16, rows_below and this update read the lower
             // triangle, the parked inverse blocks of these rows are written later, the write-back masks).  Scalar FMAs from shared
-            // memory (one 8-byte load per FMA) took 8.3 us for panel 0 -- twice the chain warp's 4.6 us; this takes under 1 us.
+            // memory (one 8-byte load per FMA) took 8.3 us for panel 0 -- twice the chain warp's panel; this runs at the SM's FP64
+            // rate (216 DMMAs for panel 0: 1.8 us).
             {
                 const int wid = (tid >> 5) - 1, lane = tid & 31;
                 const int mt = nrow2 / SB;                       // 16-row tiles; tile row mi has 2 + mi PAIRS of column tiles
@@ -332,12 +339,7 @@ __device__ __forceinline__ int potf2_inv_block(Potf2Smem& sm, int tid, double* l
                     update_tile(j0, j0 + 2 * SB + SB * mi, j0 + SB + 16 * ni, lane, std::integral_constant<int, 2>());
                 }
             }
-            CH_STAMP2(tid == 32, 3 + 3 * s);      // trailing update done
-            // block row s of the inverse (panel s of L is final): Inv_ss by warp 1, then X_sJ for J < s by the warps 1..7
-            if (tid < 64) inv_diag16(s, tid & 31);
-            named_bar_sync(BAR_ALL + 1, NTHR - 32);
-            inv_offdiag(s, (tid >> 5) - 1, tid & 31);
-            CH_STAMP2(tid == 32, 4 + 3 * s);      // block row s of the inverse done (warp 1)
+            CH_STAMP2(tid == 32, 4 + 3 * s);      // trailing update done (warp 1)
         }
         named_bar_sync(BAR_ALL, NTHR);
         if (sm.fail) return sm.fail;

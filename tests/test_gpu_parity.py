@@ -744,33 +744,85 @@ def test_i8_trsm_accuracy_check_falls_back_to_fp64(mogp, monkeypatch):
 
 def test_full_size_c3_takes_the_int8_path(mogp, monkeypatch):
     """The headline configuration itself (BASELINE config 3: 32 outputs x n=4096 x d=10 SqExp, 10000 test points, nugget
-    1e-6) on the path the benchmark measures: every output against the all-FP64 DMMA path, outputs 0 and 31 against the
-    CPU oracle (the default path at the headline shape was not in the driver-run suite)."""
+    1e-6) on the path the benchmark measures -- Cholesky history products and predict TRSM on the int8 tensor cores: every
+    output against the all-FP64 DMMA path, outputs 0 and 31 against the CPU oracle (the default path at the
+    headline shape was not in the driver-run suite)."""
     X, Y, Xs = orc.make_workload(4096, 10, 32, 10000, seed=2)
     thetas = np.zeros((32, 11))
     thetas[:, :10] = 1.0 + 0.01 * np.arange(32)[:, None]
     nugget = 1e-6
     _with_planes(monkeypatch, 7)
+    monkeypatch.delenv("MOGP_CHOL_I8", raising=False)              # the library's own choice: the tcgen05 factorisation here
     gp = mogp.MultiOutputGP_GPU(X, Y, nugget=nugget)
+    gp.timings(reset=True)
     gp.fit(thetas)
+    assert gp.timings()["chol_i8_outputs"] == 32
     gp.timings(reset=True)
     res = gp.predict(Xs, deriv=False)
     t = gp.timings()
-    assert t["i8_block_rows"] == 32 and t["i8_fallbacks"] == 0
+    assert t["i8_block_rows"] == 32 and t["i8_fallbacks"] == 0 and t["i8_prep_ms"] < 0.05      # no slicing pass: the planes of L came with the factor
     gp.close()
     _with_planes(monkeypatch, 0)
+    monkeypatch.setenv("MOGP_CHOL_I8", "0")
     gp = mogp.MultiOutputGP_GPU(X, Y, nugget=nugget)
     gp.fit(thetas)
     ref = gp.predict(Xs, deriv=False)
-    assert gp.timings()["i8_block_rows"] == 0
+    t = gp.timings()
+    assert t["i8_block_rows"] == 0 and t["chol_i8_outputs"] == 0
     gp.close()
-    assert np.array_equal(res.mean, ref.mean)
+    assert_allclose(res.mean, ref.mean, rtol=1e-9, atol=1e-9 * np.abs(ref.mean).max())
     tol = 1e-4 * np.abs(ref.unc) + 1e-4 * nugget
-    assert (np.abs(res.unc - ref.unc) / tol).max() < 0.01
+    assert (np.abs(res.unc - ref.unc) / tol).max() < 0.02
     for o in (0, 31):
         rm, rv = orc.OracleGP(X, Y[o], nugget=nugget, priors="weak").fit(thetas[o]).predict(Xs)
         assert_allclose(res.mean[o], rm, rtol=1e-6, atol=1e-9)
         assert_allclose(res.unc[o], rv, rtol=1e-4, atol=1e-4 * nugget)
+
+
+@pytest.mark.parametrize("kernel,nugget,n,d,E,theta_corr", [
+    ("SquaredExponential", 1e-6, 1000, 5, 3, 1.0),             # ragged last block row (n_pad = 1024)
+    ("Matern52", 1e-8, 1536, 3, 2, -1.0),                      # cond(K) ~ 1e10
+    ("Matern52", "adaptive", 777, 4, 2, 1.0),                  # adaptive nugget: 0.0 is chosen
+])
+def test_cholesky_int8_path_matches_fp64_path_and_oracle(mogp, monkeypatch, kernel, nugget, n, d, E, theta_corr):
+    """chol_i8_kernel (history products of the factorisation on the int8 tensor cores, forced with MOGP_CHOL_I8=1 at sizes the
+    oracle handles) against chol_dataflow_kernel (MOGP_CHOL_I8=0) and the CPU oracle: factor, log-determinant / quadratic form,
+    posterior, and the planes of L it leaves for the predict TRSM (a many-right-hand-side predict without a slicing pass)."""
+    from mogp_emulator_b200 import libmogp
+    X, Y, Xs = orc.make_workload(n, d, E, 5000, seed=61)      # (panels x outputs >= SMs: the int8 predict path)
+    thetas = np.zeros((E, d + 1))
+    thetas[:, :d] = theta_corr + 0.02 * np.arange(E)[:, None]
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MOGP_CHOL_I8", mode)
+        gp = mogp.MultiOutputGP_GPU(X, Y, kernel=kernel, nugget=nugget)
+        gp.timings(reset=True)
+        gp.fit(thetas)
+        t = gp.timings(reset=True)
+        assert t["chol_i8_outputs"] == (E if mode == "1" else 0)
+        L = np.tril(gp._handle.get(E - 1, libmogp.GET_L))
+        lp = [gp.logposterior(o) for o in range(E)] if hasattr(gp, "logposterior") else None
+        res = gp.predict(Xs, deriv=False)
+        t = gp.timings()
+        if mode == "1":
+            assert t["i8_block_rows"] > 0 and t["i8_prep_ms"] < 0.05 and t["i8_fallbacks"] == 0
+        out[mode] = (L, lp, res, list(np.atleast_1d(gp.nugget)))
+        gp.close()
+    (L0, lp0, r0, nug0), (L1, lp1, r1, nug1) = out["0"], out["1"]
+    assert nug0 == nug1
+    nug = float(nug0[0])
+    ref = orc.OracleGP(X, Y[E - 1], kernel=kernel, nugget=nugget, priors="weak").fit(thetas[E - 1])
+    kappa = np.linalg.cond(ref.get_K_matrix() + nug * np.eye(n))
+    # the factor: both GPU paths sit at the same distance from LAPACK's, set by the conditioning
+    assert np.linalg.norm(L1 - ref.L) / np.linalg.norm(ref.L) < max(1e-12, 1e-15 * kappa)
+    assert np.linalg.norm(L1 - L0) / np.linalg.norm(L0) < max(1e-12, 1e-15 * kappa)
+    assert_allclose(lp1, lp0, rtol=_logpost_rtol(ref.get_K_matrix(), max(nug, 1e-12)))
+    assert_allclose(r1.mean, r0.mean, rtol=1e-6, atol=1e-6 * np.abs(r0.mean).max() * min(1.0, 1e-10 * kappa))
+    tol = 1e-4 * np.abs(r0.unc) + 1e-4 * nug + 1e-13
+    assert (np.abs(r1.unc - r0.unc) / tol).max() < 0.05
+    rm, rv = ref.predict(Xs)
+    assert_allclose(r1.mean[E - 1], rm, rtol=1e-6, atol=1e-6 * np.abs(rm).max())
+    assert_allclose(r1.unc[E - 1], rv, rtol=1e-4, atol=1e-4 * nug + 1e-12)
 
 
 def test_integration_route_b_stub_against_reference_golden(mogp):

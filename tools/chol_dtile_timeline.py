@@ -37,12 +37,12 @@ buf2 = (ctypes.c_ulonglong * (32 * cnt))()
 lib.mogp_debug_chol_trace2(buf2, 32 * cnt)
 b = np.array(buf2[:], dtype=np.uint64).astype(np.int64).reshape(cnt, 32)
 # stamps of potf2_inv_block (shared memory, flushed after the tile): 0 start, 1 a1(0) done, then per panel s = 0..6:
-# 2+3s chain warp done (a2n + b1n + a1(s+1)), 3+3s trailing update done (warp 1), 4+3s block row s of the inverse done (warp 1)
+# 2+3s chain warp done (a2n + b1n + a1(s+1)), 3+3s a2r + block row s of the inverse done (warp 1), 4+3s trailing update done (warp 1)
 med = lambda x: float(np.median(x)) / 1e3
 print("# a1(0): %.2f us" % med(b[:, 1] - b[:, 0]))
 start = b[:, 1]
 for s_ in range(7):
     ch, up, iv = b[:, 2 + 3 * s_], b[:, 3 + 3 * s_], b[:, 4 + 3 * s_]
-    print("# panel %d (us from the barrier): chain warp %.2f | a2r + trailing update %.2f, + inverse row %.2f" % (s_, med(ch - start), med(up - start), med(iv - start)))
+    print("# panel %d (us from the barrier): chain warp %.2f | a2r + inverse row %.2f, + trailing update %.2f" % (s_, med(ch - start), med(up - start), med(iv - start)))
     start = np.maximum(ch, iv)
 print(gp._handle.timings())
