@@ -25,7 +25,17 @@ mo.fit(np.tile(np.array([1.0, 0.9, 1.1, 0.0]), (40, 1)))
 r8 = mo.predict(Xs, deriv=False)
 assert mo.timings()["i8_block_rows"] == 3, mo.timings()
 mo.close()
-print("case done", float(r.mean[0, 0]), float(c.unc[0, 0]), float(r8.unc[0, 0]))
+# the factorisation with its history products on the int8 tensor cores (csrc/chol.cu chol_i8_kernel), forced at a small size;
+# the predict then reads the planes of L the factorisation left
+os.environ["MOGP_CHOL_I8"] = "1"
+X, Y, Xs = orc.make_workload(500, 3, 40, 600, seed=3)
+mo = MultiOutputGP_GPU(X, Y, nugget=1e-6)
+mo.fit(np.tile(np.array([1.0, 0.9, 1.1, 0.0]), (40, 1)))
+assert mo.timings()["chol_i8_outputs"] == 40, mo.timings()
+rc8 = mo.predict(Xs, deriv=False)
+assert mo.timings()["i8_block_rows"] == 4, mo.timings()
+mo.close()
+print("case done", float(r.mean[0, 0]), float(c.unc[0, 0]), float(r8.unc[0, 0]), float(rc8.unc[0, 0]))
 PY
 for tool in memcheck synccheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 200 python /tmp/san_case.py > gpurun_out/sanitizer_$tool.log 2>&1
