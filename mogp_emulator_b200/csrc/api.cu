@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <limits>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges are no-ops unless a profiler injects its library
@@ -184,6 +186,25 @@ struct mogp_comm {
             return (e__ == cudaErrorMemoryAllocation) ? MOGP_ERR_NOMEM : MOGP_ERR_CUDA;              \
         }                                                                                            \
     } while (0)
+
+// Copy-out of the posteriors from the pinned staging buffer into the caller's arrays: rows[k] = {dst, src}, `bytes` each.  The
+// destination is usually freshly allocated (numpy.empty): its first touch faults every page, which bounds a single thread at
+// ~8 GB/s (0.65 ms for the 5 MB of a C3 predict, 5 % of an 8-GPU step); a few threads take the faults in parallel.
+static void copy_rows(const std::vector<std::pair<double*, const double*>>& rows, size_t bytes) {
+    const size_t total = rows.size() * bytes;
+    const int nt = total >= (size_t)1 << 20 ? (int)std::min<size_t>(4, rows.size()) : 1;
+    auto work = [&](int t) {
+        for (size_t k = t; k < rows.size(); k += nt) memcpy(rows[k].first, rows[k].second, bytes);
+    };
+    if (nt == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
 
 static int grow(double** p, size_t* cap, size_t bytes, int device) {
     // device == -1: pinned host
@@ -899,9 +920,13 @@ int mogp_predict(mogp_handle* h, const double* Xs, int64_t m, int32_t want_var, 
     if ((rc = grow(&h->h_res, &h->h_res_cap, sizeof(double) * (size_t)h->E * 2 * m, -1))) return rc;
     API_CUDA(cudaMemcpyAsync(h->h_res, h->res, sizeof(double) * (size_t)h->E * 2 * m, cudaMemcpyDeviceToHost, h->main));
     API_CUDA(cudaStreamSynchronize(h->main));
-    for (int o = 0; o < h->E; o++) {
-        memcpy(mean + (size_t)o * m, h->h_res + (size_t)o * 2 * m, sizeof(double) * m);
-        if (want_var) memcpy(var + (size_t)o * m, h->h_res + (size_t)o * 2 * m + m, sizeof(double) * m);
+    {
+        std::vector<std::pair<double*, const double*>> rows;
+        for (int o = 0; o < h->E; o++) {
+            rows.emplace_back(mean + (size_t)o * m, h->h_res + (size_t)o * 2 * m);
+            if (want_var) rows.emplace_back(var + (size_t)o * m, h->h_res + (size_t)o * 2 * m + m);
+        }
+        copy_rows(rows, sizeof(double) * m);
     }
     const auto t2 = std::chrono::steady_clock::now();
     h->timings[T_PRED_HOST] += std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -1510,14 +1535,18 @@ int mogp_predict_allgather(mogp_handle* h, mogp_comm* comm, const double* Xs, in
     tc.mark("pack + enqueue all-gather + D2H");
     API_CUDA(cudaStreamSynchronize(h->main));
     tc.mark("all-gather + D2H complete");
-    for (int rk = 0; rk < comm->world; rk++) {
-        const double* src = comm->h_recv + (size_t)rk * send_n;
-        for (int o = 0; o < e_pad; o++) {
-            const size_t row = (size_t)rk * e_pad + o;
-            memcpy(mean_all + row * m, src + (size_t)o * 2 * m, sizeof(double) * m);
-            memcpy(var_all + row * m, src + (size_t)o * 2 * m + m, sizeof(double) * m);
-            if (status_all) status_all[row] = (int32_t)src[blk + o];
+    {
+        std::vector<std::pair<double*, const double*>> rows;
+        for (int rk = 0; rk < comm->world; rk++) {
+            const double* src = comm->h_recv + (size_t)rk * send_n;
+            for (int o = 0; o < e_pad; o++) {
+                const size_t row = (size_t)rk * e_pad + o;
+                rows.emplace_back(mean_all + row * m, src + (size_t)o * 2 * m);
+                rows.emplace_back(var_all + row * m, src + (size_t)o * 2 * m + m);
+                if (status_all) status_all[row] = (int32_t)src[blk + o];
+            }
         }
+        copy_rows(rows, sizeof(double) * m);
     }
     tc.mark("host unpack");
     return MOGP_OK;
