@@ -66,7 +66,11 @@ int mogp_trim(void);
  *   quad   = y^T K^-1 y,   logdet = log det(K + nugget I),   nugget = the nugget actually used,
  *   status = MOGP_OK | MOGP_ERR_NOT_PD (that output is then marked not fit; others proceed).
  * The data part of the reference's current_logpost is 0.5*(quad + logdet + n*log(2 pi)); priors are
- * host-side scalars added by the caller.  Return value is MOGP_OK unless the call itself failed. */
+ * host-side scalars added by the caller.  Return value is MOGP_OK unless the call itself failed.
+ * Arithmetic: IEEE FP64 throughout, except that a call with enough factorisation work (outputs x (n/128)^2 >= 4096) evaluates
+ * the O(n^3) history products of the Cholesky as EXACT integer GEMM on 8 signed 7-bit planes per operand (tcgen05 int8 tensor
+ * cores; products resolved to 2^-63 of the squared scale -- the backward error of an FP64 blocked factorisation); pivots, info,
+ * the adaptive-nugget decisions, triangular solves and the log-determinant are FP64.  MOGP_CHOL_I8=0: FP64 tensor pipe only. */
 int mogp_fit(mogp_handle* h, int32_t first, int32_t count, const double* thetas, int32_t n_params,
              double* quad_out, double* logdet_out, double* nugget_out, int32_t* status_out);
 

@@ -113,7 +113,7 @@ using namespace mogp;
 constexpr int MAXM = 32;  // mean-function vectors per output (grad_max_mean())
 constexpr int I8_DEFAULT_PLANES = 7;   // default of MOGP_TRSM_I8 (see mogp_create)
 // MOGP_CHOL_I8 unset: the Cholesky takes the tcgen05 path when outputs x (block rows)^2 of the launch reaches this.  The
-// history products are ~2 x faster there (profiles/r02_chol_i8_check.txt: 32 x n=4096 24.7 -> 11.9 ms, one n=16384 43.5 -> 23.0 ms),
+// history products are ~2 x faster there (profiles/r02b_chol_i8_check.txt: 32 x n=4096 24.7 -> 11.9 ms, one n=16384 43.5 -> 23.0 ms),
 // but a launch of a few small matrices is bound by the chain D(j) -> ROW(j+1, ., j) -> DIAG(j+1) -> D(j+1), whose tiles have the
 // longer epilogue on that path (one n=4096 matrix: 2.64 ms FP64, 2.79 ms int8; four: 3.52 / 3.31 ms).  Work / chain ~ outputs x T^3 / T.
 constexpr int64_t CHOL_I8_MIN_WORK = 4096;
