@@ -252,7 +252,15 @@ int solve_alpha(const double* A_slab, int64_t n_pad, const double* Dinv_slab, co
     const int T = (int)(n_pad / NB);
     int C = 1;
     while (C * 2 <= g_max_cluster && C * 4 <= T) C *= 2;   // at least two blocks of the vector per CTA
+    // Wide clusters have to find their SMs inside one GPC, so fewer of them are resident at once than the SM count suggests
+    // (tools/solve_sweep.py, n = 4096, ms per launch: 8 outputs 0.99 at width 16 / 0.62 at 8; 16 outputs 1.17 at 8 / 0.84 at 4;
+    // 32 outputs 0.98 at 4 / 1.27 at 2): beyond width 4, keep clusters x width within 64 CTAs.
+    while (C > 4 && C * count > 64) C /= 2;
     while (C > 1 && C * count > n_sms) C /= 2;             // many outputs: all clusters resident at once beats wide clusters
+    {
+        const char* e = getenv("MOGP_SOLVE_CLUSTER");      // (tuning aid: tools/solve_sweep.py)
+        if (e && atoi(e) >= 1 && atoi(e) <= g_max_cluster && (atoi(e) & (atoi(e) - 1)) == 0) C = atoi(e);
+    }
     const int nown = (T + C - 1) / C;
     const size_t smem = (size_t)(nown * NB + C * NB + NB + 4 * NB + 16) * sizeof(double);
     if (smem > 200 * 1024) return 2;
