@@ -783,10 +783,11 @@ static int predict_device(mogp_handle* h, const double* Xs, int64_t m, int want_
                     const TrsmPlan cplan{npt, 1};
                     if (h->i8_check) {
                         // FP64 reference variances of the sampled test points (a copy of their K* rows: the FP64 kernel solves in
-                        // place) on the side stream: they take one SM per output while the persistent integer kernel starts on the
-                        // others and its remaining CTAs join the ticket queue as those SMs free up.  The side stream has the higher
-                        // priority and its kernel is enqueued first, the gather runs on the main stream before the fork: the check
-                        // must reach the SMs before the persistent kernel fills them all (it would otherwise run after it, serially).
+                        // place) on the side stream (higher priority, enqueued first; the gather runs on the main stream before the
+                        // fork).  When its CTAs reach the SMs first they take one SM per output while the persistent integer kernel
+                        // starts on the others, whose remaining CTAs join the ticket queue as those SMs free up (0.5 - 2 ms concurrent:
+                        // what happens when a slicing pass sits in front of the integer kernel, and at some output counts without
+                        // one); when the persistent kernel fills all SMs first, the check runs behind it (0.4 - 0.8 ms serial).
                         CUtensorMap tmWc;
                         if ((rc = grow(&h->chk_W, &h->chk_W_cap, sizeof(double) * (size_t)cnt * npt * np, h->device))) return rc;
                         if ((rc = grow(&h->chk_var, &h->chk_var_cap, sizeof(double) * (size_t)h->E * npt, h->device))) return rc;

@@ -21,6 +21,13 @@
 // memory (red.release / ld.acquire + proxy fences for the TMA readers) order the tiles, nothing deadlocks, and
 // there is no per-step launch, tail or wave quantisation; outputs interleave in the ticket order, so many small
 // factorisations fill the machine as well as one large one.
+//
+// Two kernels share the tiles, the ticket order, the progress counters and the D tile (chol_d_tile):
+//   chol_dataflow_kernel   the products above on the FP64 tensor pipe -- launches of a few small matrices, which are bound by
+//                          the chain D(j) -> ROW(j+1, ., j) -> DIAG(j+1, .) -> D(j+1);
+//   chol_i8_kernel         the history products sum_k L_ik L_jk^T as exact integer GEMM on 8 signed 7-bit planes per operand
+//                          (tcgen05.mma kind::i8, s32 accumulators in TMEM), FP64 epilogue -- launches bound by their O(n^3)
+//                          arithmetic (see the comment in front of it); it also leaves the planes of L the predict TRSM reads.
 #include <type_traits>
 
 #include "i8_common.cuh"
@@ -60,10 +67,9 @@ struct Potf2Smem {
 #endif
 };
 
-// pv = sqrt(d) and ri = 1 / sqrt(d) for a pivot d > 0.  A dependent FP64 instruction costs ~55 cycles on this chip and the
-// pivots of a factorisation are one dependency chain (tools/chol_dtile_timeline.py: sqrt() followed by 1.0 / pv is ~17 dependent
-// operations, 860 cycles per pivot, 128 pivots per diagonal tile on the critical path of every block column).  Only the
-// reciprocal is on that chain (the next pivot needs l = a * ri), so it is taken straight from the refined reciprocal square
+// pv = sqrt(d) and ri = 1 / sqrt(d) for a pivot d > 0.  A dependent FP64 instruction costs ~45-55 cycles on this chip and the
+// pivots of a factorisation are one dependency chain (128 per diagonal tile, on the critical path of every block column;
+// sqrt() followed by 1.0 / pv is ~17 dependent operations).  Only the reciprocal is on that chain (the next pivot needs l = a * ri), so it is taken straight from the refined reciprocal square
 // root -- hardware seed (MUFU.RSQ64H, what sqrt() starts from too) + one third-order step: 4 dependent operations, error
 // below an ulp -- and the square root itself (FMA-corrected d * y, correctly rounded) is computed off the chain.  LAPACK
 // scales by fl(1 / fl(sqrt(d))); this reciprocal differs from that by at most an ulp or two.
