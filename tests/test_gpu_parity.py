@@ -825,6 +825,28 @@ def test_cholesky_int8_path_matches_fp64_path_and_oracle(mogp, monkeypatch, kern
     assert_allclose(r1.unc[E - 1], rv, rtol=1e-4, atol=1e-4 * nug + 1e-12)
 
 
+def test_cholesky_int8_path_is_deterministic(mogp, monkeypatch):
+    """The persistent tcgen05 Cholesky hands its tiles to whichever CTA draws the ticket; the result may not depend on that:
+    exact integer products, fixed FP64 order inside a tile.  Repeated fits (more outputs than one launch group holds, ragged
+    size; a few larger matrices) must reproduce the first one bit for bit (tools/chol_i8_stress.py is the long version)."""
+    from mogp_emulator_b200 import libmogp
+    monkeypatch.setenv("MOGP_CHOL_I8", "1")
+    for n, d, E in ((300, 3, 70), (1500, 4, 5)):
+        X, Y, _ = orc.make_workload(n, d, E, 8, seed=71)
+        thetas = np.zeros((E, d + 1))
+        thetas[:, :d] = 1.0 + 0.01 * np.arange(E)[:, None]
+        h = libmogp.Handle(X, Y, 0, 2, 1e-6)
+        first = None
+        for rep in range(5):
+            quad, logdet, nug, status = h.fit(0, thetas)
+            assert status.max() == 0
+            key = (quad.tobytes(), logdet.tobytes(), h.get(E - 1, libmogp.GET_L).tobytes())
+            first = first or key
+            assert key == first
+        assert h.timings()["chol_i8_outputs"] == 5 * E
+        h.close()
+
+
 def test_integration_route_b_stub_against_reference_golden(mogp):
     """INTEGRATION.md route B: the ctypes stand-in for the reference's pybind ``DenseGP_GPU`` is executed VERBATIM from the
     document (only the library path is made absolute) and driven the way the reference front-end drives the native object

@@ -18,6 +18,7 @@ CASES = {
     "c3x4": (4096, 10, 4, 10000, 0, 2, 1e-6, None, False),
     "c2": (4096, 10, 1, 1000, 0, 2, 1e-6, None, True),
     "c4": (16384, 20, 1, 1000, 1, 0, 0.0, None, False),
+    "c5rank": (8192, 15, 8, 10000, 0, 2, 1e-6, None, False),        # 8 of the 32 outputs a rank of C5 holds
 }
 
 
