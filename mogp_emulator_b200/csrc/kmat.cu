@@ -43,7 +43,10 @@ __device__ const double kExp2Table[32] = {
 // below that the reference's numpy exp returns denormals or 0, this returns 3e-308 -- both below 1e-300.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
     const double magic = 6755399441055744.0;                // 1.5 * 2^52
-    x = fmax(x, -708.0);
+    // x = max(x, -708) on the high word (x <= 0: a more negative double has the larger unsigned high word; -708.0 is
+    // 0xC086200000000000): one integer instruction instead of a DSETP and two selects.  NaN (high word above 0xFFF0...) is
+    // clamped too -- the caller has flagged it (inf_flag) and the result is discarded.
+    x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
     const double t = fma(x, 46.16624130844683 /* 32 / ln2 */, magic);
     const int ni = __double2loint(t);                       // round(32 x / ln2), |ni| < 2^16
     const double nd = t - magic;
@@ -200,13 +203,22 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
             if (p.inf_flag) {
                 // the reference refuses infinite distances (calc_r2, Kernel.py:482-483); integer test of the bit pattern: the
                 // kernel is bound by the FP64 pipe
-                bool inf = false;
+                // r2 >= 0 (or NaN): the largest high word of the sub-tile tells whether any entry is inf / NaN; the exact test runs
+                // only then (one integer max per entry instead of two compares and a predicate)
+                int hmax = 0;
 #pragma unroll
                 for (int a = 0; a < KM_RA; a++)
 #pragma unroll
-                    for (int b = 0; b < 8; b++)
-                        inf |= (__double2hiint(r2[a][b]) == 0x7ff00000) && (__double2loint(r2[a][b]) == 0);
-                if (inf) atomicOr(p.inf_flag, 1);
+                    for (int b = 0; b < 8; b++) hmax = max(hmax, __double2hiint(r2[a][b]) & 0x7fffffff);
+                if (hmax >= 0x7ff00000) {
+                    bool inf = false;
+#pragma unroll
+                    for (int a = 0; a < KM_RA; a++)
+#pragma unroll
+                        for (int b = 0; b < 8; b++)
+                            inf |= (__double2hiint(r2[a][b]) == 0x7ff00000) && (__double2loint(r2[a][b]) == 0);
+                    if (inf) atomicOr(p.inf_flag, 1);
+                }
             }
             const double sigma2 = hyp[p.d];
             if (!CROSS) {
@@ -232,6 +244,7 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
                 }
             } else {
                 const int nvalid = (int)min((int64_t)128, p.n - (int64_t)J * 128);     // training points of this tile
+                const bool ragged = nvalid < 128;                                      // (CTA-uniform: only the last tile of a ragged n)
 #pragma unroll
                 for (int a = 0; a < KM_RA; a++) {
                     const int64_t row = (int64_t)I * KM_ROWS + ty + (KM_THREADS / 16) * a;  // test point
@@ -244,7 +257,7 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
                         for (int e = 0; e < 2; e++) {
                             const int c = 2 * tx + 32 * b + e;           // training point inside the tile
                             double w = sigma2 * kfun<KT>(r2[a][2 * b + e], tab_s);
-                            if (c >= nvalid) w = 0.0;
+                            if (ragged && c >= nvalid) w = 0.0;
                             sdot = fma(w, al_s[c], sdot);
                             v[e] = w;
                         }
