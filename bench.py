@@ -201,13 +201,31 @@ def ncu_traffic(workload, world):
         return None
 
 
-def measured_bf16():
-    """Driver-measured dense bf16 burst TFLOP/s of this pool's B200s (MEASURED_PEAKS.json), for context only."""
+_I8_PEAKS = {}
+
+
+def i8_peaks(libmogp, device):
+    """int8 tcgen05 issue peak of this device, measured in this run the way MEASURED_PEAKS.json measures its bf16 figures (which
+    has no int8 entry): BURST = best of 10 short runs of the M128 N256 K32 probe on an idle chip, SUSTAINED = the same probe back
+    to back for ~3 s, mean rate of the last 2 s (the chip is then on its power cap, like the kernels inside a benchmark step)."""
+    if device in _I8_PEAKS:
+        return _I8_PEAKS[device]
+    burst = max(libmogp.peak_i8_tops(device)[0] for _ in range(10))
+    rates, t0 = [], time.perf_counter()
+    while time.perf_counter() - t0 < 3.0:
+        rates.append((time.perf_counter() - t0, libmogp.peak_i8_tops(device, iters=100000)[0]))
+    late = [r for t, r in rates if t >= 1.0] or [r for t, r in rates]
+    _I8_PEAKS[device] = {"burst": burst, "sustained": float(np.mean(late)), "sustained_samples": len(late)}
+    return _I8_PEAKS[device]
+
+
+def measured_bf16(key="bf16_tflops"):
+    """Driver-measured dense bf16 burst (or sustained) TFLOP/s of this pool's B200s (MEASURED_PEAKS.json), for context only."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["bf16_tflops"])
+            return float(json.load(f)[key])
     except (OSError, ValueError, KeyError):
-        return 1590.0
+        return 1590.0 if key == "bf16_tflops" else 1330.0
 
 
 def run_c2(args, wl):
@@ -408,10 +426,12 @@ def cholesky_report(libmogp, device, tm, n_outputs, n, steps, peak_dmma):
     out = {"ms": ms, "outputs": n_outputs, "fp64_equivalent_tflops": tf, "vs_dmma_peak": tf / peak_dmma, "dmma_peak_tflops": peak_dmma}
     if tm.get("chol_i8_outputs", 0) > 0:
         ops = n_outputs * sum(2 * (T - j) * 4 * j for j in range(T)) * 36 * 2.0 * 128 * 64 * 32
-        peak256, _ = libmogp.peak_i8_tops(device)
+        pk = i8_peaks(libmogp, device)
+        tops = ops / (ms * 1e-3) * 1e-12
         out.update(path="int8 tcgen05 (chol_i8_kernel: 8 signed 7-bit planes per operand, pairs t + u <= 9; diagonal tiles, "
                         "triangular solves against inv(L_jj) and recombination in FP64)",
-                   int8_tops=ops / (ms * 1e-3) * 1e-12, int8_peak_tops=peak256, int8_frac=ops / (ms * 1e-3) * 1e-12 / peak256)
+                   int8_tops=tops, int8_peak_tops=pk["sustained"], int8_frac=tops / pk["sustained"],
+                   int8_peak_burst_tops=pk["burst"], int8_frac_of_burst=tops / pk["burst"])
     else:
         out["path"] = "FP64 DMMA (chol_dataflow_kernel)"
     return out
@@ -516,16 +536,19 @@ def run_b200(args, wl):
         panels = (m + 63) // 64
         ops_step = float(e_loc) * panels * (T * (T - 1) // 2) * 4 * pairs * 2.0 * 128 * 64 * 32
         rows_ms = tm["i8_rows_ms"] / args.steps
-        peak256, peak64 = libmogp.peak_i8_tops(device)
+        pk = i8_peaks(libmogp, device)
+        peak256 = pk["sustained"]
         ach = ops_step / (rows_ms * 1e-3) * 1e-12
         roofline = {"bound": "tensor", "kernel": "i8_trsm_kernel<%d> (V_i = inv(L_ii)(K*_i - sum_j L_ij V_j): tcgen05.mma kind::i8 on %d "
                                                  "plane pairs per K step, FP64 DMMA epilogue; one persistent launch)" % (planes, pairs),
                     "achieved": ach, "peak": peak256, "unit": "TOP/s", "frac": ach / peak256,
                     "traffic": ncu_traffic(args.workload + "-i8", world),
-                    "peak_source": "int8 tcgen05 issue peak (M128 N256 K32 MMAs from resident operands) measured in this run "
-                                   "(mogp_peak_i8) at the clock of an otherwise idle chip; the timed kernel runs under the 1 kW power "
-                                   "cap (see clocks).  MEASURED_PEAKS.json has no int8 entry; twice its bf16 burst figure would be "
-                                   "%.0f TOP/s" % (2.0 * measured_bf16()),
+                    "peak_source": "SUSTAINED int8 tcgen05 issue peak (M128 N256 K32 MMAs from resident operands, mogp_peak_i8, back to "
+                                   "back for 3 s: the chip on its power cap) measured in this run -- the kernel is timed inside a "
+                                   "long step under the same cap (see clocks); peak_burst / frac_of_burst: best of 10 short runs on "
+                                   "the idle chip.  MEASURED_PEAKS.json has no int8 entry; twice its bf16 figures would be %.0f "
+                                   "(burst) / %.0f (sustained) TOP/s" % (2.0 * measured_bf16(), 2.0 * measured_bf16("bf16_tflops_sustained")),
+                    "peak_burst": pk["burst"], "frac_of_burst": ach / pk["burst"],
                     "ops_per_launch": ops_step, "ms_per_launch": rows_ms,
                     "launches_per_step": 1.0, "outputs_per_launch": float(e_loc),
                     "fp64_equivalent_tflops": trsm_flops * (1.0 - 1.0 / T) / (rows_ms * 1e-3) * 1e-12,
