@@ -200,9 +200,17 @@ static void copy_rows(const std::vector<std::pair<double*, const double*>>& rows
         work(0);
         return;
     }
+    // (no exception may cross the C ABI: a thread that cannot be started leaves its share to the caller's thread)
     std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
+    std::vector<int> todo{0};
+    for (int t = 1; t < nt; t++) {
+        try {
+            th.emplace_back(work, t);
+        } catch (...) {
+            todo.push_back(t);
+        }
+    }
+    for (int t : todo) work(t);
     for (auto& x : th) x.join();
 }
 
