@@ -431,7 +431,9 @@ def cholesky_report(libmogp, device, tm, n_outputs, n, steps, peak_dmma):
         out.update(path="int8 tcgen05 (chol_i8_kernel: 8 signed 7-bit planes per operand, pairs t + u <= 9; diagonal tiles, "
                         "triangular solves against inv(L_jj) and recombination in FP64)",
                    int8_tops=tops, int8_peak_tops=pk["sustained"], int8_frac=tops / pk["sustained"],
-                   int8_peak_burst_tops=pk["burst"], int8_frac_of_burst=tops / pk["burst"])
+                   int8_peak_burst_tops=pk["burst"], int8_frac_of_burst=tops / pk["burst"],
+                   failures_rechecked_in_fp64=tm.get("chol_i8_failures_rechecked", 0.0),
+                   failures_overturned_by_fp64=tm.get("chol_i8_failures_overturned", 0.0))
     else:
         out["path"] = "FP64 DMMA (chol_dataflow_kernel)"
     return out

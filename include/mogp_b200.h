@@ -157,7 +157,9 @@ int mogp_chol_schedule(int32_t ticket, int32_t n_block_rows, int32_t n_outputs, 
  * out[11..15] = int8 path of the predict TRSM (inside predict_trsm): slicing L into planes (ms), the FP64 solve of the
  *               sampled test points for the a-posteriori accuracy check (ms), the persistent integer TRSM kernel (ms), block
  *               rows solved by it, number of groups the check sent back to the FP64 kernel
- * out[16]     = factorisations whose history products ran on the int8 tensor cores (chol_i8_kernel) */
+ * out[16]     = factorisations whose history products ran on the int8 tensor cores (chol_i8_kernel)
+ * out[17..18] = of those, the ones that reported "not positive definite" and were therefore repeated on the FP64 kernel (its
+ *               verdict is the one returned), and how many of these the FP64 kernel then factorised successfully */
 int mogp_timings(mogp_handle* h, double* out, int32_t n, int32_t reset);
 
 /* NCCL plumbing (no reference equivalent: the reference is single-device, multioutputgp_gpu.hpp:183). */

@@ -118,7 +118,7 @@ constexpr int I8_DEFAULT_PLANES = 7;   // default of MOGP_TRSM_I8 (see mogp_crea
 // longer epilogue on that path (one n=4096 matrix: 2.64 ms FP64, 2.79 ms int8; four: 3.52 / 3.31 ms).  Work / chain ~ outputs x T^3 / T.
 constexpr int64_t CHOL_I8_MIN_WORK = 4096;
 enum { T_KMAT = 0, T_CHOL, T_SOLVE, T_KSTAR, T_TRSM, T_GRAD, T_NTRSM, T_NLAUNCH, T_FIT, T_PRED_HOST, T_PRED_D2H,
-       T_I8_PREP, T_I8_CHECK, T_I8_ROWS, T_I8_NROWS, T_I8_NFALLBACK, T_CHOL_I8_N, T_COUNT };
+       T_I8_PREP, T_I8_CHECK, T_I8_ROWS, T_I8_NROWS, T_I8_NFALLBACK, T_CHOL_I8_N, T_CHOL_I8_RECHECKED, T_CHOL_I8_OVERTURNED, T_COUNT };
 
 struct mogp_handle {
     int device = 0, n_sms = 148;
@@ -459,7 +459,7 @@ int mogp_is_fit(mogp_handle* h, int32_t idx, int32_t* out) {
 
 // enqueue kernel matrix + factorisation + solves for the outputs outs[0..count) on h->main (batched launches), with
 // the nugget currently stored in h->hyper[o][d+1]; info / (logdet, quad) land in the pinned mirrors.
-static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
+static int enqueue_attempt(mogp_handle* h, const int* outs, int count, bool allow_i8 = true) {
     const int64_t np = h->n_pad;
     const int T = (int)(np / NB);
     NvtxRange nvtx_range("mogp fit attempt: kmat + cholesky + solves");
@@ -482,7 +482,7 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
         // Many or large factorisations are bound by their O(n^3) history products: those run as exact integer GEMM on the
         // tcgen05 tensor cores (chol_i8_kernel, 8 signed 7-bit planes per operand), which also leaves the planes of L the predict
         // TRSM needs.  A few small ones are bound by the chain of diagonal tiles, which is FP64 either way: DMMA kernel.
-        bool ci8 = h->chol_i8 != 0 && T >= 2 && np <= 32768 && (h->chol_i8 == 1 || (int64_t)cnt * T * T >= CHOL_I8_MIN_WORK);
+        bool ci8 = allow_i8 && h->chol_i8 != 0 && T >= 2 && np <= 32768 && (h->chol_i8 == 1 || (int64_t)cnt * T * T >= CHOL_I8_MIN_WORK);
         if (ci8 && !h->Lq) {
             h->Lq = (int8_t*)pool_alloc(i8_lq_bytes(T, chol_i8_planes()) * (size_t)h->E, h->device);
             if (!h->Lq) {
@@ -525,8 +525,12 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
             set_error("Inf enountered in kernel distance computation");      // (sic) the reference's message, Kernel.py:483
             return MOGP_ERR_FPE;
         }
+        std::vector<int> recheck;
         if (ci8) {
-            for (int i = 0; i < cnt; i++) h->lq_valid[og[i]] = (h->h_info[og[i]] == 0) ? 1 : 0;   // the planes of L came with the factor
+            for (int i = 0; i < cnt; i++) {
+                h->lq_valid[og[i]] = (h->h_info[og[i]] == 0) ? 1 : 0;   // the planes of L came with the factor
+                if (h->h_info[og[i]] != 0) recheck.push_back(og[i]);
+            }
             h->timings[T_CHOL_I8_N] += cnt;
         }
         float ms = 0.f;
@@ -538,6 +542,17 @@ static int enqueue_attempt(mogp_handle* h, const int* outs, int count) {
         h->timings[T_SOLVE] += ms;
         cudaEventElapsedTime(&ms, h->ev_a, h->ev_d);
         h->timings[T_FIT] += ms;
+        if (!recheck.empty()) {
+            // A "not positive definite" verdict of the tcgen05 factorisation is never reported as such: the outputs concerned are
+            // assembled and factorised again by the FP64 kernel, whose verdict (and LAPACK-style info) stands.  Failures are rare
+            // and fail early, so this costs next to nothing; it makes every adaptive-nugget decision the FP64 kernel's, whatever
+            // the integer path does to a pivot that sits within rounding of zero.
+            int rc = enqueue_attempt(h, recheck.data(), (int)recheck.size(), false);
+            if (rc) return rc;
+            h->timings[T_CHOL_I8_RECHECKED] += (double)recheck.size();
+            for (int o : recheck)
+                if (h->h_info[o] == 0) h->timings[T_CHOL_I8_OVERTURNED] += 1.0;
+        }
     }
     return MOGP_OK;
 }

@@ -345,11 +345,11 @@ class Handle(object):
         return out
 
     def timings(self, reset=False):
-        out = np.zeros(17)
-        check(_lib.mogp_timings(self._h, dptr(out), 17, int(reset)))
+        out = np.zeros(19)
+        check(_lib.mogp_timings(self._h, dptr(out), 19, int(reset)))
         keys = ["kmat_ms", "chol_ms", "solve_ms", "kstar_ms", "trsm_ms", "grad_ms", "n_trsm", "n_launches", "fit_ms",
                 "predict_device_wall_ms", "predict_d2h_wall_ms", "i8_prep_ms", "i8_check_ms", "i8_rows_ms", "i8_block_rows",
-                "i8_fallbacks", "chol_i8_outputs"]
+                "i8_fallbacks", "chol_i8_outputs", "chol_i8_failures_rechecked", "chol_i8_failures_overturned"]
         return dict(zip(keys, out.tolist()))
 
 
