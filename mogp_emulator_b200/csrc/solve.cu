@@ -10,7 +10,9 @@
 // in shared memory (those are the only ones its share of the GEMV touches).  Per step the C partial sums land
 // in the owner CTA's shared memory through DSMEM (st.shared::cluster), one barrier.cluster publishes them, and
 // the owner applies the precomputed inverse of the diagonal block (Dinv, from the Cholesky panel kernel) -- no
-// scalar dependency chain.  Partials are summed in rank order: results are deterministic.
+// scalar dependency chain.  Partials are summed in rank order: results are deterministic.  The GEMV of step i+1 over
+// the blocks already known runs between the arrive and the wait of step i's barrier (look-ahead): only the product
+// with the newest block and the Dinv product are on the chain, and their operands are prefetched into L2 a step ahead.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -35,6 +37,16 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// the two 128 x 128 blocks the NEXT step has on its chain -- the product with the newest block of the solution and the inverse
+// of the next diagonal block -- are pulled into L2 one step ahead (they come from HBM otherwise: the factor of 32 outputs is
+// 4 GB); every thread touches two 128-byte lines of a block
+__device__ __forceinline__ void prefetch_block_l2(const double* blk, int64_t row_stride, int tid) {
+    const double* p = blk + (int64_t)(tid >> 2) * row_stride + (tid & 3) * 32;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 16));
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // store a double into the shared memory of CTA `rank` of this cluster at the address `local` has in this CTA
 __device__ __forceinline__ void dsmem_store(double* local, uint32_t rank, double v) {
     uint32_t remote;
@@ -88,61 +100,76 @@ solve_alpha_kernel(const SolveParams sp) {
     cluster_sync_all();   // all CTAs are running before the first remote store
 
     // ---- forward substitution:  z_i = Dinv_i (y_i - sum_{j<i} L_ij z_j) ----
-    for (int i = 0; i < T; i++) {
-        const int owner = i % C;
-        {
-            double s[8];
+    // Look-ahead: the part of row i's sum over the blocks j <= i-2 was computed during step i-1, between the arrive and the wait
+    // of that step's cluster barrier (while its owner applied Dinv); only the product with the newest block z_{i-1} -- held by the
+    // CTA that has just computed it -- is on the chain.  One cluster barrier per step; every value a CTA reads from its own
+    // shared memory was written by itself (each CTA owns its blocks of the solution), only the partial sums travel (DSMEM).
+    // Before, a step began with the whole GEMV over block row i (i / C blocks of 128 KB from HBM per CTA) and had two barriers:
+    // 12.5 us per step at n = 16384.
+    {
+        auto gemv_block = [&](double (&s)[8], int i, int j, int sl) {      // s += rows (8 per warp) of L_ij times block sl of v
+            const double* rowp = A + (int64_t)(i * NB + warp * 8) * ld + (int64_t)j * NB;
 #pragma unroll
-            for (int rr = 0; rr < 8; rr++) s[rr] = 0.0;
-            const double* rowp = A + (int64_t)(i * NB + warp * 8) * ld;
-            for (int j = me, sl = 0; j < i; j += C, sl++) {
+            for (int half = 0; half < 2; half++) {
+                const int cl = half * 64 + lane * 2;
+                const double2 vv = *reinterpret_cast<const double2*>(v + sl * NB + cl);
+                const double* p = rowp + cl;
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const int cl = half * 64 + lane * 2;
-                    const double2 vv = *reinterpret_cast<const double2*>(v + sl * NB + cl);
-                    const double* p = rowp + (int64_t)j * NB + cl;
+                for (int rr = 0; rr < 8; rr++) {
+                    const double2 l = *reinterpret_cast<const double2*>(p + (int64_t)rr * ld);
+                    s[rr] = fma(l.x, vv.x, s[rr]);
+                    s[rr] = fma(l.y, vv.y, s[rr]);
+                }
+            }
+        };
+        double pre[8];
 #pragma unroll
-                    for (int rr = 0; rr < 8; rr++) {
-                        const double2 l = *reinterpret_cast<const double2*>(p + (int64_t)rr * ld);
-                        s[rr] = fma(l.x, vv.x, s[rr]);
-                        s[rr] = fma(l.y, vv.y, s[rr]);
+        for (int rr = 0; rr < 8; rr++) pre[rr] = 0.0;
+        for (int i = 0; i < T; i++) {
+            const int owner = i % C;
+            if (i + 1 < T && C >= 8) {     // (few, wide clusters: latency-bound; with many narrow ones the prefetches only add traffic)
+                if (me == owner) prefetch_block_l2(A + (int64_t)(i + 1) * NB * ld + (int64_t)i * NB, ld, tid);      // L_{i+1,i}
+                if (me == (i + 1) % C) prefetch_block_l2(Dinv + (int64_t)(i + 1) * NB * NB, NB, tid);
+            }
+            if (i > 0 && me == (i - 1) % C) gemv_block(pre, i, i - 1, (i - 1) / C);   // the newest block (CTA-uniform branch)
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double t = warp_sum(pre[rr]);
+                if (lane == 0) dsmem_store(slots + me * NB + warp * 8 + rr, (uint32_t)owner, t);
+                pre[rr] = 0.0;
+            }
+            cluster_arrive();
+            if (i + 1 < T)
+                for (int j = me, sl = 0; j <= i - 1; j += C, sl++) gemv_block(pre, i + 1, j, sl);
+            cluster_wait();
+            if (me == owner) {   // CTA-uniform
+                const int sl = i / C;
+                if (tid < NB) {
+                    double t = 0.0;
+                    for (int c = 0; c < C; c++) t += slots[c * NB + tid];
+                    acc[tid] = v[sl * NB + tid] - t;
+                }
+                __syncthreads();
+                const double* Db = Dinv + (int64_t)i * NB * NB;
+                const double2 a0 = *reinterpret_cast<const double2*>(acc + lane * 4);
+                const double2 a1 = *reinterpret_cast<const double2*>(acc + lane * 4 + 2);
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {
+                    const double* dr = Db + (int64_t)(warp * 8 + rr) * NB + lane * 4;
+                    const double2 d0 = *reinterpret_cast<const double2*>(dr);
+                    const double2 d1 = *reinterpret_cast<const double2*>(dr + 2);
+                    double t = d0.x * a0.x;
+                    t = fma(d0.y, a0.y, t);
+                    t = fma(d1.x, a1.x, t);
+                    t = fma(d1.y, a1.y, t);
+                    t = warp_sum(t);
+                    if (lane == 0) {
+                        v[sl * NB + warp * 8 + rr] = t;
+                        z_out[(int64_t)i * NB + warp * 8 + rr] = t;
                     }
                 }
+                __syncthreads();
             }
-#pragma unroll
-            for (int rr = 0; rr < 8; rr++) {
-                const double t = warp_sum(s[rr]);
-                if (lane == 0) dsmem_store(slots + me * NB + warp * 8 + rr, (uint32_t)owner, t);
-            }
-        }
-        cluster_sync_all();
-        if (me == owner) {   // CTA-uniform
-            const int sl = i / C;
-            if (tid < NB) {
-                double t = 0.0;
-                for (int c = 0; c < C; c++) t += slots[c * NB + tid];
-                acc[tid] = v[sl * NB + tid] - t;
-            }
-            __syncthreads();
-            const double* Db = Dinv + (int64_t)i * NB * NB;
-            const double2 a0 = *reinterpret_cast<const double2*>(acc + lane * 4);
-            const double2 a1 = *reinterpret_cast<const double2*>(acc + lane * 4 + 2);
-#pragma unroll
-            for (int rr = 0; rr < 8; rr++) {
-                const double* dr = Db + (int64_t)(warp * 8 + rr) * NB + lane * 4;
-                const double2 d0 = *reinterpret_cast<const double2*>(dr);
-                const double2 d1 = *reinterpret_cast<const double2*>(dr + 2);
-                double t = d0.x * a0.x;
-                t = fma(d0.y, a0.y, t);
-                t = fma(d1.x, a1.x, t);
-                t = fma(d1.y, a1.y, t);
-                t = warp_sum(t);
-                if (lane == 0) {
-                    v[sl * NB + warp * 8 + rr] = t;
-                    z_out[(int64_t)i * NB + warp * 8 + rr] = t;
-                }
-            }
-            __syncthreads();
         }
     }
 
@@ -167,55 +194,69 @@ solve_alpha_kernel(const SolveParams sp) {
     }
 
     // ---- backward substitution:  alpha_i = Dinv_i^T (z_i - sum_{j>i} L_ji^T alpha_j) ----
+    // The same look-ahead, mirrored: block column i over the blocks j >= i+2 during step i+1, the newest block alpha_{i+1} on
+    // the chain.
     const int c = tid & 127, q4 = tid >> 7;
-    for (int i = T - 1; i >= 0; i--) {
-        const int owner = i % C;
-        {
+    {
+        auto colsum_block = [&](int i, int j) -> double {      // sum over this thread's rows r of L_ji[r][c] alpha_j[r]
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            const double* colp = A + (int64_t)i * NB + c;
-            // own row blocks j > i, j = me (mod C)
-            int j = i + 1 + ((me - (i + 1)) % C + C) % C;
-            for (; j < T; j += C) {
-                const double* vb = v + (j / C) * NB;
-                const double* lp = colp + (int64_t)j * NB * ld;
+            const double* vb = v + (j / C) * NB;
+            const double* lp = A + (int64_t)i * NB + c + (int64_t)j * NB * ld;
 #pragma unroll
-                for (int r = q4; r < NB; r += 16) {
-                    s0 = fma(lp[(int64_t)r * ld], vb[r], s0);
-                    s1 = fma(lp[(int64_t)(r + 4) * ld], vb[r + 4], s1);
-                    s2 = fma(lp[(int64_t)(r + 8) * ld], vb[r + 8], s2);
-                    s3 = fma(lp[(int64_t)(r + 12) * ld], vb[r + 12], s3);
+            for (int r = q4; r < NB; r += 16) {
+                s0 = fma(lp[(int64_t)r * ld], vb[r], s0);
+                s1 = fma(lp[(int64_t)(r + 4) * ld], vb[r + 4], s1);
+                s2 = fma(lp[(int64_t)(r + 8) * ld], vb[r + 8], s2);
+                s3 = fma(lp[(int64_t)(r + 12) * ld], vb[r + 12], s3);
+            }
+            return (s0 + s1) + (s2 + s3);
+        };
+        double preb = 0.0;
+        for (int i = T - 1; i >= 0; i--) {
+            const int owner = i % C;
+            if (i >= 1 && C >= 8) {
+                if (me == owner) prefetch_block_l2(A + (int64_t)i * NB * ld + (int64_t)(i - 1) * NB, ld, tid);      // L_{i,i-1}
+                if (me == (i - 1) % C) prefetch_block_l2(Dinv + (int64_t)(i - 1) * NB * NB, NB, tid);
+            }
+            if (i + 1 < T && me == (i + 1) % C) preb += colsum_block(i, i + 1);   // the newest block (CTA-uniform branch)
+            red[q4 * NB + c] = preb;
+            preb = 0.0;
+            __syncthreads();
+            if (tid < NB)
+                dsmem_store(slots + me * NB + tid, (uint32_t)owner,
+                            (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]));
+            cluster_arrive();
+            if (i >= 1) {
+                // own row blocks j >= i + 1, j = me (mod C), of block column i - 1
+                int j = i + 1 + ((me - (i + 1)) % C + C) % C;
+                for (; j < T; j += C) preb += colsum_block(i - 1, j);
+            }
+            cluster_wait();
+            if (me == owner) {
+                const int sl = i / C;
+                __syncthreads();       // (every thread of this CTA is past its read of red above)
+                if (tid < NB) {
+                    double t = 0.0;
+                    for (int cc = 0; cc < C; cc++) t += slots[cc * NB + tid];
+                    acc[tid] = v[sl * NB + tid] - t;
+                }
+                __syncthreads();
+                {
+                    const double* Db = Dinv + (int64_t)i * NB * NB;
+                    double s = 0.0;
+                    for (int r = q4; r < NB; r += 4)
+                        if (r >= c) s = fma(Db[r * NB + c], acc[r], s);
+                    red[q4 * NB + c] = s;
+                }
+                __syncthreads();
+                if (tid < NB) {
+                    const double a = (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]);
+                    v[sl * NB + tid] = a;
+                    alpha_out[(int64_t)i * NB + tid] = a;
                 }
             }
-            red[q4 * NB + c] = (s0 + s1) + (s2 + s3);
+            __syncthreads();   // red is rewritten by the next step; alpha_i is in place for the owner's next product
         }
-        __syncthreads();
-        if (tid < NB)
-            dsmem_store(slots + me * NB + tid, (uint32_t)owner,
-                        (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]));
-        cluster_sync_all();
-        if (me == owner) {
-            const int sl = i / C;
-            if (tid < NB) {
-                double t = 0.0;
-                for (int cc = 0; cc < C; cc++) t += slots[cc * NB + tid];
-                acc[tid] = v[sl * NB + tid] - t;
-            }
-            __syncthreads();
-            {
-                const double* Db = Dinv + (int64_t)i * NB * NB;
-                double s = 0.0;
-                for (int r = q4; r < NB; r += 4)
-                    if (r >= c) s = fma(Db[r * NB + c], acc[r], s);
-                red[q4 * NB + c] = s;
-            }
-            __syncthreads();
-            if (tid < NB) {
-                const double a = (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]);
-                v[sl * NB + tid] = a;
-                alpha_out[(int64_t)i * NB + tid] = a;
-            }
-        }
-        __syncthreads();   // red is rewritten by the next step
     }
 }
 
