@@ -773,6 +773,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                 double2* dst = reinterpret_cast<double2*>(p.A + (wrow + r) * p.n_pad + (int64_t)j * NB + k8 * 8);
                 dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
             }
+            fence_proxy_async();       // the warp's generic-proxy writes into the staging tile -> the TMA load that overwrites it
             __syncwarp();
             if (lane == 0) mbar_arrive(vs_free);
             seq++;
@@ -786,6 +787,7 @@ chol_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
                 if (lane == 0) mbar_arrive(&empty[ps.stage]);
                 ps.advance();
             }
+            fence_proxy_async();       // the warp's generic-proxy writes into the staging tile -> the TMA load that overwrites it
             __syncwarp();
             if (lane == 0) mbar_arrive(vs_free);
             seq++;
@@ -1156,6 +1158,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
                 }
                 __threadfence();
+                fence_proxy_async();       // generic-proxy writes into the T buffer -> the TMA load of the next tile that overwrites it
                 named_bar_sync(1, I8_NCW * 32);
                 if (tid == 0) {
                     mbar_arrive(ts_free);

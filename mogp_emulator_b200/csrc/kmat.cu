@@ -273,6 +273,7 @@ kmat_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
                 }
             }
         }
+        fence_proxy_async();         // the tiles were scaled in place through the generic proxy; a TMA load overwrites them next
         __syncthreads();             // this stage (and sw_s / al_s) may be overwritten
     }
 }

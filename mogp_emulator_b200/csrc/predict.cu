@@ -258,6 +258,7 @@ predict_trsm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_consta
             if (lane == 0) mbar_arrive(&empty[ps.stage]);
             ps.advance();
         }
+        fence_proxy_async();           // the warp's generic-proxy writes into the staging tile -> the TMA load that overwrites it
         __syncwarp();
         if (lane == 0) mbar_arrive(vs_free);
         seq++;

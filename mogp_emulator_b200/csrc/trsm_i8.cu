@@ -464,8 +464,9 @@ i8_trsm_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ 
                         *reinterpret_cast<uint32_t*>(dst + tt * I8_BPLANE) = x;
                     }
                 }
-                fence_proxy_async();              // generic-proxy writes of the image -> the bulk store's async-proxy read
             }
+            fence_proxy_async();                  // generic-proxy writes into the T buffer / plane image -> the bulk store's async-proxy
+                                                  // read and the TMA load of the next tile that overwrites the buffer
             named_bar_sync(1, I8_NCW * 32);
             if (tid == 0) I8_STAMP(nq, 11);
             if (tid == 0) {
