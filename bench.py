@@ -432,6 +432,7 @@ def cholesky_report(libmogp, device, tm, n_outputs, n, steps, peak_dmma):
                         "triangular solves against inv(L_jj) and recombination in FP64)",
                    int8_tops=tops, int8_peak_tops=pk["sustained"], int8_frac=tops / pk["sustained"],
                    int8_peak_burst_tops=pk["burst"], int8_frac_of_burst=tops / pk["burst"],
+                   dram_bytes_per_launch_ncu=ncu_traffic(("c4" if n_outputs == 1 and n == 16384 else "c3" if n == 4096 and n_outputs == 32 else "-") + "-chol-i8", 1),
                    failures_rechecked_in_fp64=tm.get("chol_i8_failures_rechecked", 0.0),
                    failures_overturned_by_fp64=tm.get("chol_i8_failures_overturned", 0.0))
     else:
