@@ -100,3 +100,20 @@ def test_cholesky_on_int8_planes_is_fp64_equivalent(n, d, theta_corr, nugget, ke
     if theta_corr < 0:
         L7 = emu.cholesky_i8(K, 1.0, nugget, S=7)
         assert np.abs(L7 @ L7.T - K).max() > 4.0 * back
+
+
+def test_leading_seven_of_eight_digits_are_as_good_as_seven_rounded_digits():
+    """The tcgen05 Cholesky stores 8 digit planes of L; the predict TRSM reads the leading 7 (csrc/i8_common.cuh, I8_LP).
+    Cutting a signed-digit expansion after 7 digits leaves at most half a unit of digit 7 plus the tail: the bound of a direct
+    rounding to 7 digits (2^-50) up to a factor 1 + 2^-7, and every digit stays in int8 range with scaled entries up to 0.99."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-0.99, 0.99, size=20000), [0.99, -0.99, 0.5, -0.5, 2.0 ** -30]])
+    d8 = emu.digits(x, 8)
+    d7 = emu.digits(x, 7)
+    cut = sum(d8[t] * 2.0 ** (-7 * (t + 1)) for t in range(7))
+    rounded = sum(d7[t] * 2.0 ** (-7 * (t + 1)) for t in range(7))
+    assert np.max(np.abs(x - rounded)) <= 2.0 ** -50
+    assert np.max(np.abs(x - cut)) <= 2.0 ** -50 * (1.0 + 2.0 ** -6)
+    assert max(np.max(np.abs(p)) for p in d8) <= 127 and max(np.max(np.abs(p)) for p in d8[1:]) <= 64
+    full = sum(d8[t] * 2.0 ** (-7 * (t + 1)) for t in range(8))
+    assert np.max(np.abs(x - full)) <= 2.0 ** -57
